@@ -1,0 +1,665 @@
+// tcgen05 tensor-core contraction kernel for sm_100a: plain / batched GEMM, NHWC implicit-GEMM convolution
+// (forward and data-gradient) and convolution weight-gradient, all through one warp-specialised pipeline:
+//
+//   warp 0 (one lane)  TMA producer: 4-D tiled cp.async.bulk.tensor loads, SWIZZLE_128B, zero-filled halo
+//   warp 1 (one lane)  tcgen05.mma issuer (128 x BN x 16 bf16 -> fp32 in TMEM), tcgen05.commit -> mbarriers
+//   warps 2-5          epilogue: tcgen05.ld TMEM -> registers -> bias/residual/activation/mask -> global
+//
+// Replaces the cuDNN / cuBLAS calls behind every nn.Conv2d / nn.Linear of the reference hot path
+// (backbone.py:72, detr_roi_head.py:79-84, transformer.py:153-160,218-231, vilbert.py:748-761,847-898,
+//  gpv.py:140,145,162, answer_head.py:31-33) and their autograd backward.
+#include <mutex>
+#include <string.h>
+#include <unordered_map>
+#include <string>
+
+#include "../../include/gpvb200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace gpv {
+
+struct KParams {
+  int mode, M, N, a_mn, b_mn, bk, k_iters, splits, nstages, b_batched;
+  int kc_per_tap;
+  int Ho, Wo, th, tw, tiles_h, tiles_w, stride;
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_w[9];
+  int OH, OW, os, ooh, oow;
+  int act, aux_mode, d_fp32, d_atomic, vec_ok;
+  float alpha;
+  void* D;
+  bf16* D2;
+  const float* bias;
+  const float* rowscale;
+  const bf16* residual;
+  const bf16* aux;
+  long long ldd, ldr, ldaux, d_batch_stride;
+};
+
+constexpr int kThreads = 192;
+constexpr int BM = 128;
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile decode -------------------------------------------------------------------------------
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int nt = blockIdx.x % n_tiles, mt = blockIdx.x / n_tiles;
+  const int n0 = nt * BN, m0 = mt * BM;
+  const int bz = blockIdx.y;
+  const int per = (p.k_iters + p.splits - 1) / p.splits;
+  const int it0 = blockIdx.z * per;
+  const int it1 = min(it0 + per, p.k_iters);
+  if (it0 >= it1) return;  // uniform over the CTA; nothing allocated yet
+
+  int img = 0, ho0 = 0, wo0 = 0;
+  if (p.mode == 1) {
+    const int tpi = p.tiles_h * p.tiles_w;
+    img = mt / tpi;
+    const int r = mt % tpi;
+    ho0 = (r / p.tiles_w) * p.th;
+    wo0 = (r % p.tiles_w) * p.tw;
+  }
+
+  // ---- shared memory carve-up ----------------------------------------------------------------------
+  const int rowsA = (p.mode == 1) ? p.th * p.tw : BM;
+  const uint32_t a_bytes = p.a_mn ? 2u * p.bk * 128u : 128u * 128u;  // reserved per stage
+  const uint32_t b_bytes = p.b_mn ? (uint32_t)(BN / 64) * p.bk * 128u : (uint32_t)BN * 128u;
+  const uint32_t a_tx = p.a_mn ? a_bytes : (uint32_t)rowsA * 128u;    // bytes TMA actually writes
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int S = p.nstages;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)S * stage_bytes);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* accum_bar = empty_bar + S;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      for (int it = it0; it < it1; ++it) {
+        const int li = it - it0;
+        const int s = li % S;
+        const uint32_t ph = (uint32_t)(li / S) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[s], a_tx + b_bytes);
+        if (p.mode == 0) {
+          const int k0 = it * p.bk;
+          const int bzB = p.b_batched ? bz : 0;
+          if (!p.a_mn) {
+            tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, bz, 0);
+          } else {
+            tma_load_4d(sa, &tmA, &full_bar[s], m0, k0, bz, 0);
+            tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, k0, bz, 0);
+          }
+          if (!p.b_mn) {
+            tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, bzB, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, k0, bzB, 0);
+          }
+        } else if (p.mode == 1) {
+          const int tap = it / p.kc_per_tap, kc = it % p.kc_per_tap;
+          tma_load_4d(sa, &tmA, &full_bar[s], kc * 64, wo0 * p.stride + p.tap_dw[tap], ho0 * p.stride + p.tap_dh[tap], img);
+          if (!p.b_mn) {
+            tma_load_4d(sb, &tmB, &full_bar[s], kc * 64, n0, p.tap_w[tap], 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, kc * 64, p.tap_w[tap], 0);
+          }
+        } else {
+          const int tpi = p.tiles_h * p.tiles_w;
+          const int im = it / tpi, r = it % tpi;
+          const int h0 = (r / p.tiles_w) * p.th, w0 = (r % p.tiles_w) * p.tw;
+          tma_load_4d(sa, &tmA, &full_bar[s], m0, w0, h0, im);
+          tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, w0, h0, im);
+          const int wi = w0 * p.stride + p.tap_dw[bz], hi = h0 * p.stride + p.tap_dh[bz];
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, wi, hi, im);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    const uint32_t a_lbo = p.a_mn ? (uint32_t)p.bk * 128u : 0u;
+    const uint32_t b_lbo = p.b_mn ? (uint32_t)p.bk * 128u : 0u;
+    const uint32_t a_kstep = p.a_mn ? 2048u : 32u;  // bytes per UMMA_K = 16 step
+    const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+    const int ksteps = p.bk / 16;
+    for (int it = it0; it < it1; ++it) {
+      const int li = it - it0;
+      const int s = li % S;
+      const uint32_t ph = (uint32_t)(li / S) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_sdesc_sw128(sa + k * a_kstep, a_lbo, 1024u);
+          const uint64_t bd = make_sdesc_sw128(sb + k * b_kstep, b_lbo, 1024u);
+          umma_f16(tmem_base, ad, bd, idesc, (li > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);               // frees the smem stage once these MMAs retire
+        if (it == it1 - 1) umma_commit(accum_bar); // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+
+    bool row_ok;
+    long long row_off;  // element offset of (row, col 0) in D-indexed tensors, excluding the ld factor
+    long long pix = 0;
+    if (p.mode == 1) {
+      const int dy = r / p.tw, dx = r % p.tw;
+      const int ho = ho0 + dy, wo = wo0 + dx;
+      row_ok = (r < p.th * p.tw) && ho < p.Ho && wo < p.Wo;
+      pix = ((long long)img * p.OH + (ho * p.os + p.ooh)) * p.OW + (wo * p.os + p.oow);
+    } else {
+      row_ok = (m0 + r) < p.M;
+      pix = m0 + r;
+    }
+    row_off = (long long)bz * p.d_batch_stride;  // mode 0: batch, mode 2: tap, mode 1: bz == 0
+    const float rs = (p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[m0 + r] : 1.0f;
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (n0 + c0 >= p.N) break;  // warp-uniform
+      uint32_t acc[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha * rs;
+      const int nb = n0 + c0;
+      const int nvalid = min(16, p.N - nb);
+      const bool vec_ok = p.vec_ok && nvalid == 16;
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
+      }
+      if (p.residual != nullptr) {
+        const bf16* rp = p.residual + row_off + pix * p.ldr + nb;
+        if (vec_ok) {
+          const uint4 t0 = *reinterpret_cast<const uint4*>(rp);
+          const uint4 t1 = *reinterpret_cast<const uint4*>(rp + 8);
+          const uint32_t w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            v[2 * j] += f.x;
+            v[2 * j + 1] += f.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+        }
+      }
+      if (p.D2 != nullptr) {
+        bf16* dp = p.D2 + row_off + pix * p.ldd + nb;
+        if (vec_ok) {
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          *reinterpret_cast<uint4*>(dp) = o0;
+          *reinterpret_cast<uint4*>(dp + 8) = o1;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+        }
+      }
+      if (p.act == GPVB200_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+      } else if (p.act == GPVB200_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+      } else if (p.act == GPVB200_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 1.0f / (1.0f + __expf(-v[j]));
+      }
+      if (p.aux_mode != GPVB200_AUX_NONE) {
+        const bf16* ap = p.aux + row_off + pix * p.ldaux + nb;
+        float a[16];
+        if (vec_ok) {
+          const uint4 t0 = *reinterpret_cast<const uint4*>(ap);
+          const uint4 t1 = *reinterpret_cast<const uint4*>(ap + 8);
+          const uint32_t w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            a[2 * j] = f.x;
+            a[2 * j + 1] = f.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = (j < nvalid) ? __bfloat162float(ap[j]) : 0.0f;
+        }
+        if (p.aux_mode == GPVB200_AUX_RELU_MASK) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_grad(a[j]);
+        }
+      }
+      if (p.d_fp32) {
+        float* dp = reinterpret_cast<float*>(p.D) + row_off + pix * p.ldd + nb;
+        if (p.d_atomic) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) atomicAdd(dp + j, v[j]);
+        } else if (vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(dp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) dp[j] = v[j];
+        }
+      } else {
+        bf16* dp = reinterpret_cast<bf16*>(p.D) + row_off + pix * p.ldd + nb;
+        if (vec_ok) {
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          *reinterpret_cast<uint4*>(dp) = o0;
+          *reinterpret_cast<uint4*>(dp + 8) = o1;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+        }
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+struct MapKey {
+  uint64_t v[13];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 13; ++i) {
+      h ^= k.v[i];
+      h *= 1099511628211ull;
+    }
+    return (size_t)h;
+  }
+};
+
+// 4-D bf16 tensor map, SWIZZLE_128B, zero OOB fill. dims/strides innermost first; strides in elements for dims 1..3.
+static int make_map(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_el[3],
+                    const uint32_t box[4], const uint32_t estr[4]) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key;
+  key.v[0] = (uint64_t)(uintptr_t)ptr;
+  for (int i = 0; i < 4; ++i) key.v[1 + i] = dims[i];
+  for (int i = 0; i < 3; ++i) key.v[5 + i] = strides_el[i];
+  for (int i = 0; i < 4; ++i) key.v[8 + i] = ((uint64_t)box[i] << 32) | estr[i];
+  key.v[12] = 0;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return GPV_OK;
+    }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable");
+    return GPV_ERR_CUDA;
+  }
+  if (((uintptr_t)ptr & 15) != 0) {
+    set_last_error("tensor map base pointer %p not 16-byte aligned", ptr);
+    return GPV_ERR_ARG;
+  }
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < 4; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = estr[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    gstr[i] = strides_el[i] * 2;
+    if (gstr[i] % 16 != 0) {
+      set_last_error("tensor map stride %llu bytes (dim %d) not a multiple of 16", (unsigned long long)gstr[i], i + 1);
+      return GPV_ERR_ARG;
+    }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                   (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
+    return GPV_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return GPV_OK;
+}
+
+// Choose a th x tw pixel tile with th*tw <= limit (or == exact when `exact`), maximising useful rows.
+static void pick_tile(int H, int W, int limit, bool exact_mult16, int* th_out, int* tw_out) {
+  double best = -1.0;
+  int bth = 1, btw = 1;
+  for (int tw = 1; tw <= W && tw <= limit; ++tw) {
+    for (int th = 1; th <= H && th * tw <= limit; ++th) {
+      const int rows = th * tw;
+      if (exact_mult16 && (rows % 16 != 0)) continue;
+      const long long tiles = (long long)((H + th - 1) / th) * ((W + tw - 1) / tw);
+      // cost of a tile is a full MMA pass (limit rows) for mode 1, `rows` of contraction for mode 2
+      const double work = exact_mult16 ? (double)tiles * rows + tiles * 8.0 : (double)tiles * limit;
+      const double eff = (double)H * W / work;
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > btw)) {
+        best = eff;
+        bth = th;
+        btw = tw;
+      }
+    }
+  }
+  *th_out = bth;
+  *tw_out = btw;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return GPV_ERR_CUDA;
+    }
+    configured = true;
+  }
+  umma_gemm_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mb, kp);
+  return check_launch("umma_gemm_kernel");
+}
+
+}  // namespace gpv
+
+using namespace gpv;
+
+extern "C" size_t gpvb200_gemm_desc_size(void) { return sizeof(gpvb200_gemm_desc); }
+
+extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(d != nullptr, "gemm: null descriptor");
+  GPV_REQUIRE(d->mode >= 0 && d->mode <= 2, "gemm: bad mode %d", d->mode);
+  GPV_REQUIRE(d->A && d->B && d->D, "gemm: null operand");
+  GPV_REQUIRE(d->N > 0 && d->K >= 0, "gemm: bad N/K");
+  const int splits = d->splits > 1 ? d->splits : 1;
+  GPV_REQUIRE(splits == 1 || (d->d_atomic && d->d_fp32), "gemm: split-K needs fp32 atomic output");
+  GPV_REQUIRE(!d->d_atomic || d->d_fp32, "gemm: atomic output must be fp32");
+  if (d->aux_mode != GPVB200_AUX_NONE) GPV_REQUIRE(d->aux != nullptr, "gemm: aux_mode set without aux");
+
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.mode = d->mode;
+  kp.M = d->M;
+  kp.N = d->N;
+  kp.a_mn = d->a_mn ? 1 : 0;
+  kp.b_mn = d->b_mn ? 1 : 0;
+  kp.splits = splits;
+  kp.act = d->act;
+  kp.aux_mode = d->aux_mode;
+  kp.d_fp32 = d->d_fp32;
+  kp.d_atomic = d->d_atomic;
+  kp.alpha = d->alpha;
+  kp.D = d->D;
+  kp.D2 = (bf16*)d->D2;
+  kp.bias = d->bias;
+  kp.rowscale = d->rowscale;
+  kp.residual = (const bf16*)d->residual;
+  kp.aux = (const bf16*)d->aux;
+  kp.ldd = d->ldd;
+  kp.ldr = d->residual ? d->ldr : 8;
+  kp.ldaux = d->aux ? d->ldaux : 8;
+  kp.d_batch_stride = d->d_batch_stride;
+  {
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    kp.vec_ok = ((kp.ldd & 7) == 0) && ((kp.ldr & 7) == 0) && ((kp.ldaux & 7) == 0) && ((kp.d_batch_stride & 7) == 0) &&
+                al16(d->D) && al16(d->D2) && al16(d->residual) && al16(d->aux);
+  }
+  kp.stride = d->stride > 0 ? d->stride : 1;
+  kp.os = d->out_stride > 0 ? d->out_stride : 1;
+  kp.ooh = d->out_off_h;
+  kp.oow = d->out_off_w;
+  kp.OH = d->OH;
+  kp.OW = d->OW;
+  kp.Ho = d->Ho;
+  kp.Wo = d->Wo;
+  kp.ntaps = d->ntaps;
+  for (int i = 0; i < 9; ++i) {
+    kp.tap_dh[i] = d->tap_dh[i];
+    kp.tap_dw[i] = d->tap_dw[i];
+    kp.tap_w[i] = d->tap_w[i];
+  }
+
+  // ---- tile width ------------------------------------------------------------------------------------
+  int BN;
+  if (d->N > 128 && !(d->mode == 2)) BN = 256;
+  else if (d->N > 64) BN = 128;
+  else BN = 64;
+  if (d->mode == 2 && d->N > 64) BN = 128;
+
+  CUtensorMap ma, mb;
+  dim3 grid;
+  const uint32_t one4[4] = {1, 1, 1, 1};
+
+  if (d->mode == 0) {
+    GPV_REQUIRE(d->M > 0 && d->K > 0 && d->batch > 0, "gemm: bad plain shape");
+    kp.bk = 64;
+    kp.k_iters = (d->K + 63) / 64;
+    kp.b_batched = d->b_batch_stride != 0;
+    {
+      uint64_t dims[4], str[3];
+      uint32_t box[4];
+      if (!kp.a_mn) {
+        dims[0] = d->K; dims[1] = d->M; box[0] = 64; box[1] = 128;
+      } else {
+        dims[0] = d->M; dims[1] = d->K; box[0] = 64; box[1] = 64;
+      }
+      dims[2] = d->batch; dims[3] = 1; box[2] = 1; box[3] = 1;
+      str[0] = d->lda;
+      str[1] = d->batch > 1 ? (uint64_t)d->a_batch_stride : (uint64_t)d->lda * dims[1];
+      str[2] = str[1] * dims[2];
+      rc = make_map(&ma, d->A, dims, str, box, one4);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[4], str[3];
+      uint32_t box[4];
+      if (!kp.b_mn) {
+        dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = BN;
+      } else {
+        dims[0] = d->N; dims[1] = d->K; box[0] = 64; box[1] = 64;
+      }
+      const int bb = kp.b_batched ? d->batch : 1;
+      dims[2] = bb; dims[3] = 1; box[2] = 1; box[3] = 1;
+      str[0] = d->ldb;
+      str[1] = bb > 1 ? (uint64_t)d->b_batch_stride : (uint64_t)d->ldb * dims[1];
+      str[2] = str[1] * dims[2];
+      rc = make_map(&mb, d->B, dims, str, box, one4);
+      if (rc) return rc;
+    }
+    const int mt = (d->M + BM - 1) / BM, ntl = (d->N + BN - 1) / BN;
+    grid = dim3(mt * ntl, d->batch, splits);
+  } else if (d->mode == 1) {
+    GPV_REQUIRE(d->n_img > 0 && d->Hi > 0 && d->Wi > 0 && d->Ho > 0 && d->Wo > 0, "gemm: bad conv geometry");
+    GPV_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "gemm: ntaps must be 1..9");
+    GPV_REQUIRE(!kp.a_mn, "gemm: conv A must be channel-contiguous");
+    GPV_REQUIRE(kp.stride <= 2, "gemm: conv stride > 2 unsupported");
+    kp.bk = 64;
+    kp.kc_per_tap = (d->K + 63) / 64;
+    kp.k_iters = d->ntaps * kp.kc_per_tap;
+    pick_tile(d->Ho, d->Wo, 128 / 1, false, &kp.th, &kp.tw);
+    if (kp.tw * kp.stride > 256 || kp.th * kp.stride > 256) {
+      set_last_error("gemm: conv tile exceeds TMA box limit");
+      return GPV_ERR_ARG;
+    }
+    kp.tiles_h = (d->Ho + kp.th - 1) / kp.th;
+    kp.tiles_w = (d->Wo + kp.tw - 1) / kp.tw;
+    {
+      uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->Wi, (uint64_t)d->Hi, (uint64_t)d->n_img};
+      uint64_t str[3] = {(uint64_t)d->lda, (uint64_t)d->lda * d->Wi, (uint64_t)d->lda * d->Wi * d->Hi};
+      uint32_t box[4] = {64, (uint32_t)(kp.tw * kp.stride), (uint32_t)(kp.th * kp.stride), 1};
+      uint32_t es[4] = {1, (uint32_t)kp.stride, (uint32_t)kp.stride, 1};
+      rc = make_map(&ma, d->A, dims, str, box, es);
+      if (rc) return rc;
+    }
+    {
+      int ntw = 0;
+      for (int i = 0; i < d->ntaps; ++i) ntw = d->tap_w[i] + 1 > ntw ? d->tap_w[i] + 1 : ntw;
+      uint64_t dims[4], str[3];
+      uint32_t box[4];
+      if (!kp.b_mn) {
+        dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = BN;
+      } else {
+        dims[0] = d->N; dims[1] = d->K; box[0] = 64; box[1] = 64;
+      }
+      dims[2] = ntw; dims[3] = 1; box[2] = 1; box[3] = 1;
+      str[0] = d->ldb;
+      str[1] = d->b_batch_stride ? (uint64_t)d->b_batch_stride : (uint64_t)d->ldb * dims[1];
+      str[2] = str[1] * dims[2];
+      rc = make_map(&mb, d->B, dims, str, box, one4);
+      if (rc) return rc;
+    }
+    if (kp.OH == 0) { kp.OH = d->Ho; kp.OW = d->Wo; }
+    const int ntl = (d->N + BN - 1) / BN;
+    grid = dim3(d->n_img * kp.tiles_h * kp.tiles_w * ntl, 1, splits);
+  } else {
+    GPV_REQUIRE(d->n_img > 0 && d->Hi > 0 && d->Wi > 0 && d->Ho > 0 && d->Wo > 0, "gemm: bad wgrad geometry");
+    GPV_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "gemm: ntaps must be 1..9");
+    GPV_REQUIRE(d->d_atomic && d->d_fp32, "gemm: wgrad output must be fp32 atomic");
+    GPV_REQUIRE(d->M > 0, "gemm: bad wgrad M");
+    kp.a_mn = 1;
+    kp.b_mn = 1;
+    pick_tile(d->Ho, d->Wo, 96, true, &kp.th, &kp.tw);
+    kp.bk = kp.th * kp.tw;
+    GPV_REQUIRE(kp.bk % 16 == 0 && kp.bk >= 16, "gemm: no wgrad pixel tile for %dx%d", d->Ho, d->Wo);
+    kp.tiles_h = (d->Ho + kp.th - 1) / kp.th;
+    kp.tiles_w = (d->Wo + kp.tw - 1) / kp.tw;
+    kp.k_iters = d->n_img * kp.tiles_h * kp.tiles_w;
+    {
+      uint64_t dims[4] = {(uint64_t)d->M, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->n_img};
+      uint64_t str[3] = {(uint64_t)d->lda, (uint64_t)d->lda * d->Wo, (uint64_t)d->lda * d->Wo * d->Ho};
+      uint32_t box[4] = {64, (uint32_t)kp.tw, (uint32_t)kp.th, 1};
+      rc = make_map(&ma, d->A, dims, str, box, one4);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->Wi, (uint64_t)d->Hi, (uint64_t)d->n_img};
+      uint64_t str[3] = {(uint64_t)d->ldb, (uint64_t)d->ldb * d->Wi, (uint64_t)d->ldb * d->Wi * d->Hi};
+      uint32_t box[4] = {64, (uint32_t)(kp.tw * kp.stride), (uint32_t)(kp.th * kp.stride), 1};
+      uint32_t es[4] = {1, (uint32_t)kp.stride, (uint32_t)kp.stride, 1};
+      rc = make_map(&mb, d->B, dims, str, box, es);
+      if (rc) return rc;
+    }
+    const int mt = (d->M + BM - 1) / BM, ntl = (d->N + BN - 1) / BN;
+    grid = dim3(mt * ntl, d->ntaps, splits);
+  }
+  if (splits > kp.k_iters) {
+    kp.splits = kp.k_iters;
+    grid.z = kp.k_iters;
+  }
+
+  // ---- pipeline depth ---------------------------------------------------------------------------------
+  const uint32_t a_bytes = kp.a_mn ? 2u * kp.bk * 128u : 128u * 128u;
+  const uint32_t b_bytes = kp.b_mn ? (uint32_t)(BN / 64) * kp.bk * 128u : (uint32_t)BN * 128u;
+  const uint32_t stage = a_bytes + b_bytes;
+  const uint32_t budget_two = 110 * 1024, budget_one = 222 * 1024;
+  int nst = (int)(budget_two / stage);
+  if (nst < 3) nst = (int)(budget_one / stage);
+  if (nst > 6) nst = 6;
+  GPV_REQUIRE(nst >= 2, "gemm: stage of %u bytes does not fit twice in shared memory", stage);
+  kp.nstages = nst;
+  const size_t smem = (size_t)nst * stage + 1024 /*alignment slack*/ + (2 * nst + 1) * 8 + 16;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 256) return launch<256>(ma, mb, kp, grid, smem, st);
+  if (BN == 128) return launch<128>(ma, mb, kp, grid, smem, st);
+  return launch<64>(ma, mb, kp, grid, smem, st);
+}

@@ -189,3 +189,174 @@ def lsap(cost, tgt_offsets):
         _C.check(_C.lib().gpvb200_lsap(_C.ptr(_req(cost, torch.float32)), _C.ptr(_req(tgt_offsets, torch.int32)), B, Q, Tmax,
                                        _C.ptr(oq), _C.ptr(ot), _C.stream_ptr()), "lsap")
     return oq, ot
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attention_fwd(q, k, v, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None, need_lse=True, out=None):
+    """q/k/v: bf16 2-D views [B*S, >=H*dh] (row stride = tokens' leading dimension; may be slices of a packed QKV).
+    Returns (o [B*Sq, H*dh] bf16, lse [B,H,Sq] fp32 log2-domain or None)."""
+    o = out if out is not None else torch.empty((B * Sq, H * dh), device=q.device, dtype=BF16)
+    lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32) if need_lse else None
+    _C.check(_C.lib().gpvb200_attention_fwd(
+        _C.ptr(_req(q, BF16)), _C.ptr(_req(k, BF16)), _C.ptr(_req(v, BF16)), _C.ptr(o), _C.ptr(lse),
+        _C.ptr(_req(key_mask, torch.uint8)), ctypes.c_int64(q.stride(0)), ctypes.c_int64(k.stride(0)),
+        ctypes.c_int64(v.stride(0)), ctypes.c_int64(o.stride(0)), B, H, Sq, Sk, dh, int(causal), ctypes.c_float(scale),
+        _C.stream_ptr()), "attention_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None):
+    """Writes dq/dk/dv (bf16 2-D views, may be slices of one packed gradient buffer)."""
+    i64 = ctypes.c_int64
+    _C.check(_C.lib().gpvb200_attention_bwd(
+        _C.ptr(_req(q, BF16)), _C.ptr(_req(k, BF16)), _C.ptr(_req(v, BF16)), _C.ptr(_req(o, BF16)), _C.ptr(_req(d_o, BF16)),
+        _C.ptr(_req(lse, torch.float32)), _C.ptr(_req(key_mask, torch.uint8)), _C.ptr(dq), _C.ptr(dk), _C.ptr(dv),
+        i64(q.stride(0)), i64(k.stride(0)), i64(v.stride(0)), i64(o.stride(0)), i64(d_o.stride(0)), i64(dq.stride(0)),
+        i64(dk.stride(0)), i64(dv.stride(0)), B, H, Sq, Sk, dh, int(causal), ctypes.c_float(scale), _C.stream_ptr()),
+        "attention_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ layernorm
+def layernorm_fwd(x, gamma, beta, eps, *, out=None, need_stats=True):
+    M, D = x.shape
+    y = out if out is not None else torch.empty((M, D), device=x.device, dtype=BF16)
+    stats = torch.empty((M, 2), device=x.device, dtype=torch.float32) if need_stats else None
+    _C.check(_C.lib().gpvb200_layernorm_fwd(_C.ptr(_req(x, BF16)), ctypes.c_int64(x.stride(0)), _C.ptr(gamma), _C.ptr(beta),
+                                            ctypes.c_float(eps), _C.ptr(y), ctypes.c_int64(y.stride(0)), _C.ptr(stats), M, D,
+                                            _C.stream_ptr()), "layernorm_fwd")
+    return y, stats
+
+
+def layernorm_bwd(dy, x, stats, gamma, dgamma, dbeta, *, out=None):
+    M, D = x.shape
+    dx = out if out is not None else torch.empty((M, D), device=x.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_layernorm_bwd(_C.ptr(_req(dy, BF16)), ctypes.c_int64(dy.stride(0)), _C.ptr(_req(x, BF16)),
+                                            ctypes.c_int64(x.stride(0)), _C.ptr(stats), _C.ptr(gamma), _C.ptr(dx),
+                                            ctypes.c_int64(dx.stride(0)), _C.ptr(dgamma), _C.ptr(dbeta), M, D, _C.stream_ptr()),
+             "layernorm_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def add_rowbcast(x, p, *, M=None, out=None):
+    """out[m] = x[m] + p[m % P]; x may be None (pure broadcast of p over M rows)."""
+    P, D = p.shape
+    if x is not None:
+        M = x.shape[0]
+    y = out if out is not None else torch.empty((M, D), device=p.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_add_rowbcast(_C.ptr(_req(x, BF16)), ctypes.c_int64(x.stride(0) if x is not None else 0),
+                                           _C.ptr(_req(p, BF16)), ctypes.c_int64(p.stride(0)), _C.ptr(y),
+                                           ctypes.c_int64(y.stride(0)), ctypes.c_int64(M), D, P, _C.stream_ptr()), "add_rowbcast")
+    return y
+
+
+def colsum(dy, out, N=None):
+    """out[n] (fp32) += sum_m dy[m][n]."""
+    M = dy.shape[0]
+    N = N if N is not None else dy.shape[1]
+    _C.check(_C.lib().gpvb200_colsum(_C.ptr(_req(dy, BF16)), ctypes.c_int64(dy.stride(0)), _C.ptr(_req(out, torch.float32)),
+                                     ctypes.c_int64(M), N, _C.stream_ptr()), "colsum")
+
+
+def batch_reduce(x, out, B, S):
+    D = x.shape[1]
+    _C.check(_C.lib().gpvb200_batch_reduce(_C.ptr(_req(x, BF16)), ctypes.c_int64(x.stride(0)), _C.ptr(_req(out, torch.float32)),
+                                           B, S, D, _C.stream_ptr()), "batch_reduce")
+
+
+def maxpool3x3s2(x):
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), device=x.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_maxpool3x3s2(_C.ptr(_req(x, BF16)), _C.ptr(y), B, H, W, C, _C.stream_ptr()), "maxpool")
+    return y
+
+
+def stem_im2col(img, out=None):
+    """img NCHW fp32 -> [B*Ho*Wo, 152] bf16 (7x7 stride 2 pad 3, k = tap*3 + c)."""
+    B, C, H, W = img.shape
+    assert C == 3
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    col = out if out is not None else torch.empty((B * Ho * Wo, 152), device=img.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_stem_im2col(_C.ptr(_req(img.contiguous(), torch.float32)), _C.ptr(col), B, H, W, _C.stream_ptr()),
+             "stem_im2col")
+    return col, Ho, Wo
+
+
+def roi_weights(boxes, H, W, ldw):
+    """boxes [BQ, >=4] fp32 (cx,cy,w,h normalised) -> [BQ, ldw] bf16 separable ROI-mean weights."""
+    BQ = boxes.shape[0]
+    w = torch.empty((BQ, ldw), device=boxes.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_roi_weights(_C.ptr(_req(boxes, torch.float32)), ctypes.c_int64(boxes.stride(0)), _C.ptr(w),
+                                          ctypes.c_int64(ldw), BQ, H, W, _C.stream_ptr()), "roi_weights")
+    return w
+
+
+def relevance_mix_fwd(x, logits, tok, out, *, G, out_gstride, out_off):
+    M, D = x.shape
+    _C.check(_C.lib().gpvb200_relevance_mix_fwd(_C.ptr(_req(x, BF16)), ctypes.c_int64(x.stride(0)), _C.ptr(_req(logits, torch.float32)),
+                                                ctypes.c_int64(logits.stride(0)), _C.ptr(_req(tok, torch.float32)), _C.ptr(out),
+                                                ctypes.c_int64(out.stride(0)), M, D, G, out_gstride, out_off, _C.stream_ptr()),
+             "relevance_mix_fwd")
+
+
+def relevance_mix_bwd(dy, logits, tok, dlogits, dtok, *, M, G, gstride, off):
+    D = tok.shape[1]
+    _C.check(_C.lib().gpvb200_relevance_mix_bwd(_C.ptr(_req(dy, BF16)), ctypes.c_int64(dy.stride(0)), _C.ptr(_req(logits, torch.float32)),
+                                                ctypes.c_int64(logits.stride(0)), _C.ptr(_req(tok, torch.float32)),
+                                                _C.ptr(_req(dlogits, torch.float32)), ctypes.c_int64(dlogits.stride(0)),
+                                                _C.ptr(_req(dtok, torch.float32)), M, D, G, gstride, off, _C.stream_ptr()),
+             "relevance_mix_bwd")
+
+
+def gather_rows(table, ids, *, pos=None, cst=None, T=1, out=None):
+    M = ids.numel()
+    D = table.shape[1]
+    y = out if out is not None else torch.empty((M, D), device=table.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_gather_rows(_C.ptr(_req(table, torch.float32)), _C.ptr(_req(ids, torch.int64)), _C.ptr(pos), _C.ptr(cst),
+                                          _C.ptr(y), ctypes.c_int64(y.stride(0)), ctypes.c_int64(M), D, T, _C.stream_ptr()),
+             "gather_rows")
+    return y
+
+
+def copy_rows(src, dst, M, D, *, src_map=None, dst_map=None):
+    """map = (G, gstride, off): row(m) = (m // G) * gstride + off + m % G; None = identity."""
+    sG, sgs, so = src_map if src_map else (1 << 30, 0, 0)
+    dG, dgs, do = dst_map if dst_map else (1 << 30, 0, 0)
+    _C.check(_C.lib().gpvb200_copy_rows(_C.ptr(_req(src, BF16)), ctypes.c_int64(src.stride(0)), sG, sgs, so, _C.ptr(_req(dst, BF16)),
+                                        ctypes.c_int64(dst.stride(0)), dG, dgs, do, ctypes.c_int64(M), D, _C.stream_ptr()),
+             "copy_rows")
+
+
+def cast_bf16(src, out=None):
+    y = out if out is not None else torch.empty(src.shape, device=src.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_cast_f32_bf16(_C.ptr(_req(src, torch.float32)), _C.ptr(y), ctypes.c_int64(src.numel()),
+                                            _C.stream_ptr()), "cast")
+    return y
+
+
+def bn_fold(w, b, rm, rv, scale, bias):
+    _C.check(_C.lib().gpvb200_bn_fold(_C.ptr(w), _C.ptr(b), _C.ptr(rm), _C.ptr(rv), _C.ptr(scale), _C.ptr(bias), w.numel(),
+                                      _C.stream_ptr()), "bn_fold")
+
+
+# ------------------------------------------------------------------------------------------------ criterion
+def ce_fwd_bwd(logits, targets, row_weight, loss_sum, dlogits=None, row_loss=None):
+    rows, V = logits.shape
+    _C.check(_C.lib().gpvb200_ce_fwd_bwd(_C.ptr(_req(logits, torch.float32)), ctypes.c_int64(logits.stride(0)),
+                                         _C.ptr(_req(targets, torch.int64)), _C.ptr(_req(row_weight, torch.float32)),
+                                         _C.ptr(_req(loss_sum, torch.float32)), _C.ptr(row_loss), _C.ptr(dlogits),
+                                         ctypes.c_int64(dlogits.stride(0) if dlogits is not None else 0), rows, V,
+                                         _C.stream_ptr()), "ce_fwd_bwd")
+
+
+def set_criterion(logits, boxes, tgt_boxes, tgt_offsets, idx_q, idx_t, loc_valid, *, eos_coef, weight_sum, num_boxes,
+                  wt_ce, wt_bbox, wt_giou, out3, dlogits, dbox_pre):
+    B, Q = loc_valid.shape[0], logits.shape[0] // loc_valid.shape[0]
+    Kmax = idx_q.shape[1] if idx_q is not None else 0
+    f = ctypes.c_float
+    _C.check(_C.lib().gpvb200_set_criterion(
+        _C.ptr(_req(logits, torch.float32)), ctypes.c_int64(logits.stride(0)), _C.ptr(_req(boxes, torch.float32)),
+        ctypes.c_int64(boxes.stride(0)), _C.ptr(tgt_boxes), _C.ptr(_req(tgt_offsets, torch.int32)), _C.ptr(idx_q), _C.ptr(idx_t),
+        Kmax, _C.ptr(_req(loc_valid, torch.uint8)), B, Q, f(eos_coef), f(weight_sum), f(num_boxes), f(wt_ce), f(wt_bbox),
+        f(wt_giou), _C.ptr(_req(out3, torch.float32)), _C.ptr(_req(dlogits, torch.float32)), _C.ptr(_req(dbox_pre, BF16)),
+        ctypes.c_int64(dbox_pre.stride(0)), _C.stream_ptr()), "set_criterion")

@@ -107,6 +107,82 @@ int gpvb200_matcher_cost(const float* logits /*[B,Q,C]*/, const float* boxes /*[
 int gpvb200_lsap(const float* cost /*[B,Q,Tmax]*/, const int32_t* tgt_offsets /*[B+1]*/, int32_t B, int32_t Q,
                  int32_t Tmax, int64_t* out_q, int64_t* out_t, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention core: O = softmax(scale * Q K^T + mask) V, one (batch, head) per CTA, scores stay on chip.
+ * Replaces nn.MultiheadAttention's bmm/softmax/bmm (transformer.py:153-155, 218-226; gpv.py:38-43 via
+ * nn.TransformerDecoderLayer) and BertBiAttention's matmul/softmax/matmul (vilbert.py:766-815).
+ * Tensors are token-major: element (b, s, h, d) of X lives at X[(b*S + s)*ldx + h*dh + d] (bf16), so the packed
+ * QKV projection output can be read in place.  key_mask [B,Sk] (1 = ignore key) may be NULL; causal masks keys j > i.
+ * lse [B,H,Sq] fp32 (log2 domain) is written by fwd (may be NULL for inference) and consumed by bwd.
+ * ------------------------------------------------------------------------------------------------ */
+int gpvb200_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const uint8_t* key_mask,
+                          int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int32_t B, int32_t H, int32_t Sq,
+                          int32_t Sk, int32_t dh, int32_t causal, float scale, void* stream);
+int gpvb200_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                          const uint8_t* key_mask, void* dq, void* dk, void* dv, int64_t ldq, int64_t ldk, int64_t ldv,
+                          int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, int32_t B, int32_t H,
+                          int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension (nn.LayerNorm eps 1e-5: transformer.py:139-140,199-201, gpv.py:38-43;
+ * BertLayerNorm eps 1e-12: vilbert.py:296-316; F.layer_norm without affine: detr_roi_head.py:91).
+ * x, y, dy, dx bf16 with row strides; gamma/beta fp32 or both NULL; stats [M][2] = (mean, rstd) fp32.
+ * bwd accumulates dgamma/dbeta atomically (fp32).
+ * ------------------------------------------------------------------------------------------------ */
+int gpvb200_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y, int64_t ldy,
+                          float* stats, int32_t M, int32_t D, void* stream);
+int gpvb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* stats, const float* gamma,
+                          void* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound helpers (elementwise.cu)
+ * ------------------------------------------------------------------------------------------------ */
+/* out[m] = x[m] + p[m % P]  (x may be NULL): q = k = src + pos, transformer.py:153,218,223-224 */
+int gpvb200_add_rowbcast(const void* x, int64_t ldx, const void* p, int64_t ldp, void* out, int64_t ldo, int64_t M, int32_t D,
+                         int32_t P, void* stream);
+/* out[n] += sum_m dy[m][n]  (bias gradients of every nn.Linear / conv bias) */
+int gpvb200_colsum(const void* dy, int64_t ld, float* out, int64_t M, int32_t N, void* stream);
+/* out[s][d] += sum_b x[b*S+s][d]  (gradient of batch-broadcast parameters, e.g. detr.query_embed) */
+int gpvb200_batch_reduce(const void* x, int64_t ld, float* out, int32_t B, int32_t S, int32_t D, void* stream);
+/* multi-tensor fp32 -> bf16 weight packing with FrozenBN fold (backbone.py:44-54); items is a device array of
+ * {const float* src; bf16* dst; const float* scale; int32 O, I, taps, mode} */
+size_t gpvb200_pack_item_size(void);
+int gpvb200_pack_chunk(void);
+int gpvb200_pack_weights(const void* items, const int32_t* blk_item, const int32_t* blk_chunk, int32_t n_blocks, void* stream);
+int gpvb200_bn_fold(const float* w, const float* b, const float* rm, const float* rv, float* scale, float* bias, int32_t n,
+                    void* stream);
+/* torchvision resnet stem pieces (backbone.py:72): 3x3/s2 max-pool on NHWC bf16; 7x7/s2 im2col from NCHW fp32 */
+int gpvb200_maxpool3x3s2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+int gpvb200_stem_im2col(const float* img, void* col, int32_t B, int32_t H, int32_t W, void* stream);
+/* ROI-align(7x7, aligned, adaptive sampling)+mean as separable weights (detr_roi_head.py:44-56): wroi[bq][y*W+x] */
+int gpvb200_roi_weights(const float* boxes, int64_t ldb, void* wroi, int64_t ldw, int32_t BQ, int32_t H, int32_t W, void* stream);
+/* relevance conditioning gpv.py:364-375 (+ the memory concat gpv.py:175 through the output row remap) */
+int gpvb200_relevance_mix_fwd(const void* x, int64_t ldx, const float* logits, int64_t ldl, const float* tok, void* out,
+                              int64_t ldo, int32_t M, int32_t D, int32_t G, int32_t out_gstride, int32_t out_off, void* stream);
+int gpvb200_relevance_mix_bwd(const void* dy, int64_t lddy, const float* logits, int64_t ldl, const float* tok, float* dlogits,
+                              int64_t lddl, float* dtok, int32_t M, int32_t D, int32_t G, int32_t gstride, int32_t off, void* stream);
+/* out[m] = table[ids[m]] (+ pos[m % T]) (+ cst): AnswerInputEmbedding gpv.py:53, BERT embeddings */
+int gpvb200_gather_rows(const float* table, const int64_t* ids, const float* pos, const float* cst, void* out, int64_t ldo,
+                        int64_t M, int32_t D, int32_t T, void* stream);
+/* row-remapped bf16 copy: row(m) = (m / G) * gstride + off + m % G on either side */
+int gpvb200_copy_rows(const void* src, int64_t lds, int32_t sG, int32_t sgs, int32_t soff, void* dst, int64_t ldd, int32_t dG,
+                      int32_t dgs, int32_t doff, int64_t M, int32_t D, void* stream);
+int gpvb200_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Criterion (losses.py:20-26,155-176; utils/set_criterion.py:44-62,78-97)
+ * ------------------------------------------------------------------------------------------------ */
+/* loss_sum += sum_rows w[row] * CE(logits[row], targets[row]);  dlogits = w[row] * (softmax - onehot) as bf16 */
+int gpvb200_ce_fwd_bwd(const float* logits, int64_t ldl, const int64_t* targets, const float* row_weight, float* loss_sum,
+                       float* row_loss, void* dlogits, int64_t ldd, int32_t rows, int32_t V, void* stream);
+/* out3 += (loss_ce, loss_bbox, loss_giou); dlogits [B*Q][ldl] fp32 and dbox_pre [B*Q][lddb] bf16 (gradient w.r.t.
+ * the pre-sigmoid box head output), both already multiplied by the loss weights wt_*. */
+int gpvb200_set_criterion(const float* logits, int64_t ldl, const float* boxes, int64_t ldb, const float* tgt_boxes,
+                          const int32_t* tgt_offsets, const int64_t* idx_q, const int64_t* idx_t, int32_t Kmax,
+                          const uint8_t* loc_valid, int32_t B, int32_t Q, float eos_coef, float weight_sum, float num_boxes,
+                          float wt_ce, float wt_bbox, float wt_giou, float* out3, float* dlogits, void* dbox_pre, int64_t lddb,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

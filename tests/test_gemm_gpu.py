@@ -66,7 +66,9 @@ def test_linear_dgrad(cuda, M, N, K):
 def test_linear_wgrad(cuda, M, N, K):
     from gpv1_b200 import kernels as k
     torch.manual_seed(2)
-    dy, x = _bf(M, N, dev=cuda), _bf(M, K, dev=cuda)
+    # TMA needs 16-byte row strides: narrow heads (N=2,4) keep their activations in 8-wide padded buffers
+    ldn = (N + 7) // 8 * 8
+    dy, x = _bf(M, ldn, dev=cuda)[:, :N], _bf(M, K, dev=cuda)
     dw = torch.zeros(N, K, device=cuda)
     k.linear_wgrad(dy, x, dw)
     ref = dy.float().t() @ x.float()

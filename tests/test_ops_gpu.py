@@ -1,0 +1,271 @@
+"""Attention / LayerNorm / helper / criterion kernels vs. plain PyTorch fp32 references of the same ops.
+
+Tolerances (bf16 storage, fp32 accumulate): 2e-2 of the reference's max magnitude for bf16 outputs, 2e-3 for fp32 ones.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, tol=2e-2, name=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, f"{name}: max err {err:.4g} vs scale {scale:.4g}"
+
+
+def _bf(*shape, dev, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,dh,causal,masked", [
+    (2, 8, 300, 300, 32, False, True), (2, 8, 100, 100, 32, False, False), (2, 8, 100, 300, 32, False, True),
+    (3, 16, 20, 100, 48, False, False), (3, 16, 100, 20, 48, False, False), (2, 8, 20, 20, 96, True, False),
+    (2, 8, 19, 120, 96, False, False), (2, 12, 20, 20, 64, False, True), (1, 8, 7, 7, 96, True, False)])
+def test_attention(cuda, B, H, Sq, Sk, dh, causal, masked):
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(0)
+    D = H * dh
+    # packed projections, like the model produces them: q | k | v side by side when Sq == Sk
+    q = _bf(B * Sq, D, dev=cuda)
+    kv = _bf(B * Sk, 2 * D, dev=cuda)
+    kk, vv = kv[:, :D], kv[:, D:]
+    km = None
+    if masked:
+        km = torch.zeros(B, Sk, dtype=torch.uint8, device=cuda)
+        km[0, Sk - 3:] = 1
+        km[-1, : Sk // 4] = 1
+    scale = dh ** -0.5
+    o, lse = k.attention_fwd(q, kk, vv, B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=scale, causal=causal, key_mask=km)
+
+    def ref(qf, kf, vf):
+        qh = qf.view(B, Sq, H, dh).transpose(1, 2)
+        kh = kf.view(B, Sk, H, dh).transpose(1, 2)
+        vh = vf.view(B, Sk, H, dh).transpose(1, 2)
+        s = (qh @ kh.transpose(-1, -2)) * scale
+        if km is not None:
+            s = s.masked_fill(km.bool()[:, None, None, :], float("-inf"))
+        if causal:
+            s = s.masked_fill(torch.ones(Sq, Sk, device=cuda).triu(1).bool(), float("-inf"))
+        return (s.softmax(-1) @ vh).transpose(1, 2).reshape(B * Sq, D)
+
+    qf = q.float().requires_grad_(True)
+    kf = kk.float().requires_grad_(True)
+    vf = vv.float().requires_grad_(True)
+    r = ref(qf, kf, vf)
+    _close(o, r, name="attn fwd")
+    d_o = _bf(B * Sq, D, dev=cuda)
+    r.backward(d_o.float())
+    dq = torch.empty(B * Sq, D, device=cuda, dtype=torch.bfloat16)
+    dkv = torch.empty(B * Sk, 2 * D, device=cuda, dtype=torch.bfloat16)
+    k.attention_bwd(q, kk, vv, o, d_o, lse, dq, dkv[:, :D], dkv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=scale,
+                    causal=causal, key_mask=km)
+    _close(dq, qf.grad, tol=3e-2, name="attn dq")
+    _close(dkv[:, :D], kf.grad, tol=3e-2, name="attn dk")
+    _close(dkv[:, D:], vf.grad, tol=3e-2, name="attn dv")
+
+
+@pytest.mark.parametrize("M,D,eps,affine", [(9600, 256, 1e-5, True), (640, 768, 1e-12, True), (3200, 2048, 1e-5, False),
+                                            (77, 768, 1e-5, True), (5, 256, 1e-5, False)])
+def test_layernorm(cuda, M, D, eps, affine):
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(1)
+    x = _bf(M, D, dev=cuda, scale=3.0)
+    g = (torch.rand(D, device=cuda) + 0.5) if affine else None
+    b = torch.randn(D, device=cuda) if affine else None
+    y, stats = k.layernorm_fwd(x, g, b, eps)
+    xf = x.float().requires_grad_(True)
+    gf = g.clone().requires_grad_(True) if affine else None
+    bf = b.clone().requires_grad_(True) if affine else None
+    r = F.layer_norm(xf, (D,), gf, bf, eps)
+    _close(y, r, name="ln fwd")
+    dy = _bf(M, D, dev=cuda)
+    r.backward(dy.float())
+    dg = torch.zeros(D, device=cuda) if affine else None
+    db = torch.zeros(D, device=cuda) if affine else None
+    dx = k.layernorm_bwd(dy, x, stats, g, dg, db)
+    _close(dx, xf.grad, name="ln dx")
+    if affine:
+        _close(dg, gf.grad, tol=5e-3, name="ln dgamma")
+        _close(db, bf.grad, tol=5e-3, name="ln dbeta")
+    # strided output into a wider buffer (ROI features next to hs, detr_roi_head.py:92)
+    wide = torch.zeros(M, D + 256, device=cuda, dtype=torch.bfloat16)
+    k.layernorm_fwd(x, g, b, eps, out=wide[:, :D], need_stats=False)
+    _close(wide[:, :D], r, name="ln strided")
+    assert wide[:, D:].abs().max().item() == 0
+
+
+def test_helpers(cuda):
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(2)
+    B, S, D = 3, 300, 256
+    x, p = _bf(B * S, D, dev=cuda), _bf(S, D, dev=cuda)
+    _close(k.add_rowbcast(x, p), x.float() + p.float().repeat(B, 1), name="add_rowbcast")
+    _close(k.add_rowbcast(None, p, M=B * S), p.float().repeat(B, 1), name="rowbcast")
+    dy = _bf(1000, 776, dev=cuda)
+    out = torch.ones(776, device=cuda)
+    k.colsum(dy, out)
+    _close(out, 1 + dy.float().sum(0), tol=2e-3, name="colsum")
+    out = torch.zeros(S, D, device=cuda)
+    k.batch_reduce(x, out, B, S)
+    _close(out, x.float().view(B, S, D).sum(0), tol=2e-3, name="batch_reduce")
+    img = _bf(2, 30, 41, 64, dev=cuda)
+    mp = k.maxpool3x3s2(img)
+    ref = F.max_pool2d(img.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(mp.float(), ref)
+    im = torch.randn(2, 3, 37, 50, device=cuda)
+    col, Ho, Wo = k.stem_im2col(im)
+    w = torch.randn(64, 3, 7, 7, device=cuda)
+    wp = w.permute(0, 2, 3, 1).reshape(64, 147)
+    got = (col[:, :147].float() @ wp.t()).view(2, Ho, Wo, 64)
+    ref = F.conv2d(im.to(torch.bfloat16).float(), w, stride=2, padding=3).permute(0, 2, 3, 1)
+    _close(got, ref, tol=2e-3, name="stem im2col")
+    assert col[:, 147:].abs().max().item() == 0
+    tab = torch.randn(50, 768, device=cuda)
+    ids = torch.randint(0, 50, (40,), device=cuda)
+    pos = torch.randn(20, 768, device=cuda)
+    cst = torch.randn(768, device=cuda)
+    _close(k.gather_rows(tab, ids, pos=pos, cst=cst, T=20), tab[ids] + pos.repeat(2, 1) + cst, name="gather")
+    src = _bf(2 * 100, 768, dev=cuda)
+    mem = torch.zeros(2 * 120, 768, device=cuda, dtype=torch.bfloat16)
+    k.copy_rows(src, mem, 200, 768, dst_map=(100, 120, 0))
+    assert torch.equal(mem.view(2, 120, 768)[:, :100], src.view(2, 100, 768))
+    back = torch.zeros_like(src)
+    k.copy_rows(mem, back, 200, 768, src_map=(100, 120, 0))
+    assert torch.equal(back, src)
+    f = torch.randn(1001, device=cuda)
+    assert torch.equal(k.cast_bf16(f), f.to(torch.bfloat16))
+
+
+def test_roi_weights_vs_torchvision(cuda):
+    """mean over the 7x7 aligned ROI-align bins == Wroi @ features (detr_roi_head.py:44-56)."""
+    import torchvision
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(3)
+    B, Q, C, H, W = 2, 100, 64, 15, 20
+    feat = torch.randn(B, C, H, W, device=cuda)
+    boxes = torch.cat([torch.rand(B, Q, 2, device=cuda), 0.02 + 0.9 * torch.rand(B, Q, 2, device=cuda)], -1)
+    sb = torch.zeros_like(boxes)
+    sb[:, :, 0] = W * (boxes[:, :, 0] - 0.5 * boxes[:, :, 2])
+    sb[:, :, 1] = H * (boxes[:, :, 1] - 0.5 * boxes[:, :, 3])
+    sb[:, :, 2] = W * (boxes[:, :, 0] + 0.5 * boxes[:, :, 2])
+    sb[:, :, 3] = H * (boxes[:, :, 1] + 0.5 * boxes[:, :, 3])
+    ref = torchvision.ops.roi_align(feat, list(torch.unbind(sb)), output_size=7, aligned=True)
+    ref = ref.view(B, Q, C, 7, 7).mean(-1).mean(-1)
+    wr = k.roi_weights(boxes.view(B * Q, 4).contiguous(), H, W, 304).float().view(B, Q, 304)[:, :, :H * W]
+    got = torch.bmm(wr, feat.permute(0, 2, 3, 1).reshape(B, H * W, C))
+    _close(got, ref, tol=1e-2, name="roi weights")  # weights are bf16-rounded
+
+
+def test_relevance_mix(cuda):
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(4)
+    B, Q, T, D = 3, 100, 20, 768
+    x = _bf(B * Q, D, dev=cuda)
+    logits = torch.zeros(B * Q, 8, device=cuda)
+    logits[:, :2] = torch.randn(B * Q, 2, device=cuda)
+    tok = 0.1 * torch.randn(2, D, device=cuda)
+    mem = torch.zeros(B * (Q + T), D, device=cuda, dtype=torch.bfloat16)
+    k.relevance_mix_fwd(x, logits, tok, mem, G=Q, out_gstride=Q + T, out_off=0)
+    lf = logits[:, :2].clone().requires_grad_(True)
+    tf = tok.clone().requires_grad_(True)
+    ref = x.float() + lf.softmax(-1) @ tf
+    _close(mem.view(B, Q + T, D)[:, :Q].reshape(B * Q, D), ref, name="mix fwd")
+    dmem = _bf(B * (Q + T), D, dev=cuda)
+    ref.backward(dmem.view(B, Q + T, D)[:, :Q].reshape(B * Q, D).float())
+    dl = torch.zeros(B * Q, 8, device=cuda)
+    dt = torch.zeros(2, D, device=cuda)
+    k.relevance_mix_bwd(dmem, logits, tok, dl, dt, M=B * Q, G=Q, gstride=Q + T, off=0)
+    _close(dl[:, :2], lf.grad, tol=5e-3, name="mix dlogits")
+    _close(dt, tf.grad, tol=5e-3, name="mix dtok")
+
+
+def test_cross_entropy(cuda):
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(5)
+    rows, V = 57, 1000
+    logits = 3 * torch.randn(rows, V, device=cuda)
+    tg = torch.randint(0, V, (rows,), device=cuda)
+    w = torch.rand(rows, device=cuda)
+    w[::5] = 0
+    loss = torch.zeros(1, device=cuda)
+    dl = torch.empty(rows, V, device=cuda, dtype=torch.bfloat16)
+    rl = torch.empty(rows, device=cuda)
+    k.ce_fwd_bwd(logits, tg, w, loss, dl, rl)
+    lf = logits.clone().requires_grad_(True)
+    per = F.cross_entropy(lf, tg, reduction="none")
+    ref = (per * w).sum()
+    ref.backward()
+    _close(rl, per, tol=1e-4, name="ce rows")
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    _close(dl, lf.grad, name="ce dlogits")
+
+
+def test_set_criterion(cuda):
+    """Matched-pair losses and gradients vs. autograd on the reference formulas (set_criterion.py:44-97)."""
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(6)
+    B, Q = 4, 100
+    tc = [5, 0, 3, 7]
+    loc_valid = torch.tensor([1, 1, 0, 1], dtype=torch.uint8, device=cuda)
+    off = torch.tensor([0, 5, 5, 8, 15], dtype=torch.int32, device=cuda)
+    tb = torch.cat([0.2 + 0.6 * torch.rand(15, 2, device=cuda), 0.05 + 0.3 * torch.rand(15, 2, device=cuda)], -1)
+    logits = torch.zeros(B * Q, 8, device=cuda)
+    logits[:, :2] = torch.randn(B * Q, 2, device=cuda)
+    pre = torch.randn(B * Q, 4, device=cuda)
+    boxes = torch.zeros(B * Q, 8, device=cuda)
+    boxes[:, :4] = pre.sigmoid()
+    Kmax = 7
+    iq = torch.full((B, Kmax), -1, dtype=torch.int64, device=cuda)
+    it = torch.full((B, Kmax), -1, dtype=torch.int64, device=cuda)
+    for b in range(B):
+        qs = torch.randperm(Q, device=cuda)[: tc[b]].sort().values
+        iq[b, : tc[b]] = qs
+        it[b, : tc[b]] = torch.randperm(tc[b], device=cuda)
+    nvalid_img = [0, 1, 3]
+    n_match = sum(tc[b] for b in nvalid_img)
+    wsum = n_match * 1.0 + (len(nvalid_img) * Q - n_match) * 0.1
+    num_boxes = float(max(n_match, 1))
+    out3 = torch.zeros(3, device=cuda)
+    dl = torch.zeros(B * Q, 8, device=cuda)
+    dbp = torch.zeros(B * Q, 8, device=cuda, dtype=torch.bfloat16)
+    k.set_criterion(logits, boxes, tb, off, iq, it, loc_valid, eos_coef=0.1, weight_sum=wsum, num_boxes=num_boxes, wt_ce=1.0,
+                    wt_bbox=5.0, wt_giou=2.0, out3=out3, dlogits=dl, dbox_pre=dbp)
+
+    # reference formulas
+    lf = logits[:, :2].clone().view(B, Q, 2).requires_grad_(True)
+    pf = pre.clone().view(B, Q, 4).requires_grad_(True)
+    bx = pf.sigmoid()
+    sel = nvalid_img
+    tgt_cls = torch.ones(B, Q, dtype=torch.int64, device=cuda)
+    src, tgt = [], []
+    for b in sel:
+        tgt_cls[b, iq[b, : tc[b]]] = 0
+        src.append(bx[b, iq[b, : tc[b]]])
+        tgt.append(tb[off[b]: off[b + 1]][it[b, : tc[b]]])
+    src, tgt = torch.cat(src), torch.cat(tgt)
+    l_ce = F.cross_entropy(lf[sel].transpose(1, 2), tgt_cls[sel], torch.tensor([1.0, 0.1], device=cuda))
+    l_l1 = F.l1_loss(src, tgt, reduction="none").sum() / num_boxes
+
+    def xyxy(b):
+        return torch.stack([b[:, 0] - 0.5 * b[:, 2], b[:, 1] - 0.5 * b[:, 3], b[:, 0] + 0.5 * b[:, 2], b[:, 1] + 0.5 * b[:, 3]], -1)
+
+    a, c = xyxy(src), xyxy(tgt)
+    area1 = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area2 = (c[:, 2] - c[:, 0]) * (c[:, 3] - c[:, 1])
+    wh = (torch.min(a[:, 2:], c[:, 2:]) - torch.max(a[:, :2], c[:, :2])).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = area1 + area2 - inter
+    ewh = (torch.max(a[:, 2:], c[:, 2:]) - torch.min(a[:, :2], c[:, :2])).clamp(min=0)
+    earea = ewh[:, 0] * ewh[:, 1]
+    giou = inter / union - (earea - union) / earea
+    l_gi = (1 - giou).sum() / num_boxes
+    (1.0 * l_ce + 5.0 * l_l1 + 2.0 * l_gi).backward()
+    ref3 = torch.stack([l_ce, l_l1, l_gi]).detach()
+    _close(out3, ref3, tol=1e-4, name="set losses")
+    _close(dl[:, :2], lf.grad.view(B * Q, 2), tol=1e-3, name="set dlogits")
+    _close(dbp[:, :4], pf.grad.view(B * Q, 4), tol=1e-2, name="set dbox")

@@ -22,7 +22,7 @@ class GemmDesc(ctypes.Structure):
         ("ntaps", c_int32),
         ("tap_dh", c_int32 * 9), ("tap_dw", c_int32 * 9), ("tap_w", c_int32 * 9),
         ("OH", c_int32), ("OW", c_int32), ("out_stride", c_int32), ("out_off_h", c_int32), ("out_off_w", c_int32),
-        ("alpha", c_float), ("_pad0", c_int32),
+        ("alpha", c_float), ("res_fp32", c_int32),
         ("A", c_void_p), ("B", c_void_p), ("D", c_void_p), ("D2", c_void_p),
         ("bias", c_void_p), ("rowscale", c_void_p), ("residual", c_void_p), ("aux", c_void_p),
         ("lda", c_int64), ("ldb", c_int64), ("ldd", c_int64), ("ldr", c_int64), ("ldaux", c_int64),

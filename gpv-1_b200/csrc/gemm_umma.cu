@@ -26,7 +26,7 @@ struct KParams {
   int ntaps;
   int tap_dh[9], tap_dw[9], tap_w[9];
   int OH, OW, os, ooh, oow;
-  int act, aux_mode, d_fp32, d_atomic, vec_ok;
+  int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32;
   float alpha;
   void* D;
   bf16* D2;
@@ -216,7 +216,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 16; ++j)
           if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
       }
-      if (p.residual != nullptr) {
+      if (p.residual != nullptr && p.res_fp32) {
+        const float* rp = reinterpret_cast<const float*>(p.residual) + row_off + pix * p.ldr + nb;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) v[j] += rp[j];
+      } else if (p.residual != nullptr) {
         const bf16* rp = p.residual + row_off + pix * p.ldr + nb;
         if (vec_ok) {
           const uint4 t0 = *reinterpret_cast<const uint4*>(rp);
@@ -488,6 +493,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   kp.d_fp32 = d->d_fp32;
   kp.d_atomic = d->d_atomic;
   kp.alpha = d->alpha;
+  kp.res_fp32 = d->res_fp32;
   kp.D = d->D;
   kp.D2 = (bf16*)d->D2;
   kp.bias = d->bias;

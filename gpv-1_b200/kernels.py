@@ -43,7 +43,8 @@ def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, batch=1, a_
     d.alpha = alpha
     d.A, d.B, d.D, d.D2 = _C.ptr(A), _C.ptr(B), _C.ptr(D), _C.ptr(D2)
     d.bias, d.rowscale = _C.ptr(_req(bias, torch.float32)), _C.ptr(_req(rowscale, torch.float32))
-    d.residual, d.aux = _C.ptr(_req(residual, BF16)), _C.ptr(_req(aux, BF16))
+    d.residual, d.aux = _C.ptr(_req(residual)), _C.ptr(_req(aux, BF16))
+    d.res_fp32 = int(residual is not None and residual.dtype == torch.float32)
     d.lda, d.ldb, d.ldd, d.ldr, d.ldaux = lda, ldb, ldd, ldr, ldaux
     d.a_batch_stride, d.b_batch_stride, d.d_batch_stride = a_bs, b_bs, d_bs
     _launch_gemm(d)

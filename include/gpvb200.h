@@ -75,7 +75,7 @@ typedef struct gpvb200_gemm_desc {
   int32_t tap_dh[9], tap_dw[9], tap_w[9];
   int32_t OH, OW, out_stride, out_off_h, out_off_w;
   float alpha;
-  int32_t _pad0;
+  int32_t res_fp32;       /* residual element type: 0 bf16, 1 fp32 */
   const void* A;
   const void* B;
   void* D;

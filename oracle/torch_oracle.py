@@ -1,0 +1,404 @@
+"""ORACLE -- test infrastructure only (never imported by gpv-1_b200/).
+
+fp32 PyTorch restatement of the GPV-1 forward pass and criterion as one pure function of a name->tensor dict that
+uses the reference's ``state_dict()`` keys.  It is the checker for the CUDA path (tests/, smoke()) and the
+``cpu_baseline`` / ``--impl reference`` leg of bench.py (the reference itself is Python and cannot travel to the GPU
+box).  Pinned against the unmodified reference modules by ``oracle/make_golden.py`` (fixtures: tests/golden/gpv_*.pt).
+
+Every block cites the reference lines it restates:
+  backbone            exp/gpv/models/backbone.py:44-54,71-79 + torchvision resnet50 (v1.5 bottleneck)
+  position encoding   exp/gpv/models/position_encoding.py:28-48
+  DETR transformer    exp/gpv/models/transformer.py:46-58,148-161,211-232,94-123 (nn.MultiheadAttention math)
+  ROI head            exp/gpv/models/detr_roi_head.py:44-56,58-94,105-117
+  BERT                exp/gpv/models/bert.py:11-22 (HF BertModel, eval)
+  co-attention        exp/gpv/models/vilbert.py:737-824,845-856,872-900
+  relevance / memory  exp/gpv/models/gpv.py:137-207,364-375
+  text decoder        exp/gpv/models/gpv.py:37-43,449-466 (nn.TransformerDecoderLayer post-norm, ReLU, ff 2048)
+  answer head         exp/gpv/models/answer_head.py:26-33
+  criterion           exp/gpv/models/losses.py:20-26,41-138,155-176; utils/set_criterion.py:44-62,78-97,150-191;
+                      utils/matcher.py:32-77; utils/box_ops.py:9-59
+Dropout is inactive (the parity contract is eval()-mode-with-grad).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+RESNET50 = [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]
+TASK_LOSS = {"CocoCaptioning": "loss_caption", "CocoVqa": "loss_vqa", "CocoClassification": "loss_cls"}
+DEFAULT_LOSS_WTS = {"loss_caption": 0.05, "loss_vqa": 1.0, "loss_cls": 1.0, "loss_ce": 1.0, "loss_bbox": 5.0, "loss_giou": 2.0}
+
+
+# ------------------------------------------------------------------------------------------------ primitives
+def lin(P, name, x):
+    return F.linear(x, P[name + ".weight"], P[name + ".bias"])
+
+
+def ln(P, name, x, eps):
+    return F.layer_norm(x, (x.shape[-1],), P[name + ".weight"], P[name + ".bias"], eps)
+
+
+def frozen_bn(P, name, x):
+    """backbone.py:44-54: y = x * (w * rsqrt(rv + 1e-5)) + (b - rm * scale)."""
+    scale = P[name + ".weight"] * (P[name + ".running_var"] + 1e-5).rsqrt()
+    bias = P[name + ".bias"] - P[name + ".running_mean"] * scale
+    return x * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+
+
+def mha(P, name, q_in, k_in, v_in, nheads, key_padding_mask=None, causal=False):
+    """nn.MultiheadAttention on batch-first [B,S,D] tensors.  in_proj_weight rows [0:D]=W_q, [D:2D]=W_k, [2D:3D]=W_v;
+    Q is scaled by d_h^-1/2 after its bias; masked keys get -inf; softmax; P.V; out_proj."""
+    D = q_in.shape[-1]
+    W, bvec = P[name + ".in_proj_weight"], P[name + ".in_proj_bias"]
+    q = F.linear(q_in, W[:D], bvec[:D])
+    k = F.linear(k_in, W[D:2 * D], bvec[D:2 * D])
+    v = F.linear(v_in, W[2 * D:], bvec[2 * D:])
+    B, Sq, _ = q.shape
+    Sk = k.shape[1]
+    dh = D // nheads
+    q = q.view(B, Sq, nheads, dh).transpose(1, 2) * (dh ** -0.5)
+    k = k.view(B, Sk, nheads, dh).transpose(1, 2)
+    v = v.view(B, Sk, nheads, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    if causal:
+        s = s.masked_fill(torch.ones(Sq, Sk, dtype=torch.bool, device=s.device).triu(1), float("-inf"))
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, Sq, D)
+    return lin(P, name + ".out_proj", o)
+
+
+# ------------------------------------------------------------------------------------------------ backbone
+def resnet50_c5(P, x, prefix="detr.backbone.0.body"):
+    x = F.conv2d(x, P[f"{prefix}.conv1.weight"], stride=2, padding=3)
+    x = F.relu(frozen_bn(P, f"{prefix}.bn1", x))
+    x = F.max_pool2d(x, 3, 2, 1)
+    inplanes = 64
+    for li, (planes, blocks, stride) in enumerate(RESNET50, start=1):
+        for bi in range(blocks):
+            s = stride if bi == 0 else 1
+            p = f"{prefix}.layer{li}.{bi}"
+            idn = x
+            y = F.relu(frozen_bn(P, p + ".bn1", F.conv2d(x, P[p + ".conv1.weight"])))
+            y = F.relu(frozen_bn(P, p + ".bn2", F.conv2d(y, P[p + ".conv2.weight"], stride=s, padding=1)))
+            y = frozen_bn(P, p + ".bn3", F.conv2d(y, P[p + ".conv3.weight"]))
+            if bi == 0 and (s != 1 or inplanes != planes * 4):
+                idn = frozen_bn(P, p + ".downsample.1", F.conv2d(x, P[p + ".downsample.0.weight"], stride=s))
+            x = F.relu(y + idn)
+            inplanes = planes * 4
+    return x
+
+
+def sine_position(mask, num_pos_feats=128, temperature=10000.0):
+    """mask [B,H,W] bool (True = padding) -> [B,2*num_pos_feats,H,W]."""
+    nm = ~mask
+    y = nm.cumsum(1, dtype=torch.float32)
+    x = nm.cumsum(2, dtype=torch.float32)
+    y = y / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
+    x = x / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
+    i = torch.arange(num_pos_feats, dtype=torch.float32, device=mask.device)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / num_pos_feats)
+    px = x[..., None] / dim_t
+    py = y[..., None] / dim_t
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((py, px), dim=3).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ DETR
+def detr_forward(P, images, mask=None, nheads=8, n_enc=6, n_dec=6):
+    """images [B,3,H,W]; mask [B,H,W] bool or None (no padding).  Returns dict like detr_roi_head.DETR.forward."""
+    B = images.shape[0]
+    if mask is None:
+        mask = torch.zeros(images.shape[0], images.shape[2], images.shape[3], dtype=torch.bool, device=images.device)
+    c5 = resnet50_c5(P, images)
+    H, W = c5.shape[-2:]
+    m = F.interpolate(mask[None].float(), size=(H, W)).to(torch.bool)[0]
+    pos = sine_position(m).flatten(2).transpose(1, 2)                      # [B,HW,256]
+    kpm = m.flatten(1)
+    src = F.conv2d(c5, P["detr.input_proj.weight"], P["detr.input_proj.bias"]).flatten(2).transpose(1, 2)
+    x = src
+    for i in range(n_enc):
+        p = f"detr.transformer.encoder.layers.{i}"
+        qk = x + pos
+        x = ln(P, p + ".norm1", x + mha(P, p + ".self_attn", qk, qk, x, nheads, kpm), 1e-5)
+        ff = lin(P, p + ".linear2", F.relu(lin(P, p + ".linear1", x)))
+        x = ln(P, p + ".norm2", x + ff, 1e-5)
+    memory = x
+    qpos = P["detr.query_embed.weight"][None].expand(B, -1, -1)
+    t = torch.zeros_like(qpos)
+    for i in range(n_dec):
+        p = f"detr.transformer.decoder.layers.{i}"
+        qk = t + qpos
+        t = ln(P, p + ".norm1", t + mha(P, p + ".self_attn", qk, qk, t, nheads), 1e-5)
+        t = ln(P, p + ".norm2", t + mha(P, p + ".multihead_attn", t + qpos, memory + pos, memory, nheads, kpm), 1e-5)
+        ff = lin(P, p + ".linear2", F.relu(lin(P, p + ".linear1", t)))
+        t = ln(P, p + ".norm3", t + ff, 1e-5)
+    hs = ln(P, "detr.transformer.decoder.norm", t, 1e-5)                    # last layer only  [B,Q,256]
+    logits = lin(P, "detr.class_embed", hs)
+    y = F.relu(lin(P, "detr.bbox_embed.layers.0", hs))
+    y = F.relu(lin(P, "detr.bbox_embed.layers.1", y))
+    boxes = lin(P, "detr.bbox_embed.layers.2", y).sigmoid()
+    roi = roi_mean(c5, boxes)
+    roi = F.layer_norm(roi, (roi.shape[-1],))
+    return {"pred_relevance_logits": logits, "pred_boxes": boxes, "detr_hs": torch.cat((roi, hs), -1), "c5": c5}
+
+
+def roi_mean(c5, boxes):
+    """detr_roi_head.py:44-56: 7x7 aligned ROI-align of the normalised cxcywh boxes on C5, mean over the bins."""
+    import torchvision
+    B, C, H, W = c5.shape
+    N = boxes.shape[1]
+    x0 = W * (boxes[..., 0] - 0.5 * boxes[..., 2])
+    y0 = H * (boxes[..., 1] - 0.5 * boxes[..., 3])
+    x1 = W * (boxes[..., 0] + 0.5 * boxes[..., 2])
+    y1 = H * (boxes[..., 1] + 0.5 * boxes[..., 3])
+    sb = torch.stack((x0, y0, x1, y1), -1)
+    r = torchvision.ops.roi_align(c5, list(torch.unbind(sb)), output_size=7, aligned=True)
+    return r.view(B, N, C, 49).mean(-1)
+
+
+# ------------------------------------------------------------------------------------------------ BERT
+def bert_forward(P, ids, prefix="bert.model", nheads=12, n_layers=12):
+    """HF BertModel (eval): embeddings (word + position + token_type 0) -> LN(1e-12) -> post-LN encoder, erf-GELU."""
+    B, T = ids.shape
+    e = P[f"{prefix}.embeddings.word_embeddings.weight"][ids] + P[f"{prefix}.embeddings.position_embeddings.weight"][:T][None] \
+        + P[f"{prefix}.embeddings.token_type_embeddings.weight"][0][None, None]
+    x = ln(P, f"{prefix}.embeddings.LayerNorm", e, 1e-12)
+    dh = x.shape[-1] // nheads
+    for i in range(n_layers):
+        p = f"{prefix}.encoder.layer.{i}"
+        q = lin(P, p + ".attention.self.query", x).view(B, T, nheads, dh).transpose(1, 2)
+        k = lin(P, p + ".attention.self.key", x).view(B, T, nheads, dh).transpose(1, 2)
+        v = lin(P, p + ".attention.self.value", x).view(B, T, nheads, dh).transpose(1, 2)
+        a = ((q @ k.transpose(-1, -2)) / math.sqrt(dh)).softmax(-1) @ v
+        a = a.transpose(1, 2).reshape(B, T, -1)
+        x = ln(P, p + ".attention.output.LayerNorm", lin(P, p + ".attention.output.dense", a) + x, 1e-12)
+        h = F.gelu(lin(P, p + ".intermediate.dense", x))
+        x = ln(P, p + ".output.LayerNorm", lin(P, p + ".output.dense", h) + x, 1e-12)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ co-attention
+def co_attention_layer(P, p, lang, vis, nheads=16):
+    """vilbert.py:872-900 with tensor1 = language, tensor2 = vision (gpv.py:149-154)."""
+    def heads(x):
+        B, S, D = x.shape
+        return x.view(B, S, nheads, D // nheads).transpose(1, 2)
+
+    def merge(x):
+        B, Hh, S, d = x.shape
+        return x.transpose(1, 2).reshape(B, S, Hh * d)
+
+    a = p + ".biattention"
+    q1, k1, v1 = (heads(lin(P, f"{a}.{n}1", lang)) for n in ("query", "key", "value"))
+    q2, k2, v2 = (heads(lin(P, f"{a}.{n}2", vis)) for n in ("query", "key", "value"))
+    dh = q1.shape[-1]
+    ctx1 = merge(((q2 @ k1.transpose(-1, -2)) / math.sqrt(dh)).softmax(-1) @ v1)   # vision rows, language values
+    ctx2 = merge(((q1 @ k2.transpose(-1, -2)) / math.sqrt(dh)).softmax(-1) @ v2)   # language rows, vision values
+    att1 = ln(P, p + ".biOutput.LayerNorm1", lin(P, p + ".biOutput.dense1", ctx2) + lang, 1e-12)
+    att2 = ln(P, p + ".biOutput.LayerNorm2", lin(P, p + ".biOutput.dense2", ctx1) + vis, 1e-12)
+    o1 = ln(P, p + ".v_output.LayerNorm", lin(P, p + ".v_output.dense", F.gelu(lin(P, p + ".v_intermediate.dense", att1))) + att1, 1e-12)
+    o2 = ln(P, p + ".t_output.LayerNorm", lin(P, p + ".t_output.dense", F.gelu(lin(P, p + ".t_intermediate.dense", att2))) + att2, 1e-12)
+    return o1, o2
+
+
+# ------------------------------------------------------------------------------------------------ text decoder
+def text_decode(P, target, memory, nheads=8, n_layers=3):
+    """gpv.py:449-466: target [B,S,D], memory [B,Tm,D] -> logits [B,S,V]."""
+    x = target
+    for i in range(n_layers):
+        p = f"text_decoder.layers.{i}"
+        x = ln(P, p + ".norm1", x + mha(P, p + ".self_attn", x, x, x, nheads, causal=True), 1e-5)
+        x = ln(P, p + ".norm2", x + mha(P, p + ".multihead_attn", x, memory, memory, nheads), 1e-5)
+        x = ln(P, p + ".norm3", x + lin(P, p + ".linear2", F.relu(lin(P, p + ".linear1", x))), 1e-5)
+    wc = lin(P, "answer_head.classifier_transform", P["answer_head.vocab_embed"])      # [V,D], every call
+    return x @ wc.t()
+
+
+def embed_answer(P, ids):
+    return lin(P, "answer_input_embedings.transform", P["answer_input_embedings.embedding_layer.weight"][ids])
+
+
+# ------------------------------------------------------------------------------------------------ encode (shared trunk)
+def gpv_encode(P, images, query_ids, mask=None, n_co=3):
+    """gpv.py:137-175 up to `memory`.  Returns (outputs dict, memory [B,Q+Tl,D])."""
+    out = detr_forward(P, images, mask)
+    vis = joined = lin(P, "detr_joiner", out["detr_hs"])
+    with torch.no_grad():
+        qe = bert_forward(P, query_ids)
+    lang = lin(P, "bert_joiner", qe.detach())
+    for i in range(n_co):
+        lang, vis = co_attention_layer(P, f"co_att_transformer.{i}", lang, vis)
+    logits = out["pred_relevance_logits"] + lin(P, "relevance_predictor", vis)
+    prob = logits.softmax(-1)
+    vis = vis + prob @ P["relevance_tokens"]
+    outputs = {"pred_relevance_logits": logits, "pred_boxes": out["pred_boxes"], "detr_hs": joined[None]}
+    return outputs, torch.cat((vis, lang), 1)
+
+
+def gpv_forward(P, images, query_ids, answer_token_ids=None, targets=None, vocab_mask=None, mask=None, max_text_len=20,
+                cls_id=1, loss_wts=None):
+    """GPV.forward (gpv.py:137-207).  answer_token_ids None -> greedy decode; targets given -> total loss."""
+    outputs, memory = gpv_encode(P, images, query_ids, mask)
+    B = memory.shape[0]
+    if answer_token_ids is None:
+        ids = torch.full((B, 1), cls_id, dtype=torch.long, device=memory.device)
+        for _ in range(max_text_len - 1):
+            lg = text_decode(P, embed_answer(P, ids), memory)[:, -1]
+            if vocab_mask is not None:
+                lg = lg + vocab_mask
+            ids = torch.cat((ids, lg.topk(1, -1).indices), -1)
+        lg = text_decode(P, embed_answer(P, ids), memory)
+        if vocab_mask is not None:
+            lg = lg + vocab_mask
+        outputs["answer_logits"] = lg[None]
+    else:
+        outputs["answer_logits"] = text_decode(P, embed_answer(P, answer_token_ids), memory)[:, :-1][None]
+    if targets is None:
+        return outputs
+    return gpv_criterion(outputs, targets, loss_wts or DEFAULT_LOSS_WTS)[0]
+
+
+# ------------------------------------------------------------------------------------------------ criterion
+def box_xyxy(b):
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), -1)
+
+
+def giou_pairs(a, b):
+    """GIoU of matched pairs (diag of box_ops.generalized_box_iou), xyxy inputs [N,4]."""
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    wh = (torch.min(a[:, 2:], b[:, 2:]) - torch.max(a[:, :2], b[:, :2])).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = area_a + area_b - inter
+    iou = inter / union
+    whc = (torch.max(a[:, 2:], b[:, 2:]) - torch.min(a[:, :2], b[:, :2])).clamp(min=0)
+    area_c = whc[:, 0] * whc[:, 1]
+    return iou - (area_c - union) / area_c
+
+
+def hungarian(logits, boxes, tgt_boxes_list, w=(1.0, 5.0, 2.0)):
+    """utils/matcher.py:32-77 through the C restatement (oracle/matcher_oracle.c, pinned to scipy + the reference)."""
+    import oracle
+    sizes = [int(t.shape[0]) for t in tgt_boxes_list]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    tb = torch.cat(list(tgt_boxes_list), 0).detach().cpu().numpy() if sum(sizes) else np.zeros((0, 4), np.float32)
+    cost = oracle.matcher_cost(logits.detach().cpu().numpy(), boxes.detach().cpu().numpy(), tb, np.zeros(int(off[-1]), np.int64), off,
+                               w[0], w[1], w[2])
+    oq, ot = oracle.lsap_batched(cost, off)
+    res = []
+    for b, n in enumerate(sizes):
+        k = min(n, logits.shape[1])
+        res.append((torch.as_tensor(oq[b, :k].copy()), torch.as_tensor(ot[b, :k].copy())))
+    return res
+
+
+def gpv_criterion(outputs, targets, loss_wts=None, eos_coef=0.1):
+    """GPVCriterion.forward (losses.py:155-176) with CaptionLoss / VqaLoss / ClsLoss / Localization."""
+    loss_wts = loss_wts or DEFAULT_LOSS_WTS
+    losses = {}
+    al = outputs["answer_logits"][0]                                          # [B,S,V]
+    for task, name in TASK_LOSS.items():
+        idx = [i for i, t in enumerate(targets) if "answer" in t and t["task"] == task]
+        if not idx:
+            losses[name] = None
+            continue
+        lg = al[idx]
+        tg = torch.stack([targets[i]["answer_token_ids"] for i in idx])
+        ce = F.cross_entropy(lg.reshape(-1, lg.shape[-1]), tg.reshape(-1), reduction="none").view(len(idx), -1)
+        losses[name] = ce.mean(0).sum()
+    idx = [i for i, t in enumerate(targets) if "boxes" in t]
+    if not idx:
+        losses.update(loss_ce=None, loss_bbox=None, loss_giou=None)
+    else:
+        logits = outputs["pred_relevance_logits"][idx]
+        boxes = outputs["pred_boxes"][idx]
+        tb = [targets[i]["boxes"] for i in idx]
+        ind = hungarian(logits, boxes, tb)
+        num_boxes = max(float(sum(t.shape[0] for t in tb)), 1.0)
+        tc = torch.ones(logits.shape[:2], dtype=torch.long, device=logits.device)
+        bi = torch.cat([torch.full_like(q, i) for i, (q, _) in enumerate(ind)])
+        qi = torch.cat([q for q, _ in ind])
+        tc[bi, qi] = 0
+        wvec = torch.tensor([1.0, eos_coef], device=logits.device)
+        losses["loss_ce"] = F.cross_entropy(logits.transpose(1, 2), tc, wvec)
+        sb = boxes[bi, qi]
+        tbm = torch.cat([t[j] for t, (_, j) in zip(tb, ind)], 0)
+        losses["loss_bbox"] = (sb - tbm).abs().sum() / num_boxes
+        losses["loss_giou"] = (1 - giou_pairs(box_xyxy(sb), box_xyxy(tbm))).sum() / num_boxes
+        losses["_indices"] = ind
+    if all(v is None for k, v in losses.items() if not k.startswith("_")):
+        return None, losses
+    total = 0
+    for k, wt in loss_wts.items():
+        if losses.get(k) is not None:
+            total = total + wt * losses[k]
+    return total, losses
+
+
+# ------------------------------------------------------------------------------------------------ beam search
+def beam_search(P, memory, K, max_text_len=20, cls_id=1):
+    """gpv.py:256-328 semantics: returns (seqs [B,K,max_text_len-1], log_prob [B,K]).
+    Candidates are ordered (k1 major, k2 minor); ties keep the first occurrence (stable descending sort); at t=0 only
+    beam 0 is live; __stop__ never stops a beam."""
+    B = memory.shape[0]
+    ids = torch.full((B, K, 1), cls_id, dtype=torch.long)
+    score = torch.zeros(B, K)
+    for t in range(max_text_len - 1):
+        lp = []
+        for k1 in range(K):
+            lg = text_decode(P, embed_answer(P, ids[:, k1]), memory)
+            lp.append(F.log_softmax(lg, -1)[:, -1])
+        lp = torch.stack(lp, 1)                                               # [B,K,V]
+        top = lp.topk(K, -1)
+        cand = score[:, :, None] + top.values                                 # [B,K1,K2]
+        if t == 0:
+            cand[:, 1:] = cand[:, 1:] * 0 - 1e9
+        flat = cand.reshape(B, K * K)
+        order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, :K]
+        k1 = order // K
+        k2 = order % K
+        new_last = torch.gather(top.indices.reshape(B, K * K), 1, order)
+        ids = torch.cat((torch.gather(ids, 1, k1[:, :, None].expand(-1, -1, ids.shape[2])), new_last[:, :, None]), 2)
+        score = torch.gather(flat, 1, order)
+    return ids[:, :, 1:], score
+
+
+# ------------------------------------------------------------------------------------------------ deterministic weights
+def make_state(specs, seed=0, device="cpu"):
+    """Seeded, name-ordered random weights for a list of (name, shape, kind) specs: the same tensors in the oracle,
+    the reference (load_state_dict) and the CUDA model.  Scales keep activations O(1) through every block."""
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    for name, shape, kind in specs:
+        shape = tuple(shape)
+        if name.endswith("running_var"):
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif name.endswith("running_mean"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif ".bn" in name or ".downsample.1." in name:
+            t = (1.0 + 0.1 * torch.randn(shape, generator=g)) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
+        elif "LayerNorm" in name or ".norm" in name:
+            t = (1.0 + 0.1 * torch.randn(shape, generator=g)) if name.endswith("weight") else 0.05 * torch.randn(shape, generator=g)
+        elif name == "criterion.localization_criterion.set_criterion.empty_weight":
+            t = torch.tensor([1.0, 0.1])
+        elif name == "pos_enc":
+            t = torch.zeros(shape)
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        elif name in ("answer_head.vocab_embed", "answer_input_embedings.embedding_layer.weight"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("_embeddings.weight") or name == "detr.query_embed.weight":
+            t = 0.5 * torch.randn(shape, generator=g)
+        elif len(shape) == 2 and name != "relevance_tokens":
+            t = torch.randn(shape, generator=g) * (1.0 / math.sqrt(shape[1]))
+        else:
+            t = 0.05 * torch.randn(shape, generator=g)
+        P[name] = t.to(device)
+    if "answer_input_embedings.embedding_layer.weight" in P and "answer_head.vocab_embed" in P:
+        P["answer_input_embedings.embedding_layer.weight"] = P["answer_head.vocab_embed"].clone()
+    return P

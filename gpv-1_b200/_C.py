@@ -42,6 +42,7 @@ def lib():
         if L.gpvb200_gemm_desc_size() != ctypes.sizeof(GemmDesc):
             raise RuntimeError("gpvb200_gemm_desc layout mismatch between _C.py and libgpvb200.so")
         L.gpvb200_last_error.argtypes = [ctypes.c_char_p, c_size_t]
+        L.gpvb200_pack_item_size.restype = c_size_t
         _lib = L
     return _lib
 

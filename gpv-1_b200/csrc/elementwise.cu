@@ -510,3 +510,59 @@ extern "C" int gpvb200_cast_f32_bf16(const float* src, void* dst, int64_t n, voi
   cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST>>>(src, (bf16*)dst, n);
   return check_launch("cast_f32_bf16_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Conv weight-gradient unpack: packed fp32 [taps][O][I] (what the wgrad GEMM accumulates) -> master layout
+// [O][I][taps] (torch Conv2d weight [O,I,kh,kw]); dst = src (accumulate == 0) or dst += src.
+// ------------------------------------------------------------------------------------------------
+namespace gpv {
+__global__ void unpack_conv_grad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int taps, int accumulate) {
+  const long long OI = (long long)O * I, n = OI * taps;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long oi = e / taps;
+    const int t = (int)(e % taps);
+    const float v = src[(long long)t * OI + oi];
+    dst[e] = accumulate ? dst[e] + v : v;
+  }
+}
+
+// out = a + b (bf16, row strides), vectorised 16 B
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ b, long long ldb,
+                                bf16* __restrict__ out, long long ldo, long long M, int D) {
+  const int nch = D >> 3;
+  const long long total = M * nch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / nch;
+    const int c = (int)(i % nch);
+    const uint4 x = *reinterpret_cast<const uint4*>(a + m * lda + c * 8);
+    const uint4 y = *reinterpret_cast<const uint4*>(b + m * ldb + c * 8);
+    const uint32_t wa[4] = {x.x, x.y, x.z, x.w}, wb[4] = {y.x, y.y, y.z, y.w};
+    uint32_t wo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = unpack_bf16x2(wa[j]), fb = unpack_bf16x2(wb[j]);
+      wo[j] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+    }
+    *reinterpret_cast<uint4*>(out + m * ldo + c * 8) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  }
+}
+}  // namespace gpv
+
+extern "C" int gpvb200_unpack_conv_grad(const float* src, float* dst, int32_t O, int32_t I, int32_t taps, int32_t accumulate,
+                                        void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(src && dst && O > 0 && I > 0 && taps > 0, "unpack_conv_grad: bad arguments");
+  unpack_conv_grad_kernel<<<grid_for((long long)O * I * taps, 256), 256, 0, ST>>>(src, dst, O, I, taps, accumulate);
+  return check_launch("unpack_conv_grad_kernel");
+}
+
+extern "C" int gpvb200_add_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t M, int32_t D,
+                                void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(a && b && out && D % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "add_bf16: bad arguments");
+  if (M == 0) return GPV_OK;
+  add_bf16_kernel<<<grid_for(M * (D / 8), 256), 256, 0, ST>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out, ldo, M, D);
+  return check_launch("add_bf16_kernel");
+}

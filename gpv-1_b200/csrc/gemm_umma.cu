@@ -428,8 +428,10 @@ static int make_map(CUtensorMap* out, const void* ptr, const uint64_t dims[4], c
 static void pick_tile(int H, int W, int limit, bool exact_mult16, int* th_out, int* tw_out) {
   double best = -1.0;
   int bth = 1, btw = 1;
-  for (int tw = 1; tw <= W && tw <= limit; ++tw) {
-    for (int th = 1; th <= H && th * tw <= limit; ++th) {
+  // weight-gradient tiles may hang over the image edge (TMA zero-fills), which lets tiny maps reach a multiple of 16
+  const int Wm = exact_mult16 ? (W < 8 ? 8 : W) : W, Hm = exact_mult16 ? (H < 8 ? 8 : H) : H;
+  for (int tw = 1; tw <= Wm && tw <= limit; ++tw) {
+    for (int th = 1; th <= Hm && th * tw <= limit; ++th) {
       const int rows = th * tw;
       if (exact_mult16 && (rows % 16 != 0)) continue;
       const long long tiles = (long long)((H + th - 1) / th) * ((W + tw - 1) / tw);

@@ -16,14 +16,14 @@ namespace gpv {
 // ------------------------------------------------------------------------------------------------------
 __global__ void matcher_cost_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                     const float* __restrict__ tboxes, const int64_t* __restrict__ tlabels,
-                                    const int32_t* __restrict__ toff, int Q, int C, int Tmax, float w_class,
-                                    float w_bbox, float w_giou, float* __restrict__ cost) {
+                                    const int32_t* __restrict__ toff, int Q, int C, int Tmax, long long ldl, long long ldb,
+                                    float w_class, float w_bbox, float w_giou, float* __restrict__ cost) {
   const int b = blockIdx.x;
   const int t0 = toff[b], T = toff[b + 1] - t0;
   for (int idx = threadIdx.x; idx < Q * T; idx += blockDim.x) {
     const int q = idx / T, t = idx % T;
     // --- class term: -softmax(logits)[label]   (matcher.py:56, 63) ; x * (1/sum) like ATen's CPU softmax
-    const float* lg = logits + ((size_t)b * Q + q) * C;
+    const float* lg = logits + ((size_t)b * Q + q) * ldl;
     float mx = lg[0];
     for (int c = 1; c < C; ++c) mx = fmaxf(mx, lg[c]);
     float sum = 0.0f;
@@ -32,7 +32,7 @@ __global__ void matcher_cost_kernel(const float* __restrict__ logits, const floa
     const float prob = __fmul_rn(expf(__fsub_rn(lg[lab], mx)), __fdiv_rn(1.0f, sum));
     const float cost_class = -prob;
     // --- L1 term: cdist(p=1)                   (matcher.py:66)
-    const float4 ob = *reinterpret_cast<const float4*>(boxes + ((size_t)b * Q + q) * 4);
+    const float4 ob = *reinterpret_cast<const float4*>(boxes + ((size_t)b * Q + q) * ldb);
     const float4 tb = *reinterpret_cast<const float4*>(tboxes + (size_t)(t0 + t) * 4);
     float l1 = fabsf(__fsub_rn(ob.x, tb.x));
     l1 = __fadd_rn(l1, fabsf(__fsub_rn(ob.y, tb.y)));
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(32) lsap_kernel(const float* __restrict__ cost
 
 using namespace gpv;
 
-extern "C" int gpvb200_matcher_cost(const float* logits, const float* boxes, const float* tgt_boxes,
+extern "C" int gpvb200_matcher_cost(const float* logits, int64_t ldl, const float* boxes, int64_t ldb, const float* tgt_boxes,
                                     const int64_t* tgt_labels, const int32_t* tgt_offsets, int32_t B, int32_t Q,
                                     int32_t C, int32_t Tmax, float w_class, float w_bbox, float w_giou, float* cost,
                                     void* stream) {
@@ -227,7 +227,8 @@ extern "C" int gpvb200_matcher_cost(const float* logits, const float* boxes, con
   GPV_REQUIRE(B >= 0 && Q > 0 && C > 0 && Tmax >= 0, "matcher_cost: bad shape");
   if (B == 0 || Tmax == 0) return GPV_OK;
   GPV_REQUIRE(logits && boxes && tgt_boxes && tgt_labels && tgt_offsets && cost, "matcher_cost: null pointer");
-  matcher_cost_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, boxes, tgt_boxes, tgt_labels, tgt_offsets, Q, C, Tmax,
+  GPV_REQUIRE(ldl >= C && ldb >= 4 && ldb % 4 == 0 && ((uintptr_t)boxes & 15) == 0, "matcher_cost: bad row strides");
+  matcher_cost_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, boxes, tgt_boxes, tgt_labels, tgt_offsets, Q, C, Tmax, ldl, ldb,
                                                            w_class, w_bbox, w_giou, cost);
   return check_launch("matcher_cost_kernel");
 }

@@ -166,13 +166,16 @@ def conv_wgrad(dy, x, dw, *, ksize, stride=1, rowscale=None, splits=0):
 
 
 # ------------------------------------------------------------------------------------------------ matcher
-def matcher_cost(logits, boxes, tgt_boxes, tgt_labels, tgt_offsets, Tmax, w_class, w_bbox, w_giou):
-    """fp32 cost blocks [B,Q,Tmax] (utils/matcher.py:53-72)."""
-    B, Q, C = logits.shape
+def matcher_cost(logits, boxes, tgt_boxes, tgt_labels, tgt_offsets, Tmax, w_class, w_bbox, w_giou, *, C=None):
+    """fp32 cost blocks [B,Q,Tmax] (utils/matcher.py:53-72).  logits/boxes are [B,Q,>=C] / [B,Q,>=4] with a contiguous
+    last dimension (padded rows are read in place through their row stride)."""
+    B, Q = logits.shape[:2]
+    C = C if C is not None else logits.shape[2]
     cost = torch.zeros((B, Q, max(Tmax, 1)), device=logits.device, dtype=torch.float32)
     if B and Tmax:
         _C.check(_C.lib().gpvb200_matcher_cost(
-            _C.ptr(_req(logits, torch.float32)), _C.ptr(_req(boxes, torch.float32)), _C.ptr(_req(tgt_boxes, torch.float32)),
+            _C.ptr(_req(logits, torch.float32)), ctypes.c_int64(logits.stride(1)), _C.ptr(_req(boxes, torch.float32)),
+            ctypes.c_int64(boxes.stride(1)), _C.ptr(_req(tgt_boxes, torch.float32)),
             _C.ptr(_req(tgt_labels, torch.int64)), _C.ptr(_req(tgt_offsets, torch.int32)), B, Q, C, Tmax,
             ctypes.c_float(w_class), ctypes.c_float(w_bbox), ctypes.c_float(w_giou), _C.ptr(cost), _C.stream_ptr()),
             "matcher_cost")
@@ -333,6 +336,52 @@ def cast_bf16(src, out=None):
     _C.check(_C.lib().gpvb200_cast_f32_bf16(_C.ptr(_req(src, torch.float32)), _C.ptr(y), ctypes.c_int64(src.numel()),
                                             _C.stream_ptr()), "cast")
     return y
+
+
+def add(a, b, out=None):
+    """out = a + b (bf16 2-D, row strides allowed)."""
+    M, D = a.shape
+    y = out if out is not None else torch.empty((M, D), device=a.device, dtype=BF16)
+    _C.check(_C.lib().gpvb200_add_bf16(_C.ptr(_req(a, BF16)), ctypes.c_int64(a.stride(0)), _C.ptr(_req(b, BF16)),
+                                       ctypes.c_int64(b.stride(0)), _C.ptr(y), ctypes.c_int64(y.stride(0)), ctypes.c_int64(M), D,
+                                       _C.stream_ptr()), "add_bf16")
+    return y
+
+
+def unpack_conv_grad(src, dst, accumulate=False):
+    """src fp32 [taps,O,I] -> dst fp32 [O,I,kh,kw] (Conv2d weight layout)."""
+    taps, O, I = src.shape
+    _C.check(_C.lib().gpvb200_unpack_conv_grad(_C.ptr(_req(src, torch.float32)), _C.ptr(_req(dst, torch.float32)), O, I, taps,
+                                               int(accumulate), _C.stream_ptr()), "unpack_conv_grad")
+
+
+class PackPlan:
+    """One-launch multi-tensor fp32 -> bf16 weight packing (gpvb200_pack_weights).  items: list of
+    (src fp32 tensor, dst bf16 tensor, scale fp32 tensor or None, O, I, taps, mode)."""
+
+    def __init__(self, items, device):
+        import numpy as np
+        chunk = _C.lib().gpvb200_pack_chunk()
+        self.keep = items
+        rec = np.zeros(len(items), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("scale", "<u8"), ("O", "<i4"), ("I", "<i4"),
+                                                   ("taps", "<i4"), ("mode", "<i4")]))
+        assert rec.dtype.itemsize == _C.lib().gpvb200_pack_item_size()
+        bi, bc = [], []
+        for i, (src, dst, scale, O, I, taps, mode) in enumerate(items):
+            _req(src, torch.float32), _req(dst, BF16)
+            rec[i] = (src.data_ptr(), dst.data_ptr(), scale.data_ptr() if scale is not None else 0, O, I, taps, mode)
+            n = O * 152 if mode == 1 else taps * O * I
+            assert dst.numel() >= n and src.is_contiguous() and dst.is_contiguous()
+            nb = (n + chunk - 1) // chunk
+            bi += [i] * nb
+            bc += list(range(nb))
+        self.items = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
+        self.blk_item = torch.tensor(bi, dtype=torch.int32).to(device)
+        self.blk_chunk = torch.tensor(bc, dtype=torch.int32).to(device)
+
+    def run(self):
+        _C.check(_C.lib().gpvb200_pack_weights(_C.ptr(self.items), _C.ptr(self.blk_item), _C.ptr(self.blk_chunk),
+                                               self.blk_item.numel(), _C.stream_ptr()), "pack_weights")
 
 
 def bn_fold(w, b, rm, rv, scale, bias):

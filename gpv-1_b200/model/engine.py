@@ -1,0 +1,742 @@
+"""Explicit forward/backward execution of the GPV-1 hot path on the sm_100a kernels (no autograd graph inside).
+
+`Engine` owns the derived state of one model replica:
+  * packed bf16 copies of every weight (FrozenBN folded into the conv weights, q/k/v projections concatenated,
+    3x3 convs in [tap][Cout][Cin] order) refreshed by ONE multi-tensor kernel when a parameter version changes;
+  * one flat fp32 gradient arena holding the gradient of every parameter that can receive one (the reference
+    needs DDP(find_unused_parameters=True) for the rest: train_distr.py:192-193) -- this is also the buffer the
+    data-parallel all-reduce runs on (parallel.py);
+  * the activations a training step has to keep for its backward, as bf16 token-major / NHWC tensors.
+
+forward_train()/backward() are hand-scheduled sequences of C-ABI calls: every GEMM/conv is the tcgen05 kernel with
+bias / residual / activation / ReLU-mask / GELU' fused in its epilogue, attention and LayerNorm are single
+kernels, and the matcher + criterion run on the device, so a step never synchronises with the host.
+
+Reference call stack this replaces: GPV.forward gpv.py:137-207 -> DETR.forward detr_roi_head.py:58-94 ->
+Backbone backbone.py:71-79, Transformer transformer.py:46-58 -> BertConnectionLayer vilbert.py:872-900 ->
+decode_text gpv.py:449-466 -> GPVCriterion losses.py:155-176 -> SetCriterion set_criterion.py:150-191 ->
+HungarianMatcher matcher.py:32-77, and autograd's backward of all of it.
+"""
+import math
+
+import torch
+
+from .. import kernels as k
+from ..convops import conv_dgrad
+from .spec import N_STAGES, grad_stage, never_gets_grad, resnet_blocks
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+RELU, GELU, SIGMOID = k.ACT_RELU, k.ACT_GELU, k.ACT_SIGMOID
+MASK_RELU, GRAD_GELU = k.AUX_RELU_MASK, k.AUX_GELU_GRAD
+TASK_LOSS = {"CocoCaptioning": "loss_caption", "CocoVqa": "loss_vqa", "CocoClassification": "loss_cls"}
+BB = "detr.backbone.0.body"
+
+
+def sine_position_table(H, W, device, num_pos_feats=128, temperature=10000.0):
+    """position_encoding.py:28-48 for an unpadded H x W map (mask all False): constant, built once per size."""
+    y = torch.arange(1, H + 1, dtype=F32, device=device)[:, None].expand(H, W)
+    x = torch.arange(1, W + 1, dtype=F32, device=device)[None, :].expand(H, W)
+    y = y / (H + 1e-6) * (2 * math.pi)
+    x = x / (W + 1e-6) * (2 * math.pi)
+    i = torch.arange(num_pos_feats, dtype=F32, device=device)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / num_pos_feats)
+    px, py = x[..., None] / dim_t, y[..., None] / dim_t
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=3).flatten(2)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=3).flatten(2)
+    return torch.cat((py, px), dim=2).reshape(H * W, 2 * num_pos_feats)
+
+
+class Engine:
+    def __init__(self, tensors, specs, cfg, device):
+        """tensors: name -> fp32 CUDA tensor for every state_dict entry (nn.Parameters and buffers of the module that
+        owns this engine); specs: model.spec.gpv_specs(); cfg: the `model:` config block."""
+        self.P = tensors
+        self.cfg = cfg
+        self.dev = device
+        self.d = cfg.detr.hidden_dim
+        self.D = cfg.hidden_dim
+        self.Q = cfg.detr.num_queries
+        self.n_enc, self.n_dec = cfg.detr.num_encoder_layers, cfg.detr.num_decoder_layers
+        self.n_co, self.n_txt = cfg.co_att.num_layers, cfg.text_decoder.num_layers
+        self.h_detr, self.h_co, self.h_txt = cfg.detr.nheads, cfg.co_att.bi_num_attention_heads, cfg.text_decoder.nheads
+        self.V = tensors["answer_head.vocab_embed"].shape[0]
+        self.Vp = (self.V + 7) // 8 * 8
+        self.blocks = list(resnet_blocks())
+        self.unit_upstream_grad = True
+        lw = {}
+        for _, lc in cfg.losses.items():
+            lw.update(lc.loss_wts)
+        self.loss_wts = {kk: float(v) for kk, v in lw.items()}
+        loc = cfg.losses.Localization
+        self.cost_w = (float(loc.cost_wts.ce), float(loc.cost_wts.bbox), float(loc.cost_wts.giou))
+        self.eos_coef = float(loc.eos_coef)
+        lwv = [1.0, self.loss_wts["loss_ce"], self.loss_wts["loss_bbox"], self.loss_wts["loss_giou"]]
+        self._wts_loc = torch.tensor(lwv, dtype=F32, device=device)
+        self._wts_noloc = torch.tensor([1.0, 0.0, 0.0, 0.0], dtype=F32, device=device)
+        self._setup_weights()
+        self._setup_grads(specs)
+        self._versions = None
+        self._pos_cache = {}
+        self.saved = None
+
+    # ================================================================================================ weights
+    def _setup_weights(self):
+        P, dev = self.P, self.dev
+        items, W, self.Bcat_src, self.Bcat = [], {}, {}, {}
+
+        def lin(name, key=None):
+            t = P[name]
+            N, K = t.shape[0], t.numel() // t.shape[0]
+            dst = torch.empty((N, K), device=dev, dtype=BF16)
+            items.append((t, dst, None, N, K, 1, 0))
+            W[key or name] = dst
+
+        def cat(key, names):
+            K = P[names[0] + ".weight"].shape[1]
+            Ns = [P[n + ".weight"].shape[0] for n in names]
+            dst = torch.empty((sum(Ns), K), device=dev, dtype=BF16)
+            off = 0
+            for n, N in zip(names, Ns):
+                items.append((P[n + ".weight"], dst[off:off + N], None, N, K, 1, 0))
+                off += N
+            W[key] = dst
+            self.Bcat_src[key] = [P[n + ".bias"] for n in names]
+            self.Bcat[key] = torch.empty(sum(Ns), device=dev, dtype=F32)
+
+        # ---- backbone: FrozenBN folded (scale into the packed weight rows, bias into the epilogue)
+        bns = [f"{BB}.bn1"]
+        for li, bi, inp, planes, s, ds in self.blocks:
+            p = f"{BB}.layer{li}.{bi}"
+            bns += [p + ".bn1", p + ".bn2", p + ".bn3"] + ([p + ".downsample.1"] if ds else [])
+        tot = sum(P[b + ".weight"].numel() for b in bns)
+        self._bn_flat = torch.empty(2 * tot, device=dev, dtype=F32)
+        self.bn_scale, self.bn_bias, off = {}, {}, 0
+        for b in bns:
+            n = P[b + ".weight"].numel()
+            self.bn_scale[b] = self._bn_flat[off:off + n]
+            self.bn_bias[b] = self._bn_flat[tot + off:tot + off + n]
+            off += n
+        self.bns = bns
+
+        def conv(name, bn):
+            t = P[name]
+            O, I, kh, kw = t.shape
+            dst = torch.empty((kh * kw, O, I), device=dev, dtype=BF16)
+            items.append((t, dst, self.bn_scale[bn], O, I, kh * kw, 0))
+            W[name] = dst
+
+        stem = torch.empty((64, 152), device=dev, dtype=BF16)
+        items.append((P[f"{BB}.conv1.weight"], stem, self.bn_scale[f"{BB}.bn1"], 64, 3, 49, 1))
+        W[f"{BB}.conv1.weight"] = stem
+        for li, bi, inp, planes, s, ds in self.blocks:
+            p = f"{BB}.layer{li}.{bi}"
+            conv(p + ".conv1.weight", p + ".bn1")
+            conv(p + ".conv2.weight", p + ".bn2")
+            conv(p + ".conv3.weight", p + ".bn3")
+            if ds:
+                conv(p + ".downsample.0.weight", p + ".downsample.1")
+        # ---- DETR
+        lin("detr.input_proj.weight")
+        lin("detr.query_embed.weight")
+        for i in range(self.n_enc):
+            p = f"detr.transformer.encoder.layers.{i}"
+            for n in ("self_attn.in_proj_weight", "self_attn.out_proj.weight", "linear1.weight", "linear2.weight"):
+                lin(f"{p}.{n}")
+        for i in range(self.n_dec):
+            p = f"detr.transformer.decoder.layers.{i}"
+            for n in ("self_attn.in_proj_weight", "self_attn.out_proj.weight", "multihead_attn.in_proj_weight",
+                      "multihead_attn.out_proj.weight", "linear1.weight", "linear2.weight"):
+                lin(f"{p}.{n}")
+        for n in ("detr.class_embed", "detr.bbox_embed.layers.0", "detr.bbox_embed.layers.1", "detr.bbox_embed.layers.2",
+                  "detr_joiner", "bert_joiner", "relevance_predictor", "answer_head.classifier_transform",
+                  "answer_input_embedings.transform"):
+            lin(n + ".weight")
+        lin("answer_head.vocab_embed")
+        # ---- BERT (forward only)
+        for i in range(12):
+            p = f"bert.model.encoder.layer.{i}"
+            cat(p + ".qkv", [p + ".attention.self.query", p + ".attention.self.key", p + ".attention.self.value"])
+            for n in ("attention.output.dense", "intermediate.dense", "output.dense"):
+                lin(f"{p}.{n}.weight")
+        # ---- co-attention
+        for i in range(self.n_co):
+            p = f"co_att_transformer.{i}"
+            cat(p + ".qkv1", [f"{p}.biattention.{n}1" for n in ("query", "key", "value")])
+            cat(p + ".qkv2", [f"{p}.biattention.{n}2" for n in ("query", "key", "value")])
+            for n in ("biOutput.dense1", "biOutput.dense2", "v_intermediate.dense", "v_output.dense", "t_intermediate.dense",
+                      "t_output.dense"):
+                lin(f"{p}.{n}.weight")
+        # ---- text decoder
+        for i in range(self.n_txt):
+            p = f"text_decoder.layers.{i}"
+            for n in ("self_attn.in_proj_weight", "self_attn.out_proj.weight", "multihead_attn.in_proj_weight",
+                      "multihead_attn.out_proj.weight", "linear1.weight", "linear2.weight"):
+                lin(f"{p}.{n}")
+        self.W = W
+        self._plan = k.PackPlan(items, dev)
+
+    @torch.no_grad()
+    def refresh(self, force=False):
+        """Re-derive the packed bf16 weights when any parameter changed (optimizer step, load_state_dict)."""
+        ver = sum(t._version for t in self.P.values())
+        if not force and ver == self._versions:
+            return
+        P = self.P
+        for b in self.bns:
+            k.bn_fold(P[b + ".weight"], P[b + ".bias"], P[b + ".running_mean"], P[b + ".running_var"], self.bn_scale[b],
+                      self.bn_bias[b])
+        self._plan.run()
+        for key, srcs in self.Bcat_src.items():
+            torch.cat(srcs, out=self.Bcat[key])
+        self._versions = sum(t._version for t in self.P.values())
+
+    # ================================================================================================ gradients
+    def _setup_grads(self, specs):
+        live = [s for s in specs if s.kind == "param" and not never_gets_grad(s.name)]
+        live.sort(key=lambda s: grad_stage(s.name))          # stable: spec order within a stage
+        byname = {s.name: s for s in live}
+        groups = []
+        for i in range(self.n_co):
+            p = f"co_att_transformer.{i}.biattention"
+            for sfx in ("1", "2"):
+                groups.append([f"{p}.{n}{sfx}.weight" for n in ("query", "key", "value")])
+                groups.append([f"{p}.{n}{sfx}.bias" for n in ("query", "key", "value")])
+        first = {g[0]: g for g in groups}
+        member = {n for g in groups for n in g}
+        order = []
+        for s in live:
+            if s.name in first:
+                order += first[s.name]
+            elif s.name not in member:
+                order.append(s.name)
+        total = 0
+        offs = {}
+        for n in order:
+            offs[n] = total
+            total += (math.prod(byname[n].shape) + 7) // 8 * 8 if n not in member else math.prod(byname[n].shape)
+        total = (total + 7) // 8 * 8
+        self.stage_end = [0] * N_STAGES                       # arena offset (elements) where each stage's gradients end
+        for n in order:
+            st = grad_stage(n)
+            self.stage_end[st] = max(self.stage_end[st], (offs[n] + math.prod(byname[n].shape) + 7) // 8 * 8)
+        for st in range(1, N_STAGES):
+            self.stage_end[st] = max(self.stage_end[st], self.stage_end[st - 1])
+        self.stage_end[-1] = total
+        self.on_stage_done = None                             # parallel.py: callable(stage) fired as backward finishes a stage
+        self.grad_arena = torch.zeros(total, device=self.dev, dtype=F32)
+        self.G = {n: self.grad_arena[offs[n]:offs[n] + math.prod(byname[n].shape)].view(byname[n].shape) for n in order}
+        self.live_names = order
+        for i in range(self.n_co):
+            p = f"co_att_transformer.{i}"
+            for sfx in ("1", "2"):
+                names = [f"{p}.biattention.{n}{sfx}" for n in ("query", "key", "value")]
+                o = offs[names[0] + ".weight"]
+                Dm = byname[names[0] + ".weight"].shape
+                self.G[f"{p}.qkv{sfx}.weight"] = self.grad_arena[o:o + 3 * Dm[0] * Dm[1]].view(3 * Dm[0], Dm[1])
+                o = offs[names[0] + ".bias"]
+                self.G[f"{p}.qkv{sfx}.bias"] = self.grad_arena[o:o + 3 * Dm[0]]
+        # packed [taps,O,I] accumulators for the 3x3 convs (unpacked into the Conv2d layout at the end of backward)
+        n3 = 0
+        self._g3 = []
+        for li, bi, inp, planes, s, ds in self.blocks:
+            if li >= 2:
+                self._g3.append((f"{BB}.layer{li}.{bi}.conv2.weight", planes, n3))
+                n3 += 9 * planes * planes
+        self.grad_pack = torch.zeros(n3, device=self.dev, dtype=F32)
+        self.Gp = {n: self.grad_pack[o:o + 9 * c * c].view(9, c, c) for n, c, o in self._g3}
+
+    # ================================================================================================ small helpers
+    def _done(self, stage):
+        if self.on_stage_done is not None:
+            self.on_stage_done(stage)
+
+    def _pos(self, H, W):
+        key = (H, W)
+        if key not in self._pos_cache:
+            self._pos_cache[key] = k.cast_bf16(sine_position_table(H, W, self.dev))
+        return self._pos_cache[key]
+
+    def _lin_bwd(self, name, x, dy, *, need_dx=True, aux=None, aux_mode=k.AUX_NONE, residual=None, wkey=None, gkey=None,
+                 bias=True):
+        """dW += dy^T x, db += colsum(dy), returns dx = (dy W + residual) (*) mask."""
+        g = gkey or name
+        k.linear_wgrad(dy, x, self.G[g + ".weight"].view(dy.shape[1], -1))
+        if bias:
+            k.colsum(dy, self.G[g + ".bias"])
+        if need_dx:
+            return k.linear_dgrad(dy, self.W[wkey or (name + ".weight")], aux=aux, aux_mode=aux_mode, residual=residual)
+        return None
+
+    # ================================================================================================ backbone
+    def _backbone_fwd(self, images, save):
+        W, bb = self.W, self.bn_bias
+        B = images.shape[0]
+        col, Ho, Wo = k.stem_im2col(images)
+        x = k.linear(col, W[f"{BB}.conv1.weight"], bb[f"{BB}.bn1"], act=RELU).view(B, Ho, Wo, 64)
+        del col
+        x = k.maxpool3x3s2(x)
+        acts = []
+        for blk in self.blocks:
+            y, saved = self._bottleneck_fwd(blk, x)
+            if save and blk[0] >= 2:
+                acts.append(saved)
+            x = y
+        return x, acts
+
+    def _bottleneck_fwd(self, blk, x):
+        """torchvision Bottleneck (v1.5) with FrozenBN folded: relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1 x))))))) + idn)."""
+        W, bb = self.W, self.bn_bias
+        li, bi, inp, planes, s, ds = blk
+        p = f"{BB}.layer{li}.{bi}"
+        n, H, Wd, _ = x.shape
+        h1 = k.linear(x.view(-1, inp), W[p + ".conv1.weight"][0], bb[p + ".bn1"], act=RELU).view(n, H, Wd, planes)
+        h2 = k.conv(h1, W[p + ".conv2.weight"], ksize=3, stride=s, bias=bb[p + ".bn2"], act=RELU)
+        Ho2, Wo2 = h2.shape[1], h2.shape[2]
+        if ds:
+            if s == 1:
+                idn = k.linear(x.view(-1, inp), W[p + ".downsample.0.weight"][0], bb[p + ".downsample.1"]).view(n, H, Wd, planes * 4)
+            else:
+                idn = k.conv(x, W[p + ".downsample.0.weight"], ksize=1, stride=s, bias=bb[p + ".downsample.1"])
+        else:
+            idn = x
+        y = k.linear(h2.view(-1, planes), W[p + ".conv3.weight"][0], bb[p + ".bn3"], residual=idn.view(-1, planes * 4),
+                     act=RELU).view(n, Ho2, Wo2, planes * 4)
+        return y, (x, h1, h2, y)
+
+    def _bottleneck_bwd(self, blk, dpre, saved, need_dx):
+        """Backward of one torchvision Bottleneck with FrozenBN.  dpre: gradient w.r.t. the block's pre-ReLU output
+        (already masked by relu'(y)).  Returns the masked gradient w.r.t. the previous block's pre-ReLU output."""
+        W, G, sc = self.W, self.G, self.bn_scale
+        li, bi, inp, planes, s, ds = blk
+        p = f"{BB}.layer{li}.{bi}"
+        x, h1, h2, y = saved
+        n, H, Wd, _ = x.shape
+        dpre2 = dpre.view(-1, planes * 4)
+        h2f, h1f, xf = h2.view(-1, planes), h1.view(-1, planes), x.view(-1, inp)
+        # conv3 (1x1)
+        dh2 = k.linear_dgrad(dpre2, W[p + ".conv3.weight"][0], aux=h2f, aux_mode=MASK_RELU)
+        k.linear_wgrad(dpre2, h2f, G[p + ".conv3.weight"].view(planes * 4, planes), rowscale=sc[p + ".bn3"])
+        # conv2 (3x3, stride s)
+        dh2 = dh2.view(h2.shape)
+        dh1 = conv_dgrad(dh2, W[p + ".conv2.weight"], ksize=3, stride=s, in_hw=(H, Wd), aux=h1, aux_mode=MASK_RELU)
+        k.conv_wgrad(dh2, h1, self.Gp[p + ".conv2.weight"], ksize=3, stride=s, rowscale=sc[p + ".bn2"])
+        # identity / downsample branch
+        if ds:
+            gds = G[p + ".downsample.0.weight"].view(1, planes * 4, inp)
+            if s == 1:
+                k.linear_wgrad(dpre2, xf, gds[0], rowscale=sc[p + ".downsample.1"])
+            else:
+                k.conv_wgrad(dpre, x, gds, ksize=1, stride=s, rowscale=sc[p + ".downsample.1"])
+            didn = conv_dgrad(dpre, W[p + ".downsample.0.weight"], ksize=1, stride=s, in_hw=(H, Wd)) if need_dx else None
+        else:
+            didn = dpre
+        # conv1 (1x1): dx = (dh1 W1 + didn) * relu'(x)  -> already the masked gradient of the previous block
+        k.linear_wgrad(dh1.view(-1, planes), xf, G[p + ".conv1.weight"].view(planes, inp), rowscale=sc[p + ".bn1"])
+        if not need_dx:
+            return None
+        return k.linear_dgrad(dh1.view(-1, planes), W[p + ".conv1.weight"][0], residual=didn.view(-1, inp), aux=xf,
+                              aux_mode=MASK_RELU).view(x.shape)
+
+    def _backbone_bwd(self, dpre, acts):
+        """dpre: gradient w.r.t. the pre-ReLU output of the last block (already masked), NHWC bf16."""
+        trainable = [b for b in self.blocks if b[0] >= 2]
+        for idx in range(len(trainable) - 1, -1, -1):
+            blk = trainable[idx]
+            li, bi = blk[0], blk[1]
+            saved, acts[idx] = acts[idx], None
+            dpre = self._bottleneck_bwd(blk, dpre, saved, need_dx=idx > 0)
+            if bi == 0:                                        # first block of layer `li` was the last one to finish
+                for name, c, _ in self._g3:
+                    if f".layer{li}." in name:
+                        k.unpack_conv_grad(self.Gp[name], self.G[name])
+                self._done({4: 4, 3: 5, 2: 6}[li])
+
+    # ================================================================================================ attention blocks
+    def _self_attn_fwd(self, p, x, pos, P_rows, B, S, H, *, causal=False, eps=1e-5, norm="norm1", attn="self_attn"):
+        """y = LN(x + out_proj(MHA(q = k = x + pos, v = x))).  x [B*S, D]; pos [P_rows, D] bf16 or None."""
+        W, Pm = self.W, self.P
+        D = x.shape[1]
+        wi, bi_ = W[f"{p}.{attn}.in_proj_weight"], Pm[f"{p}.{attn}.in_proj_bias"]
+        qkv = torch.empty((x.shape[0], 3 * D), device=self.dev, dtype=BF16)
+        if pos is not None:
+            qk_in = k.add_rowbcast(x, pos)
+            k.linear(qk_in, wi[:2 * D], bi_[:2 * D], out=qkv[:, :2 * D])
+            k.linear(x, wi[2 * D:], bi_[2 * D:], out=qkv[:, 2 * D:])
+        else:
+            qk_in = x
+            k.linear(x, wi, bi_, out=qkv)
+        dh = D // H
+        o, lse = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5,
+                                 causal=causal)
+        pre = k.linear(o, W[f"{p}.{attn}.out_proj.weight"], Pm[f"{p}.{attn}.out_proj.bias"], residual=x)
+        y, st = k.layernorm_fwd(pre, Pm[f"{p}.{norm}.weight"], Pm[f"{p}.{norm}.bias"], eps)
+        return y, (x, qk_in, qkv, o, lse, pre, st)
+
+    def _self_attn_bwd(self, p, dy, sv, pos_grad, B, S, H, *, causal=False, norm="norm1", attn="self_attn", has_pos=True):
+        """Returns dx.  pos_grad: fp32 [S, D] accumulator for a learned position (query_embed) or None."""
+        W, Pm, G = self.W, self.P, self.G
+        x, qk_in, qkv, o, lse, pre, st = sv
+        D = x.shape[1]
+        dh = D // H
+        dpre = k.layernorm_bwd(dy, pre, st, Pm[f"{p}.{norm}.weight"], G[f"{p}.{norm}.weight"], G[f"{p}.{norm}.bias"])
+        do = self._lin_bwd(f"{p}.{attn}.out_proj", o, dpre)
+        dqkv = torch.empty_like(qkv)
+        k.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                        B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5, causal=causal)
+        wi = W[f"{p}.{attn}.in_proj_weight"]
+        gw, gb = G[f"{p}.{attn}.in_proj_weight"], G[f"{p}.{attn}.in_proj_bias"]
+        k.colsum(dqkv, gb)
+        if not has_pos:
+            k.linear_wgrad(dqkv, x, gw)
+            return k.linear_dgrad(dqkv, wi, residual=dpre)
+        k.linear_wgrad(dqkv[:, :2 * D], qk_in, gw[:2 * D])
+        k.linear_wgrad(dqkv[:, 2 * D:], x, gw[2 * D:])
+        dx = k.linear_dgrad(dqkv[:, 2 * D:], wi[2 * D:], residual=dpre)
+        if pos_grad is None:
+            return k.linear_dgrad(dqkv[:, :2 * D], wi[:2 * D], residual=dx)
+        dqk_in = k.linear_dgrad(dqkv[:, :2 * D], wi[:2 * D])
+        k.batch_reduce(dqk_in, pos_grad, B, S)
+        return k.add(dx, dqk_in, out=dx)
+
+    def _cross_attn_fwd(self, p, x, qpos, kmem, vmem, B, Sq, Sk, H, *, eps=1e-5, norm="norm2"):
+        """y = LN(x + out_proj(MHA(q = x + qpos, k = kmem, v = vmem)))  (kmem already carries its position)."""
+        W, Pm = self.W, self.P
+        D = x.shape[1]
+        wi, bi_ = W[f"{p}.multihead_attn.in_proj_weight"], Pm[f"{p}.multihead_attn.in_proj_bias"]
+        q_in = k.add_rowbcast(x, qpos) if qpos is not None else x
+        q = k.linear(q_in, wi[:D], bi_[:D])
+        kv = torch.empty((kmem.shape[0], 2 * D), device=self.dev, dtype=BF16)
+        if kmem is vmem:
+            k.linear(kmem, wi[D:], bi_[D:], out=kv)
+        else:
+            k.linear(kmem, wi[D:2 * D], bi_[D:2 * D], out=kv[:, :D])
+            k.linear(vmem, wi[2 * D:], bi_[2 * D:], out=kv[:, D:])
+        dh = D // H
+        o, lse = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=dh ** -0.5)
+        pre = k.linear(o, W[f"{p}.multihead_attn.out_proj.weight"], Pm[f"{p}.multihead_attn.out_proj.bias"], residual=x)
+        y, st = k.layernorm_fwd(pre, Pm[f"{p}.{norm}.weight"], Pm[f"{p}.{norm}.bias"], eps)
+        return y, (x, q_in, q, kv, o, lse, pre, st)
+
+    def _cross_attn_bwd(self, p, dy, sv, kmem, vmem, dmem, pos_grad, B, Sq, Sk, H, *, norm="norm2"):
+        """Returns (dx, dmem) with dmem = dmem_in + d(kmem) + d(vmem) (chained through the GEMM residual input)."""
+        W, Pm, G = self.W, self.P, self.G
+        x, q_in, q, kv, o, lse, pre, st = sv
+        D = x.shape[1]
+        dh = D // H
+        a = f"{p}.multihead_attn"
+        dpre = k.layernorm_bwd(dy, pre, st, Pm[f"{p}.{norm}.weight"], G[f"{p}.{norm}.weight"], G[f"{p}.{norm}.bias"])
+        do = self._lin_bwd(a + ".out_proj", o, dpre)
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        k.attention_bwd(q, kv[:, :D], kv[:, D:], o, do, lse, dq, dkv[:, :D], dkv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh,
+                        scale=dh ** -0.5)
+        wi, gw, gb = W[a + ".in_proj_weight"], G[a + ".in_proj_weight"], G[a + ".in_proj_bias"]
+        k.colsum(dq, gb[:D])
+        k.colsum(dkv, gb[D:])
+        k.linear_wgrad(dq, q_in, gw[:D])
+        if kmem is vmem:
+            k.linear_wgrad(dkv, kmem, gw[D:])
+            dmem = k.linear_dgrad(dkv, wi[D:], residual=dmem)
+        else:
+            k.linear_wgrad(dkv[:, :D], kmem, gw[D:2 * D])
+            k.linear_wgrad(dkv[:, D:], vmem, gw[2 * D:])
+            dmem = k.linear_dgrad(dkv[:, :D], wi[D:2 * D], residual=dmem)
+            dmem = k.linear_dgrad(dkv[:, D:], wi[2 * D:], residual=dmem)
+        if pos_grad is None:
+            dx = k.linear_dgrad(dq, wi[:D], residual=dpre)
+        else:
+            dq_in = k.linear_dgrad(dq, wi[:D])
+            k.batch_reduce(dq_in, pos_grad, B, Sq)
+            dx = k.add(dpre, dq_in, out=dq_in)
+        return dx, dmem
+
+    def _ffn_fwd(self, w1, w2, ln, x, eps, act=RELU):
+        """y = LN(x + W2 act(W1 x + b1) + b2)."""
+        W, Pm = self.W, self.P
+        if act == GELU:
+            hpre = torch.empty((x.shape[0], W[w1 + ".weight"].shape[0]), device=self.dev, dtype=BF16)
+            h = k.linear(x, W[w1 + ".weight"], Pm[w1 + ".bias"], act=GELU, out2=hpre)
+        else:
+            h = k.linear(x, W[w1 + ".weight"], Pm[w1 + ".bias"], act=RELU)
+            hpre = h
+        pre = k.linear(h, W[w2 + ".weight"], Pm[w2 + ".bias"], residual=x)
+        y, st = k.layernorm_fwd(pre, Pm[ln + ".weight"], Pm[ln + ".bias"], eps)
+        return y, (x, h, hpre, pre, st)
+
+    def _ffn_bwd(self, w1, w2, ln, dy, sv, act=RELU):
+        Pm, G = self.P, self.G
+        x, h, hpre, pre, st = sv
+        dpre = k.layernorm_bwd(dy, pre, st, Pm[ln + ".weight"], G[ln + ".weight"], G[ln + ".bias"])
+        dh = self._lin_bwd(w2, h, dpre, aux=hpre, aux_mode=GRAD_GELU if act == GELU else MASK_RELU)
+        return self._lin_bwd(w1, x, dh, residual=dpre)
+
+    # ================================================================================================ BERT (no grad)
+    def _bert_fwd(self, ids):
+        """bert.py:11-22 / HF BertModel in eval mode; ids [B,T] int64 on device -> [B*T,768] bf16."""
+        P, W = self.P, self.W
+        b = "bert.model"
+        B, T = ids.shape
+        e = k.gather_rows(P[f"{b}.embeddings.word_embeddings.weight"], ids.reshape(-1), pos=P[f"{b}.embeddings.position_embeddings.weight"],
+                          cst=P[f"{b}.embeddings.token_type_embeddings.weight"], T=T)
+        x, _ = k.layernorm_fwd(e, P[f"{b}.embeddings.LayerNorm.weight"], P[f"{b}.embeddings.LayerNorm.bias"], 1e-12, need_stats=False)
+        D = x.shape[1]
+        for i in range(12):
+            p = f"{b}.encoder.layer.{i}"
+            qkv = k.linear(x, W[p + ".qkv"], self.Bcat[p + ".qkv"])
+            o, _ = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=12, Sq=T, Sk=T, dh=64, scale=0.125, need_lse=False)
+            pre = k.linear(o, W[p + ".attention.output.dense.weight"], P[p + ".attention.output.dense.bias"], residual=x)
+            x1, _ = k.layernorm_fwd(pre, P[p + ".attention.output.LayerNorm.weight"], P[p + ".attention.output.LayerNorm.bias"], 1e-12,
+                                    need_stats=False)
+            h = k.linear(x1, W[p + ".intermediate.dense.weight"], P[p + ".intermediate.dense.bias"], act=GELU)
+            pre = k.linear(h, W[p + ".output.dense.weight"], P[p + ".output.dense.bias"], residual=x1)
+            x, _ = k.layernorm_fwd(pre, P[p + ".output.LayerNorm.weight"], P[p + ".output.LayerNorm.bias"], 1e-12, need_stats=False)
+        return x
+
+    # ================================================================================================ co-attention
+    def _coatt_fwd(self, p, lang, vis, B, Tl, Q):
+        """vilbert.py:872-900 with tensor1 = language, tensor2 = vision (gpv.py:149-154)."""
+        W, Pm = self.W, self.P
+        D, H = self.D, self.h_co
+        dh = D // H
+        sc = 1.0 / math.sqrt(dh)
+        qkv1 = k.linear(lang, W[p + ".qkv1"], self.Bcat[p + ".qkv1"])
+        qkv2 = k.linear(vis, W[p + ".qkv2"], self.Bcat[p + ".qkv2"])
+        ctx1, lse1 = k.attention_fwd(qkv2[:, :D], qkv1[:, D:2 * D], qkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc)
+        ctx2, lse2 = k.attention_fwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
+        pa1 = k.linear(ctx2, W[p + ".biOutput.dense1.weight"], Pm[p + ".biOutput.dense1.bias"], residual=lang)
+        att1, sa1 = k.layernorm_fwd(pa1, Pm[p + ".biOutput.LayerNorm1.weight"], Pm[p + ".biOutput.LayerNorm1.bias"], 1e-12)
+        pa2 = k.linear(ctx1, W[p + ".biOutput.dense2.weight"], Pm[p + ".biOutput.dense2.bias"], residual=vis)
+        att2, sa2 = k.layernorm_fwd(pa2, Pm[p + ".biOutput.LayerNorm2.weight"], Pm[p + ".biOutput.LayerNorm2.bias"], 1e-12)
+        o1, f1 = self._ffn_fwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", att1, 1e-12, GELU)
+        o2, f2 = self._ffn_fwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", att2, 1e-12, GELU)
+        return o1, o2, (lang, vis, qkv1, qkv2, ctx1, lse1, ctx2, lse2, pa1, sa1, pa2, sa2, f1, f2)
+
+    def _coatt_bwd(self, p, do1, do2, sv, B, Tl, Q, need_dlang=True):
+        W, Pm, G = self.W, self.P, self.G
+        D, H = self.D, self.h_co
+        dh = D // H
+        sc = 1.0 / math.sqrt(dh)
+        lang, vis, qkv1, qkv2, ctx1, lse1, ctx2, lse2, pa1, sa1, pa2, sa2, f1, f2 = sv
+        datt1 = self._ffn_bwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", do1, f1, GELU)
+        datt2 = self._ffn_bwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", do2, f2, GELU)
+        dpa1 = k.layernorm_bwd(datt1, pa1, sa1, Pm[p + ".biOutput.LayerNorm1.weight"], G[p + ".biOutput.LayerNorm1.weight"],
+                               G[p + ".biOutput.LayerNorm1.bias"])
+        dpa2 = k.layernorm_bwd(datt2, pa2, sa2, Pm[p + ".biOutput.LayerNorm2.weight"], G[p + ".biOutput.LayerNorm2.weight"],
+                               G[p + ".biOutput.LayerNorm2.bias"])
+        dctx2 = self._lin_bwd(p + ".biOutput.dense1", ctx2, dpa1)
+        dctx1 = self._lin_bwd(p + ".biOutput.dense2", ctx1, dpa2)
+        dqkv1, dqkv2 = torch.empty_like(qkv1), torch.empty_like(qkv2)
+        k.attention_bwd(qkv2[:, :D], qkv1[:, D:2 * D], qkv1[:, 2 * D:], ctx1, dctx1, lse1, dqkv2[:, :D], dqkv1[:, D:2 * D],
+                        dqkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc)
+        k.attention_bwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], ctx2, dctx2, lse2, dqkv1[:, :D], dqkv2[:, D:2 * D],
+                        dqkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
+        dlang = self._lin_bwd(p + ".qkv1", lang, dqkv1, residual=dpa1, wkey=p + ".qkv1", need_dx=need_dlang)
+        dvis = self._lin_bwd(p + ".qkv2", vis, dqkv2, residual=dpa2, wkey=p + ".qkv2")
+        return dlang, dvis
+
+    # ================================================================================================ trunk forward
+    @torch.no_grad()
+    def encode(self, images, qids, save):
+        """gpv.py:137-175: everything up to `memory`.  Returns a dict of the tensors later stages need."""
+        self.refresh()
+        W, Pm = self.W, self.P
+        B = images.shape[0]
+        d, D, Q = self.d, self.D, self.Q
+        s = {"B": B}
+        c5, acts = self._backbone_fwd(images, save)
+        _, Hf, Wf, C5 = c5.shape
+        S = Hf * Wf
+        s.update(acts=acts, c5=c5, S=S, Hf=Hf, Wf=Wf)
+        c5f = c5.view(B * S, C5)
+        pos = self._pos(Hf, Wf)
+        x = k.linear(c5f, W["detr.input_proj.weight"], Pm["detr.input_proj.bias"])
+        enc = []
+        for i in range(self.n_enc):
+            p = f"detr.transformer.encoder.layers.{i}"
+            x, sa = self._self_attn_fwd(p, x, pos, S, B, S, self.h_detr)
+            x, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm2", x, 1e-5)
+            enc.append((sa, sf))
+        mem = x
+        mem_pos = k.add_rowbcast(mem, pos)
+        qe = W["detr.query_embed.weight"]
+        t = torch.zeros((B * Q, d), device=self.dev, dtype=BF16)
+        dec = []
+        for i in range(self.n_dec):
+            p = f"detr.transformer.decoder.layers.{i}"
+            t, sa = self._self_attn_fwd(p, t, qe, Q, B, Q, self.h_detr)
+            t, sc = self._cross_attn_fwd(p, t, qe, mem_pos, mem, B, Q, S, self.h_detr)
+            t, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm3", t, 1e-5)
+            dec.append((sa, sc, sf))
+        # heads (detr_roi_head.py:81-92).  detr_hs = [LN(roi) | hs] is written in place, no cat.
+        M = B * Q
+        detr_hs = torch.empty((M, C5 + d), device=self.dev, dtype=BF16)
+        hs = detr_hs[:, C5:]
+        _, st_dn = k.layernorm_fwd(t, Pm["detr.transformer.decoder.norm.weight"], Pm["detr.transformer.decoder.norm.bias"], 1e-5, out=hs)
+        lg_detr = torch.zeros((M, 8), device=self.dev, dtype=F32)
+        k.linear(hs, W["detr.class_embed.weight"], Pm["detr.class_embed.bias"], out=lg_detr)
+        y1 = k.linear(hs, W["detr.bbox_embed.layers.0.weight"], Pm["detr.bbox_embed.layers.0.bias"], act=RELU)
+        y2 = k.linear(y1, W["detr.bbox_embed.layers.1.weight"], Pm["detr.bbox_embed.layers.1.bias"], act=RELU)
+        boxes = torch.zeros((M, 8), device=self.dev, dtype=F32)
+        k.linear(y2, W["detr.bbox_embed.layers.2.weight"], Pm["detr.bbox_embed.layers.2.bias"], act=SIGMOID, out=boxes)
+        ldw = (S + 7) // 8 * 8
+        wroi = k.roi_weights(boxes, Hf, Wf, ldw)
+        roi_raw = torch.empty((M, C5), device=self.dev, dtype=BF16)
+        k.gemm(wroi, c5f, roi_raw, M=Q, N=C5, K=S, lda=ldw, ldb=C5, ldd=C5, b_mn=True, batch=B, a_bs=Q * ldw, b_bs=S * C5, d_bs=Q * C5)
+        _, st_roi = k.layernorm_fwd(roi_raw, None, None, 1e-5, out=detr_hs[:, :C5])
+        vis = k.linear(detr_hs, W["detr_joiner.weight"], Pm["detr_joiner.bias"])
+        s["detr_hs_joined"] = vis
+        # language stream
+        qe_b = self._bert_fwd(qids)
+        Tl = qids.shape[1]
+        lang = k.linear(qe_b, W["bert_joiner.weight"], Pm["bert_joiner.bias"])
+        co = []
+        for i in range(self.n_co):
+            lang, vis, sv = self._coatt_fwd(f"co_att_transformer.{i}", lang, vis, B, Tl, Q)
+            co.append(sv)
+        # relevance (gpv.py:162-175): logits = detr logits + Linear(vis); memory = [vis + softmax(logits) tokens | lang]
+        logits = torch.zeros((M, 8), device=self.dev, dtype=F32)
+        k.linear(vis, W["relevance_predictor.weight"], Pm["relevance_predictor.bias"], residual=lg_detr, out=logits)
+        Tm = Q + Tl
+        memory = torch.empty((B * Tm, D), device=self.dev, dtype=BF16)
+        if self.cfg.relevance_conditioning:
+            k.relevance_mix_fwd(vis, logits, Pm["relevance_tokens"], memory, G=Q, out_gstride=Tm, out_off=0)
+        else:
+            k.copy_rows(vis, memory, M, D, dst_map=(Q, Tm, 0))
+        k.copy_rows(lang, memory, B * Tl, D, dst_map=(Tl, Tm, Q))
+        s.update(pos=pos, enc=enc, mem=mem, mem_pos=mem_pos, dec=dec, t_final=t, st_dn=st_dn, detr_hs=detr_hs, y1=y1, y2=y2,
+                 boxes=boxes, wroi=wroi, ldw=ldw, roi_raw=roi_raw, st_roi=st_roi, qe_b=qe_b, Tl=Tl, co=co, vis=vis, lang=lang,
+                 logits=logits, memory=memory, Tm=Tm)
+        return s
+
+    @torch.no_grad()
+    def decode_text(self, tok_ids, memory, B, Sx, Tm, save):
+        """gpv.py:449-466 teacher-forced: tok_ids [B*Sx] int64 -> (logits fp32 [B*Sx, Vp], saved)."""
+        W, Pm = self.W, self.P
+        emb = k.gather_rows(Pm["answer_input_embedings.embedding_layer.weight"], tok_ids)
+        x = k.linear(emb, W["answer_input_embedings.transform.weight"], Pm["answer_input_embedings.transform.bias"])
+        layers = []
+        for i in range(self.n_txt):
+            p = f"text_decoder.layers.{i}"
+            x, sa = self._self_attn_fwd(p, x, None, 0, B, Sx, self.h_txt, causal=True)
+            x, sc = self._cross_attn_fwd(p, x, None, memory, memory, B, Sx, Tm, self.h_txt)
+            x, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm3", x, 1e-5)
+            layers.append((sa, sc, sf))
+        wc = k.linear(W["answer_head.vocab_embed"], W["answer_head.classifier_transform.weight"], Pm["answer_head.classifier_transform.bias"])
+        logits = torch.empty((B * Sx, self.Vp), device=self.dev, dtype=F32)
+        k.gemm(x, wc, logits, M=B * Sx, N=self.V, K=self.D, lda=x.stride(0), ldb=wc.stride(0), ldd=self.Vp)
+        return logits, (emb, layers, x, wc)
+
+    # ================================================================================================ training step
+    @torch.no_grad()
+    def forward_train(self, images, qids, ans_ids, tgt):
+        """images [B,3,H,W] fp32, qids [B,Tl] int64, ans_ids [B,S] int64 (device).  tgt: HostTargets (see gpv.py).
+        Returns (total_loss fp32 [1] on device, outputs dict)."""
+        s = self.encode(images, qids, save=True)
+        B, Q, D = s["B"], self.Q, self.D
+        M = B * Q
+        S = ans_ids.shape[1]
+        logits_v, sv_txt = self.decode_text(ans_ids.reshape(-1), s["memory"], B, S, s["Tm"], save=True)
+        # ---- criterion
+        loss_terms = torch.zeros(4, device=self.dev, dtype=F32)        # [answer CE (weighted), loss_ce, loss_bbox, loss_giou]
+        dlogits_v = torch.empty((B * S, self.Vp), device=self.dev, dtype=BF16)
+        if self.Vp != self.V:
+            dlogits_v.zero_()
+        k.ce_fwd_bwd(logits_v[:, :self.V], tgt.ce_targets, tgt.ce_row_weight, loss_terms[0:1], dlogits_v[:, :self.V])
+        dlg = torch.zeros((M, 8), device=self.dev, dtype=F32)
+        dbox = torch.zeros((M, 8), device=self.dev, dtype=BF16)
+        idx_q = idx_t = None
+        if tgt.n_loc > 0:
+            lg3, bx3 = s["logits"].view(B, Q, 8), s["boxes"].view(B, Q, 8)
+            if tgt.Tmax > 0:
+                cost = k.matcher_cost(lg3, bx3, tgt.boxes, tgt.labels, tgt.offsets, tgt.Tmax, *self.cost_w, C=2)
+                idx_q, idx_t = k.lsap(cost, tgt.offsets)
+            k.set_criterion(s["logits"], s["boxes"], tgt.boxes, tgt.offsets, idx_q, idx_t, tgt.loc_valid, eos_coef=self.eos_coef,
+                            weight_sum=tgt.weight_sum, num_boxes=tgt.num_boxes, wt_ce=self.loss_wts["loss_ce"],
+                            wt_bbox=self.loss_wts["loss_bbox"], wt_giou=self.loss_wts["loss_giou"], out3=loss_terms[1:4], dlogits=dlg,
+                            dbox_pre=dbox)
+        loss = (loss_terms * (self._wts_loc if tgt.n_loc else self._wts_noloc)).sum().reshape(1)
+        s.update(S_ans=S, sv_txt=sv_txt, dlogits_v=dlogits_v, dlg=dlg, dbox=dbox, loss_terms=loss_terms, idx_q=idx_q, idx_t=idx_t)
+        self.saved = s
+        return loss, s
+
+    @torch.no_grad()
+    def backward(self):
+        """Gradients of the last forward_train() into the arena (self.G).  Consumes the saved activations."""
+        s = self.saved
+        assert s is not None, "backward() without a forward_train()"
+        self.saved = None
+        W, Pm, G = self.W, self.P, self.G
+        self.grad_arena.zero_()
+        self.grad_pack.zero_()
+        B, Q, D, d = s["B"], self.Q, self.D, self.d
+        M, S, Tl, Tm, Sx = B * Q, s["S"], s["Tl"], s["Tm"], s["S_ans"]
+        # ---- answer head + text decoder
+        emb, layers, xf, wc = s["sv_txt"]
+        dlv = s["dlogits_v"]
+        dwc = torch.empty((self.V, D), device=self.dev, dtype=BF16)
+        k.gemm(dlv, xf, dwc, M=self.V, N=D, K=B * Sx, lda=dlv.stride(0), ldb=xf.stride(0), ldd=D, a_mn=True, b_mn=True)
+        self._lin_bwd("answer_head.classifier_transform", W["answer_head.vocab_embed"], dwc, need_dx=False)
+        dx = k.gemm(dlv, wc, torch.empty((B * Sx, D), device=self.dev, dtype=BF16), M=B * Sx, N=D, K=self.V, lda=dlv.stride(0),
+                    ldb=wc.stride(0), ldd=D, b_mn=True)
+        dmemory = None
+        for i in range(self.n_txt - 1, -1, -1):
+            p = f"text_decoder.layers.{i}"
+            sa, sc, sf = layers[i]
+            dx = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm3", dx, sf)
+            dx, dmemory = self._cross_attn_bwd(p, dx, sc, s["memory"], s["memory"], dmemory, None, B, Sx, Tm, self.h_txt)
+            dx = self._self_attn_bwd(p, dx, sa, None, B, Sx, self.h_txt, causal=True, has_pos=False)
+        self._lin_bwd("answer_input_embedings.transform", emb, dx, need_dx=False)
+        self._done(0)
+        # ---- memory split, relevance conditioning
+        dvis = torch.empty((M, D), device=self.dev, dtype=BF16)
+        dlang = torch.empty((B * Tl, D), device=self.dev, dtype=BF16)
+        k.copy_rows(dmemory, dvis, M, D, src_map=(Q, Tm, 0))
+        k.copy_rows(dmemory, dlang, B * Tl, D, src_map=(Tl, Tm, Q))
+        dlg = s["dlg"]
+        if self.cfg.relevance_conditioning:
+            k.relevance_mix_bwd(dmemory, s["logits"], Pm["relevance_tokens"], dlg, G["relevance_tokens"], M=M, G=Q, gstride=Tm, off=0)
+        dlg_b = k.cast_bf16(dlg)                                             # [M,8] bf16, columns 2.. are zero
+        dvis = self._lin_bwd("relevance_predictor", s["vis"], dlg_b[:, :2], residual=dvis)
+        # ---- co-attention
+        for i in range(self.n_co - 1, -1, -1):
+            dlang, dvis = self._coatt_bwd(f"co_att_transformer.{i}", dlang, dvis, s["co"][i], B, Tl, Q)
+        self._lin_bwd("bert_joiner", s["qe_b"], dlang, need_dx=False)
+        self._done(1)
+        # ---- detr_joiner, ROI head, box / class heads
+        detr_hs = s["detr_hs"]
+        C5 = detr_hs.shape[1] - d
+        d_hs_all = self._lin_bwd("detr_joiner", detr_hs, dvis)                 # [M, C5 + d]
+        hs = detr_hs[:, C5:]
+        dy2 = self._lin_bwd("detr.bbox_embed.layers.2", s["y2"], s["dbox"][:, :4], aux=s["y2"], aux_mode=MASK_RELU)
+        dy1 = self._lin_bwd("detr.bbox_embed.layers.1", s["y1"], dy2, aux=s["y1"], aux_mode=MASK_RELU)
+        dhs = self._lin_bwd("detr.bbox_embed.layers.0", hs, dy1, residual=d_hs_all[:, C5:])
+        dhs = self._lin_bwd("detr.class_embed", hs, dlg_b[:, :2], residual=dhs)
+        droi = k.layernorm_bwd(d_hs_all[:, :C5], s["roi_raw"], s["st_roi"], None, None, None)
+        dc5 = torch.empty((B * S, C5), device=self.dev, dtype=BF16)
+        k.gemm(s["wroi"], droi, dc5, M=S, N=C5, K=Q, lda=s["ldw"], ldb=C5, ldd=C5, a_mn=True, b_mn=True, batch=B,
+               a_bs=Q * s["ldw"], b_bs=Q * C5, d_bs=S * C5)
+        dt = k.layernorm_bwd(dhs, s["t_final"], s["st_dn"], Pm["detr.transformer.decoder.norm.weight"],
+                             G["detr.transformer.decoder.norm.weight"], G["detr.transformer.decoder.norm.bias"])
+        # ---- DETR decoder / encoder
+        gq = G["detr.query_embed.weight"]
+        dmem = None
+        for i in range(self.n_dec - 1, -1, -1):
+            p = f"detr.transformer.decoder.layers.{i}"
+            sa, sc, sf = s["dec"][i]
+            dt = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm3", dt, sf)
+            dt, dmem = self._cross_attn_bwd(p, dt, sc, s["mem_pos"], s["mem"], dmem, gq, B, Q, S, self.h_detr)
+            dt = self._self_attn_bwd(p, dt, sa, gq, B, Q, self.h_detr)
+        self._done(2)
+        dx = dmem
+        for i in range(self.n_enc - 1, -1, -1):
+            p = f"detr.transformer.encoder.layers.{i}"
+            sa, sf = s["enc"][i]
+            dx = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm2", dx, sf)
+            dx = self._self_attn_bwd(p, dx, sa, None, B, S, self.h_detr)
+        # ---- input_proj: dC5 = (dx Wip + dC5_roi) * relu'(c5)  -> masked gradient of the last bottleneck
+        c5f = s["c5"].view(B * S, C5)
+        dpre = self._lin_bwd("detr.input_proj", c5f, dx, residual=dc5, aux=c5f, aux_mode=MASK_RELU)
+        self._done(3)
+        self._backbone_bwd(dpre.view(s["c5"].shape), s["acts"])
+        return self.G

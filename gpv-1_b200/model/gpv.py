@@ -1,0 +1,398 @@
+"""Host-side mirror of the reference module surface for the hot path: `GPV` (exp/gpv/models/gpv.py:58-466).
+
+Same constructor config (`cfg.model` of configs/exp/gpv.yaml), same `state_dict()` keys and shapes (836 entries, so
+reference checkpoints load by name: inference.py:57-62, train_distr.py:264-272), same call signatures and return
+values:
+
+    loss = model(images, queries, answer_token_ids, targets)        # scalar; loss.backward() fills p.grad
+    out  = model(images, queries, None)                             # greedy decode (gpv.py:178-196)
+    out  = model.forward_beam_search(images, queries, beam_size)    # gpv.py:209-254
+
+All arithmetic runs in the sm_100a kernels through `Engine`; there is no PyTorch-op or CPU fallback -- constructing
+the engine on a machine without the built library or without a Blackwell GPU raises.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import kernels as k
+from .engine import Engine, TASK_LOSS
+from .spec import gpv_specs, never_gets_grad
+
+SPECIAL = ("__pad__", "__cls__", "__stop__", "__unk__")
+
+
+def positionalencoding1d(d_model, length):
+    """gpv.py:18-34 (sin/cos interleaved); only materialised as the frozen `pos_enc` parameter."""
+    pe = torch.zeros(length, d_model)
+    position = torch.arange(0, length).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float) * -(math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position.float() * div_term)
+    pe[:, 1::2] = torch.cos(position.float() * div_term)
+    return pe
+
+
+class _Node(nn.Module):
+    """Bare container so that parameters keep the reference's dotted names (e.g. detr.backbone.0.body.conv1.weight)."""
+
+
+def _register(root, dotted, tensor, kind):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    if kind == "buffer":
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=(kind == "param")))
+
+
+def _init_tensor(name, shape, g):
+    """Random init in the spirit of the reference constructors (xavier/kaiming-scale matrices, unit norms, identity BN)."""
+    if name.endswith(("running_var",)):
+        return torch.ones(shape)
+    if name.endswith(("running_mean",)):
+        return torch.zeros(shape)
+    is_norm = ".bn" in name or ".downsample.1." in name or "LayerNorm" in name or ".norm" in name
+    if is_norm:
+        return torch.ones(shape) if name.endswith("weight") else torch.zeros(shape)
+    if name == "criterion.localization_criterion.set_criterion.empty_weight":
+        return torch.ones(shape)
+    if name == "pos_enc":
+        return positionalencoding1d(shape[2], shape[1]).view(shape)
+    if len(shape) == 4:
+        return torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[1] * shape[2] * shape[3]))
+    if len(shape) == 2 and name not in ("relevance_tokens",):
+        if name.endswith("_embeddings.weight"):
+            return 0.02 * torch.randn(shape, generator=g)
+        if name == "detr.query_embed.weight":
+            return torch.randn(shape, generator=g)
+        return torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[0] + shape[1]))
+    if name in ("vision_token", "lang_token", "relevance_tokens"):
+        return 0.1 * torch.randn(shape, generator=g)
+    return torch.zeros(shape)
+
+
+class HostTargets:
+    """Per-step host bookkeeping of the criterion (losses.py:41-138, set_criterion.py:150-168): which rows carry which
+    loss weight, ragged target offsets, normalisers.  Built from Python-side shapes only -- no device sync."""
+
+    def __init__(self, targets, B, S, Q, loss_wts, eos_coef, device):
+        self.device = device
+        # ---- text losses: CE(reduction none).mean(0).sum(0).sum() per task (losses.py:20-26) -> weight wt/B' per row
+        counts = {}
+        for t in targets:
+            if "answer" in t and t.get("task") in TASK_LOSS:
+                counts[t["task"]] = counts.get(t["task"], 0) + 1
+        roww = np.zeros((B, S), np.float32)
+        tg_rows = []
+        zero_row = None
+        for b, t in enumerate(targets):
+            if "answer" in t and t.get("task") in TASK_LOSS:
+                roww[b, :S - 1] = loss_wts[TASK_LOSS[t["task"]]] / counts[t["task"]]
+                ids = t["answer_token_ids"]
+                if ids.shape[0] != S - 1:
+                    raise ValueError("targets[i]['answer_token_ids'] must be answer_token_ids[i, 1:] (train_distr.py:410-412)")
+                tg_rows.append(ids.to(device=device, dtype=torch.int64))
+            else:
+                if zero_row is None:
+                    zero_row = torch.zeros(S - 1, dtype=torch.int64, device=device)
+                tg_rows.append(zero_row)
+        tg = torch.zeros((B, S), dtype=torch.int64, device=device)
+        if S > 1:
+            tg[:, :S - 1] = torch.stack(tg_rows)
+        self.ce_targets = tg.view(-1)
+        self.n_text = sum(counts.values())
+        # ---- localisation: images that have a 'boxes' key (losses.py:101-121); T_b may be 0
+        sizes = [int(t["boxes"].shape[0]) if "boxes" in t else 0 for t in targets]
+        valid = [1 if "boxes" in t else 0 for t in targets]
+        self.n_loc = sum(valid)
+        self.Tmax = max(sizes) if sizes else 0
+        sumT = sum(sizes)
+        n_match = sum(min(Q, s) for s in sizes)
+        self.weight_sum = float(n_match + eos_coef * (self.n_loc * Q - n_match)) if self.n_loc else 1.0
+        self.num_boxes = float(max(sumT, 1))
+        host = np.zeros(B + 1 + B, np.int32)
+        host[1:B + 1] = np.cumsum(sizes)
+        host[B + 1:] = valid
+        hb = torch.from_numpy(np.concatenate([host.view(np.float32), roww.reshape(-1)])).pin_memory()
+        dv = hb.to(device, non_blocking=True)
+        self.offsets = dv[:B + 1].view(torch.int32)
+        self.loc_valid = dv[B + 1:2 * B + 1].view(torch.int32).to(torch.uint8)
+        self.ce_row_weight = dv[2 * B + 1:]
+        if sumT:
+            self.boxes = torch.cat([t["boxes"].to(device=device, dtype=torch.float32).reshape(-1, 4) for t in targets if "boxes" in t and t["boxes"].shape[0]])
+            lab = [t["labels"].to(device=device, dtype=torch.int64) for t in targets if "boxes" in t and t["boxes"].shape[0]]
+            self.labels = torch.cat(lab)
+        else:
+            self.boxes = torch.zeros((1, 4), device=device)
+            self.labels = torch.zeros(1, dtype=torch.int64, device=device)
+        self.sizes = sizes
+
+
+class _Step(torch.autograd.Function):
+    """One autograd node for the whole step: forward already ran in the engine; backward runs the engine's explicit
+    backward and hands each parameter its slice of the gradient arena."""
+
+    @staticmethod
+    def forward(ctx, anchor, loss, model):
+        ctx.model = model
+        return loss.clone().view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.model._run_backward(g)
+        return None, None, None
+
+
+class GPV(nn.Module):
+    def __init__(self, cfg, vocab=None, vocab_embed=None, seed=None):
+        """cfg: the `model:` block (attribute access).  vocab / vocab_embed override cfg.vocab / cfg.vocab_embed paths
+        (answer_head.py:61-74) when given as a list / array."""
+        super().__init__()
+        self.cfg = cfg
+        if vocab is None:
+            with open(cfg.vocab) as f:
+                vocab = json.load(f)
+        if vocab_embed is None and cfg.vocab_embed is not None:
+            vocab_embed = np.load(cfg.vocab_embed)
+        self.vocab = list(vocab)
+        self.word_to_idx = {w: i for i, w in enumerate(self.vocab)}
+        for w in SPECIAL:
+            if w not in self.word_to_idx:
+                raise ValueError(f"vocab lacks {w}")
+        V = len(self.vocab)
+        if cfg.roi_head is not True or cfg.answer_head == "linear" or cfg.detr.aux_loss or cfg.detr.pre_norm:
+            raise NotImplementedError("only the default GPV-1 variant (roi_head, generated answer head, post-norm, no aux loss) is built")
+        self.specs = gpv_specs(cfg, V)
+        g = torch.Generator().manual_seed(0 if seed is None else seed)
+        for s in self.specs:
+            t = _init_tensor(s.name, tuple(s.shape), g)
+            _register(self, s.name, t, s.kind)
+        if vocab_embed is not None:
+            ve = torch.as_tensor(np.asarray(vocab_embed), dtype=torch.float32)
+            if tuple(ve.shape) != (V, cfg.bert_joiner.bert_dim):
+                raise ValueError(f"vocab_embed must be [{V},{cfg.bert_joiner.bert_dim}]")
+        else:
+            ve = 0.1 * torch.randn(V, cfg.bert_joiner.bert_dim, generator=g)
+        with torch.no_grad():
+            self.answer_head.vocab_embed.copy_(ve)
+            self.answer_input_embedings.embedding_layer.weight.copy_(ve)
+            self.criterion.localization_criterion.set_criterion.empty_weight[-1] = cfg.losses.Localization.eos_coef
+        self.init_detr_params = []
+        self._engine = None
+        self._engine_key = None
+        self._anchor_t = None
+        self._tokenizer = None
+        self.grad_sync = None          # parallel.GradSync installs itself here
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    @property
+    def engine(self):
+        dev = self.vision_token.device
+        if dev.type != "cuda":
+            raise RuntimeError("GPV (gpv-1_b200) runs only on a CUDA sm_100a device: move the module with .cuda() first; "
+                               "there is no CPU path")
+        key = (dev, self.vision_token.data_ptr())
+        if self._engine is None or self._engine_key != key:
+            tensors = {n: t for n, t in self.state_dict(keep_vars=True).items()}
+            self._engine = Engine(tensors, self.specs, self.cfg, dev)
+            self._engine_key = key
+            self._live = [(n, tensors[n]) for n in self._engine.live_names]
+            if self.grad_sync is not None:
+                self.grad_sync.attach(self._engine)
+        return self._engine
+
+    def _anchor(self):
+        dev = self.vision_token.device
+        if self._anchor_t is None or self._anchor_t.device != dev:
+            self._anchor_t = torch.zeros(1, device=dev, requires_grad=True)
+        return self._anchor_t
+
+    def _run_backward(self, g):
+        eng = self.engine
+        eng.backward()
+        if self.grad_sync is not None:
+            self.grad_sync.finish()
+        if not eng.unit_upstream_grad:
+            eng.grad_arena.mul_(g)
+        for n, p in self._live:
+            gv = eng.G[n]
+            if p.grad is None or p.grad.data_ptr() != gv.data_ptr():
+                p.grad = gv
+
+    def load_pretr_detr(self):
+        """gpv.py:122-135: copy same-shaped tensors of a DETR checkpoint under the `detr.` prefix."""
+        loaded = torch.load(self.cfg.pretr_detr, map_location="cpu")["model"]
+        cur = self.state_dict()
+        for lk, v in loaded.items():
+            dk = "detr." + lk
+            if dk in cur and cur[dk].size() == v.size():
+                self.init_detr_params.append(dk)
+                cur[dk] = v
+        self.load_state_dict(cur)
+
+    # ------------------------------------------------------------------------------------------------ inputs
+    def _images(self, images):
+        dev = self.vision_token.device
+        if hasattr(images, "tensors") and hasattr(images, "mask"):
+            if images.mask is not None and bool(images.mask.any()):
+                raise NotImplementedError("padded (mixed-size) image batches are not built yet: resize to one size as the "
+                                          "reference data loader does (coco_generic_dataset.py:61)")
+            images = images.tensors
+        if isinstance(images, (list, tuple)):
+            if len({tuple(i.shape) for i in images}) != 1:
+                raise NotImplementedError("padded (mixed-size) image batches are not built yet")
+            images = torch.stack(list(images))
+        return images.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+    def _queries(self, queries):
+        dev = self.vision_token.device
+        if torch.is_tensor(queries):
+            return queries.to(device=dev, dtype=torch.int64, non_blocking=True)
+        if len(queries) and not isinstance(queries[0], str):
+            return torch.as_tensor(np.asarray(queries), dtype=torch.int64).to(dev, non_blocking=True)
+        if self._tokenizer is None:
+            from .tokenizer import load_tokenizer
+            self._tokenizer = load_tokenizer(getattr(self.cfg, "bert_vocab", None))
+        ids = self._tokenizer(list(queries))
+        return torch.as_tensor(ids, dtype=torch.int64).to(dev, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, images, queries, answer_token_ids, targets=None, vocab_mask=None):
+        eng = self.engine
+        images, qids = self._images(images), self._queries(queries)
+        B, Q = images.shape[0], self.cfg.detr.num_queries
+        if answer_token_ids is not None and targets is not None:
+            ans = answer_token_ids.to(device=images.device, dtype=torch.int64)
+            S = ans.shape[1]
+            tgt = HostTargets(targets, B, S, Q, eng.loss_wts, eng.eos_coef, images.device)
+            if tgt.n_text == 0 and tgt.n_loc == 0:
+                return None
+            loss, _ = eng.forward_train(images, qids, ans, tgt)
+            if torch.is_grad_enabled():
+                return _Step.apply(self._anchor(), loss, self)
+            eng.saved = None
+            return loss.view(())
+        with torch.no_grad():
+            s = eng.encode(images, qids, save=False)
+            outputs = self._outputs(s)
+            if answer_token_ids is None:
+                outputs["answer_logits"] = self._greedy(s, vocab_mask)
+            else:
+                ans = answer_token_ids.to(device=images.device, dtype=torch.int64)
+                S = ans.shape[1]
+                lg, _ = eng.decode_text(ans.reshape(-1), s["memory"], B, S, s["Tm"], save=False)
+                outputs["answer_logits"] = lg.view(1, B, S, -1)[:, :, :-1, :eng.V]
+            if targets is not None:
+                raise ValueError("targets given without answer_token_ids")
+        return outputs
+
+    def _outputs(self, s):
+        B, Q = s["B"], self.cfg.detr.num_queries
+        return {"pred_relevance_logits": s["logits"].view(B, Q, 8)[:, :, :2], "pred_boxes": s["boxes"].view(B, Q, 8)[:, :, :4],
+                "detr_hs": s["detr_hs_joined"].float().view(1, B, Q, -1)}
+
+    def _greedy(self, s, vocab_mask):
+        """gpv.py:178-196: append the arg-max token max_text_len-1 times, then return the logits of the full sequence."""
+        eng = self.engine
+        B = s["B"]
+        ids = torch.full((B, 1), self.word_to_idx["__cls__"], dtype=torch.int64, device=eng.dev)
+        vm = vocab_mask.to(eng.dev).float() if vocab_mask is not None else None
+        lg = None
+        for t in range(self.cfg.max_text_len):
+            lg, _ = eng.decode_text(ids.reshape(-1), s["memory"], B, ids.shape[1], s["Tm"], save=False)
+            lg = lg.view(B, ids.shape[1], -1)[:, :, :eng.V]
+            if vm is not None:
+                lg = lg + vm
+            if t == self.cfg.max_text_len - 1:
+                break
+            ids = torch.cat((ids, lg[:, -1].argmax(-1, keepdim=True)), 1)
+        return lg.unsqueeze(0)
+
+    def forward_beam_search(self, images, queries, beam_size=1):
+        eng = self.engine
+        images, qids = self._images(images), self._queries(queries)
+        with torch.no_grad():
+            s = eng.encode(images, qids, save=False)
+            outputs = self._outputs(s)
+            seqs, logp = self._beam(s, beam_size)
+        seqs_h, p_h = seqs.cpu().tolist(), logp.exp().cpu().tolist()
+        stop = {self.word_to_idx["__stop__"], self.word_to_idx["__pad__"]}
+        answers = []
+        for b in range(len(seqs_h)):
+            answers.append([])
+            for kk in range(beam_size):
+                words = []
+                for t in seqs_h[b][kk]:
+                    if t in stop:
+                        break
+                    words.append(self.vocab[t])
+                answers[b].append(words)
+        outputs["answers"] = answers
+        outputs["answer_probs"] = p_h
+        outputs["beam_token_ids"] = seqs
+        return outputs
+
+    def _beam(self, s, K):
+        """gpv.py:256-328 with the beams folded into the batch (row b*K + k); bookkeeping stays on the device.
+        Candidate order (k1 major, k2 minor), first-occurrence tie break, beam 0 only at t = 0, __stop__ never ends a beam."""
+        eng = self.engine
+        B, Tm, D = s["B"], s["Tm"], eng.D
+        mem = s["memory"].view(B, 1, Tm, D).expand(B, K, Tm, D).reshape(B * K * Tm, D).contiguous()
+        ids = torch.full((B, K, 1), self.word_to_idx["__cls__"], dtype=torch.int64, device=eng.dev)
+        score = torch.zeros((B, K), device=eng.dev)
+        for t in range(self.cfg.max_text_len - 1):
+            L = ids.shape[2]
+            lg, _ = eng.decode_text(ids.reshape(-1), mem, B * K, L, Tm, save=False)
+            last = lg.view(B, K, L, -1)[:, :, -1, :eng.V]
+            top = torch.log_softmax(last, -1).topk(K, -1)
+            cand = score[:, :, None] + top.values
+            if t == 0:
+                cand[:, 1:] = -1e9
+            flat = cand.reshape(B, K * K)
+            order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, :K]
+            k1 = torch.div(order, K, rounding_mode="floor")
+            new_last = torch.gather(top.indices.reshape(B, K * K), 1, order)
+            ids = torch.cat((torch.gather(ids, 1, k1[:, :, None].expand(-1, -1, L)), new_last[:, :, None]), 2)
+            score = torch.gather(flat, 1, order)
+        return ids[:, :, 1:], score
+
+    # ------------------------------------------------------------------------------------------------ answers (host)
+    def encode_answers(self, targets):
+        """gpv.py:377-430 (generation / classification answer encoding; whitespace + punctuation tokenisation stands in
+        for nltk.word_tokenize when nltk is absent)."""
+        from .tokenizer import word_tokenize
+        answers = [t.get("answer", "") for t in targets]
+        w2i = self.word_to_idx
+        unk = w2i["__unk__"]
+        if self.cfg.answering_type == "classification":
+            padded = [["__cls__", a] for a in answers]
+            ids = [[w2i.get(tok, unk) for tok in row] for row in padded]
+        elif self.cfg.answering_type == "generation":
+            padded = []
+            for a in answers:
+                sent = "__cls__ __stop__" if a == "" else f"__cls__ {a} __stop__"
+                padded.append([w.lower() for w in word_tokenize(sent)])
+            S = max(len(p) for p in padded)
+            ids = []
+            for p in padded:
+                p.extend(["__pad__"] * (S - len(p)))
+                ids.append([w2i.get(tok, unk) for tok in p][: self.cfg.max_text_len])
+        else:
+            raise NotImplementedError
+        return padded, torch.as_tensor(ids, dtype=torch.int64).to(self.vision_token.device)
+
+    def token_ids_to_words(self, token_ids):
+        ids = token_ids.tolist() if torch.is_tensor(token_ids) else token_ids
+        return [[self.vocab[j] for j in row] for row in ids]
+
+    @property
+    def cls_token(self):
+        raise NotImplementedError("cls_token (unused by the reference's own call sites) is not exposed")

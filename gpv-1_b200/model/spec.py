@@ -131,3 +131,25 @@ def gpv_specs(cfg, V):
 # the indicator tokens (never used), and BertBiOutput.q_dense1/2 (vilbert.py:835-843, unused in forward 845-856).
 def never_gets_grad(name):
     return name.startswith("bert.") or name in ("vision_token", "lang_token") or ".biOutput.q_dense" in name
+
+
+# Backward completes the gradient arena in this order; the data-parallel all-reduce is bucketed along it
+# (parallel.py) so that every bucket but the last is reduced underneath the remaining backward kernels.
+N_STAGES = 7
+
+
+def grad_stage(name):
+    if name.startswith(("text_decoder.", "answer_head.", "answer_input_embedings.")):
+        return 0
+    if name.startswith(("co_att_transformer.", "relevance_predictor.", "bert_joiner.")) or name == "relevance_tokens":
+        return 1
+    if name.startswith("detr.backbone."):
+        for li, st in ((4, 4), (3, 5), (2, 6)):
+            if f".layer{li}." in name:
+                return st
+        raise KeyError(name)
+    if name.startswith(("detr.transformer.encoder.", "detr.input_proj.")):
+        return 3
+    if name.startswith(("detr.", "detr_joiner.")):
+        return 2
+    raise KeyError(name)

@@ -97,8 +97,8 @@ int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream);
 /* Cost blocks C[b][q][t] = w_bbox*L1 + w_class*(-softmax(logits[b,q])[label]) + w_giou*(-GIoU), fp32, in the
  * reference's op order (matcher.py:53-72).  Targets are ragged: image b owns rows tgt_offsets[b]..tgt_offsets[b+1]
  * of tgt_boxes/tgt_labels.  cost is written as B dense blocks [Q][Tmax] (row stride Tmax). */
-int gpvb200_matcher_cost(const float* logits /*[B,Q,C]*/, const float* boxes /*[B,Q,4] cxcywh*/,
-                         const float* tgt_boxes /*[sumT,4]*/, const int64_t* tgt_labels /*[sumT]*/,
+int gpvb200_matcher_cost(const float* logits /*[B*Q] rows of C, row stride ldl*/, int64_t ldl,
+                         const float* boxes /*[B*Q] rows of 4 (cxcywh), row stride ldb*/, int64_t ldb, const float* tgt_boxes /*[sumT,4]*/, const int64_t* tgt_labels /*[sumT]*/,
                          const int32_t* tgt_offsets /*[B+1]*/, int32_t B, int32_t Q, int32_t C, int32_t Tmax,
                          float w_class, float w_bbox, float w_giou, float* cost /*[B,Q,Tmax]*/, void* stream);
 /* Rectangular linear sum assignment per image, shortest augmenting path in float64 with scipy's visiting
@@ -168,6 +168,10 @@ int gpvb200_gather_rows(const float* table, const int64_t* ids, const float* pos
 int gpvb200_copy_rows(const void* src, int64_t lds, int32_t sG, int32_t sgs, int32_t soff, void* dst, int64_t ldd, int32_t dG,
                       int32_t dgs, int32_t doff, int64_t M, int32_t D, void* stream);
 int gpvb200_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* conv weight gradient: packed fp32 [taps][O][I] -> Conv2d master layout [O][I][taps]; dst = src or dst += src */
+int gpvb200_unpack_conv_grad(const float* src, float* dst, int32_t O, int32_t I, int32_t taps, int32_t accumulate, void* stream);
+/* out = a + b on bf16 rows (gradient joins of residual branches) */
+int gpvb200_add_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t M, int32_t D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Criterion (losses.py:20-26,155-176; utils/set_criterion.py:44-62,78-97)

@@ -107,24 +107,28 @@ def sine_position(mask, num_pos_feats=128, temperature=10000.0):
 
 
 # ------------------------------------------------------------------------------------------------ DETR
-def detr_forward(P, images, mask=None, nheads=8, n_enc=6, n_dec=6):
+def detr_forward(P, images, mask=None, nheads=8, n_enc=6, n_dec=6, trace=None):
     """images [B,3,H,W]; mask [B,H,W] bool or None (no padding).  Returns dict like detr_roi_head.DETR.forward."""
     B = images.shape[0]
     if mask is None:
         mask = torch.zeros(images.shape[0], images.shape[2], images.shape[3], dtype=torch.bool, device=images.device)
+    tr = trace if trace is not None else {}
     c5 = resnet50_c5(P, images)
+    tr["c5"] = c5
     H, W = c5.shape[-2:]
     m = F.interpolate(mask[None].float(), size=(H, W)).to(torch.bool)[0]
     pos = sine_position(m).flatten(2).transpose(1, 2)                      # [B,HW,256]
     kpm = m.flatten(1)
     src = F.conv2d(c5, P["detr.input_proj.weight"], P["detr.input_proj.bias"]).flatten(2).transpose(1, 2)
     x = src
+    tr["src"] = src
     for i in range(n_enc):
         p = f"detr.transformer.encoder.layers.{i}"
         qk = x + pos
         x = ln(P, p + ".norm1", x + mha(P, p + ".self_attn", qk, qk, x, nheads, kpm), 1e-5)
         ff = lin(P, p + ".linear2", F.relu(lin(P, p + ".linear1", x)))
         x = ln(P, p + ".norm2", x + ff, 1e-5)
+        tr[f"enc{i}"] = x
     memory = x
     qpos = P["detr.query_embed.weight"][None].expand(B, -1, -1)
     t = torch.zeros_like(qpos)
@@ -135,13 +139,16 @@ def detr_forward(P, images, mask=None, nheads=8, n_enc=6, n_dec=6):
         t = ln(P, p + ".norm2", t + mha(P, p + ".multihead_attn", t + qpos, memory + pos, memory, nheads, kpm), 1e-5)
         ff = lin(P, p + ".linear2", F.relu(lin(P, p + ".linear1", t)))
         t = ln(P, p + ".norm3", t + ff, 1e-5)
+        tr[f"dec{i}"] = t
     hs = ln(P, "detr.transformer.decoder.norm", t, 1e-5)                    # last layer only  [B,Q,256]
     logits = lin(P, "detr.class_embed", hs)
     y = F.relu(lin(P, "detr.bbox_embed.layers.0", hs))
     y = F.relu(lin(P, "detr.bbox_embed.layers.1", y))
     boxes = lin(P, "detr.bbox_embed.layers.2", y).sigmoid()
     roi = roi_mean(c5, boxes)
+    tr["roi_raw"] = roi
     roi = F.layer_norm(roi, (roi.shape[-1],))
+    tr["hs"] = hs
     return {"pred_relevance_logits": logits, "pred_boxes": boxes, "detr_hs": torch.cat((roi, hs), -1), "c5": c5}
 
 
@@ -222,15 +229,18 @@ def embed_answer(P, ids):
 
 
 # ------------------------------------------------------------------------------------------------ encode (shared trunk)
-def gpv_encode(P, images, query_ids, mask=None, n_co=3):
+def gpv_encode(P, images, query_ids, mask=None, n_co=3, trace=None):
     """gpv.py:137-175 up to `memory`.  Returns (outputs dict, memory [B,Q+Tl,D])."""
-    out = detr_forward(P, images, mask)
+    tr = trace if trace is not None else {}
+    out = detr_forward(P, images, mask, trace=tr)
     vis = joined = lin(P, "detr_joiner", out["detr_hs"])
     with torch.no_grad():
         qe = bert_forward(P, query_ids)
     lang = lin(P, "bert_joiner", qe.detach())
+    tr["bert"], tr["lang_in"], tr["vis_in"] = qe, lang, vis
     for i in range(n_co):
         lang, vis = co_attention_layer(P, f"co_att_transformer.{i}", lang, vis)
+        tr[f"co{i}_lang"], tr[f"co{i}_vis"] = lang, vis
     logits = out["pred_relevance_logits"] + lin(P, "relevance_predictor", vis)
     prob = logits.softmax(-1)
     vis = vis + prob @ P["relevance_tokens"]
@@ -380,7 +390,9 @@ def make_state(specs, seed=0, device="cpu"):
         elif name.endswith("running_mean"):
             t = 0.1 * torch.randn(shape, generator=g)
         elif ".bn" in name or ".downsample.1." in name:
-            t = (1.0 + 0.1 * torch.randn(shape, generator=g)) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
+            # the last BN of a bottleneck gets a small gain so that 16 residual adds keep C5 at O(1) magnitudes
+            gain = 0.3 if ".bn3." in name else (0.7 if ".downsample.1." in name else 1.0)
+            t = gain * (1.0 + 0.1 * torch.randn(shape, generator=g)) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
         elif "LayerNorm" in name or ".norm" in name:
             t = (1.0 + 0.1 * torch.randn(shape, generator=g)) if name.endswith("weight") else 0.05 * torch.randn(shape, generator=g)
         elif name == "criterion.localization_criterion.set_criterion.empty_weight":

@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the GPV-1 data-parallel training hot path (BASELINE.json: samples/sec, img+query fwd+bwd).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # this repo's sm_100a path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                      # one rank per GPU, weak scaling (32 samples / GPU)
+    python bench.py --impl reference --steps K --warmup W           # the reference arithmetic (fp32 oracle port) on host cores
+
+Workload (BASELINE.json configs[1]; SURVEY.md 8d "Config 2"): per GPU a batch of 32 synthetic 3x480x640 images,
+20-token prompts, 20-token teacher-forced answers (CocoCaptioning), 1-8 target boxes per image, random-init weights of
+the GPV-1 architecture (227 M parameters, V = 8192), one step = GPV.forward(images, queries, answer_token_ids, targets)
+-> loss.backward() including the Hungarian-matched criterion and, for N > 1, the bucketed gradient all-reduce.
+Prints ONE JSON line (see the task contract): `value` with inputs resident in HBM, `e2e` through the public module API
+from pinned host buffers with a device->host read of the loss every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V_BENCH = 8192
+H_IMG, W_IMG, T_L, S_ANS = 480, 640, 20, 20
+RESNET = [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]
+
+
+# ---------------------------------------------------------------------------------------------------- algorithmic work
+def algorithmic_gflop(B, H=H_IMG, W=W_IMG, Tl=T_L, S=S_ANS, V=V_BENCH, Q=100):
+    """(forward, forward+backward) GFLOP per SAMPLE, 2 FLOP per MAC, from the layer shapes.
+    Backward = data gradient + weight gradient (2x forward) wherever a gradient flows; none for the frozen stem/layer1
+    and BERT (gpv.py:142-145); weight gradient only where no upstream data gradient is needed."""
+    fwd = bwd = 0.0
+    h, w = (H + 1) // 2, (W + 1) // 2
+    fwd += 2 * h * w * 64 * 147
+    h, w = (h + 1) // 2, (w + 1) // 2
+    inp = 64
+    for li, (planes, blocks, stride) in enumerate(RESNET, start=1):
+        for bi in range(blocks):
+            s = stride if bi == 0 else 1
+            ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+            convs = [(h * w, planes, inp, 1), (ho * wo, planes, planes, 9), (ho * wo, planes * 4, planes, 1)]
+            if bi == 0:
+                convs.append((ho * wo, planes * 4, inp, 1))
+            for ci, (pix, co, cin, kk) in enumerate(convs):
+                f = 2 * pix * co * cin * kk
+                fwd += f
+                if li >= 2:
+                    first = li == 2 and bi == 0 and ci in (0, 3)      # layer2.0 conv1 / downsample: no data gradient
+                    bwd += f if first else 2 * f
+            h, w, inp = ho, wo, planes * 4
+    Sv, d, D = h * w, 256, 768
+
+    def both(f):
+        nonlocal fwd, bwd
+        fwd += f
+        bwd += 2 * f
+
+    both(2 * Sv * 2048 * d)                                                        # input_proj
+    both(6 * (4 * 2 * Sv * d * d + 4 * 8 * Sv * Sv * 32 + 2 * 2 * Sv * d * 2048))  # DETR encoder
+    both(6 * (4 * 2 * Q * d * d + 4 * 8 * Q * Q * 32 + 2 * 2 * Q * d * d + 2 * 2 * Sv * d * d + 4 * 8 * Q * Sv * 32
+              + 2 * 2 * Q * d * 2048))                                             # DETR decoder
+    both(2 * Q * d * 2 + 2 * Q * (2 * d * d + d * 4) + 2 * Q * Sv * 2048 + 2 * Q * 2304 * D)   # heads, ROI, detr_joiner
+    fwd += 12 * (4 * 2 * Tl * D * D + 4 * 12 * Tl * Tl * 64 + 2 * 2 * Tl * D * 3072)           # BERT (no backward)
+    fwd += 2 * Tl * D * D
+    bwd += 2 * Tl * D * D                                                          # bert_joiner: weight gradient only
+    both(3 * (2 * (Tl + Q) * D * 3 * D + 2 * 4 * 16 * Q * Tl * 48 + 2 * (Tl + Q) * D * D + 2 * 2 * (Tl + Q) * D * 3072))
+    both(2 * Q * D * 2)
+    Tm = Q + Tl
+    fwd += 2 * S * D * D
+    bwd += 2 * S * D * D
+    both(3 * (4 * 2 * S * D * D + 4 * 8 * S * S * 96 + 2 * 2 * S * D * D + 2 * 2 * Tm * D * D + 4 * 8 * S * Tm * 96 + 2 * 2 * S * D * 2048))
+    both(2 * V * D * D / B + 2 * S * D * V)                                        # answer head (classifier once per batch)
+    return fwd / 1e9, (fwd + bwd) / 1e9
+
+
+# ---------------------------------------------------------------------------------------------------- synthetic batch
+def make_batch(B, seed, V=V_BENCH):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(B, 3, H_IMG, W_IMG, generator=g)
+    qids = torch.randint(1000, 30000, (B, T_L), generator=g)
+    ans = torch.randint(4, V, (B, S_ANS), generator=g)
+    ans[:, 0], ans[:, -1] = 1, 2
+    targets = []
+    for b in range(B):
+        nb = int(torch.randint(1, 9, (1,), generator=g))
+        cxcy = 0.25 + 0.5 * torch.rand(nb, 2, generator=g)
+        wh = 0.05 + 0.3 * torch.rand(nb, 2, generator=g)
+        targets.append({"task": "CocoCaptioning", "answer": "x", "boxes": torch.cat((cxcy, wh), -1),
+                        "labels": torch.zeros(nb, dtype=torch.long), "answer_token_ids": ans[b, 1:]})
+    return images, qids, ans, targets
+
+
+def vocab_list(V):
+    return ["__pad__", "__cls__", "__stop__", "__unk__"] + [f"w{i}" for i in range(V - 4)]
+
+
+# ---------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._pump, daemon=True).start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_steps(steps, warmup, B_cpu=2, seed=1):
+    """The reference's arithmetic (fp32 oracle port of GPV.forward + criterion + autograd backward) on the host cores.
+    Each step is a bounded sample of the workload: B_cpu images of the same shape instead of 32."""
+    from oracle import torch_oracle as TO
+    import oracle
+    oracle.build()
+    from gpv1_b200.config import load_config
+    from gpv1_b200.model.spec import gpv_specs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = load_config()
+    specs = gpv_specs(cfg.model, V_BENCH)
+    P = TO.make_state([(s.name, s.shape, s.kind) for s in specs], seed=0)
+    Pg = {n: (t.requires_grad_(True) if s.kind == "param" and not n.startswith("bert.") else t) for (n, t), s in zip(P.items(), specs)}
+    images, qids, ans, targets = make_batch(B_cpu, seed)
+    times = []
+    for i in range(warmup + steps):
+        for t in Pg.values():
+            t.grad = None
+        t0 = time.perf_counter()
+        loss = TO.gpv_forward(Pg, images, qids, ans, targets)
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+    timed = times[warmup:]
+    sps = B_cpu * len(timed) / sum(timed)
+    return sps, cores, f"{len(timed)} steps of {B_cpu} samples (3x{H_IMG}x{W_IMG}, Tl={T_L}, S={S_ANS}, V={V_BENCH}) fp32 torch on {cores} host threads", \
+        1e3 * sum(timed) / len(timed)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 6))
+    warmup = max(1, min(args.warmup, 1))
+    sps, cores, sample, ms = cpu_reference_steps(steps, warmup)
+    line = {"impl": "reference", "metric": "samples/sec (img+query fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(32)},
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(B):
+    return f"configs[1]: batch={B}/GPU synthetic 3x{H_IMG}x{W_IMG} + {T_L}-tok prompts + {S_ANS}-tok answers, full fwd+bwd with SetCriterion, V={V_BENCH}"
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiling", action="store_true", help="under ncu only: allow fewer than 3 warm-up steps, skip the e2e loop")
+    ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown of one extra step to this file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not args.profiling:
+        args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gpv1_b200 import _C
+    from gpv1_b200.config import load_config
+    from gpv1_b200.model import GPV
+    from gpv1_b200.parallel import GradSync, broadcast_parameters
+    cfg = load_config()
+    B = args.batch
+    model = GPV(cfg.model, vocab=vocab_list(V_BENCH), seed=0).to(dev)
+    sync = GradSync(model) if world > 1 else None
+    broadcast_parameters(model)
+
+    images, qids, ans, targets = make_batch(B, seed=1000 + rank)
+    # resident copies (for `value`) and pinned host copies (for `e2e`)
+    d_images, d_qids, d_ans = images.to(dev), qids.to(dev), ans.to(dev)
+    d_targets = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
+    h_images, h_qids, h_ans = images.pin_memory(), qids.pin_memory(), ans.pin_memory()
+    h_targets = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
+
+    def step_resident():
+        loss = model(d_images, d_qids, d_ans, d_targets)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        loss = model(h_images, h_qids, h_ans, h_targets)
+        loss.backward()
+        return loss.item()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step_resident()
+    lib = _C.lib()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.launches
+    ms = timed(step_resident, args.steps)
+    launches = (lib.launches - n0) // args.steps
+    if args.profiling:
+        print(json.dumps({"profiling": True, "ms_per_step_under_profiler": ms / args.steps, "launches_per_step": launches}))
+        return
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = step_e2e()
+
+    breakdown = None
+    if rank == 0 and args.breakdown:
+        lib.trace = []
+        step_resident()
+        torch.cuda.synchronize()
+        tr, lib.trace = lib.trace, None
+        agg = {}
+        for name, a, e0, e1 in tr:
+            key = name.replace("gpvb200_", "")
+            if name == "gpvb200_gemm":
+                d = a[0]._obj
+                kind = {(0, 0): "fwd", (0, 1): "dgrad", (1, 1): "wgrad", (1, 0): "a_mn"}[(d.a_mn, d.b_mn)]
+                if d.mode == 0:
+                    key = f"gemm {kind} M{d.M} N{d.N} K{d.K} b{d.batch} s{d.splits}"
+                elif d.mode == 1:
+                    key = f"conv {kind} {d.n_img}x{d.Ho}x{d.Wo} N{d.N} K{d.K} taps{d.ntaps} st{d.stride}"
+                else:
+                    key = f"conv wgrad {d.n_img}x{d.Ho}x{d.Wo} M{d.M} N{d.N} taps{d.ntaps} st{d.stride} s{d.splits}"
+            t = e0.elapsed_time(e1)
+            c = agg.setdefault(key, [0, 0.0])
+            c[0] += 1
+            c[1] += t
+        breakdown = {kk: {"calls": v[0], "ms": round(v[1], 3)} for kk, v in sorted(agg.items(), key=lambda x: -x[1][1])}
+        with open(args.breakdown, "w") as f:
+            json.dump({"note": "CUDA-event time per C-ABI entry point over one extra step (serialised by the events; shares, not absolutes)",
+                       "ms_per_step_untraced": ms / args.steps, "entries": breakdown}, f, indent=1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms / args.steps
+    sps = world * B * args.steps / (ms / 1e3)
+    sps_e2e = world * B * args.steps / (ms_e2e / 1e3)
+    gf_fwd, gf_all = algorithmic_gflop(B)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved = gf_all * B / ms_step              # TFLOP/s per GPU: GFLOP/sample * samples / ms
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_reference_steps(steps=2, warmup=1)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+    h2d = h_images.numel() * 4 + h_qids.numel() * 8 + h_ans.numel() * 8 + sum(t["boxes"].numel() * 4 + t["labels"].numel() * 8 + t["answer_token_ids"].numel() * 8 for t in targets)
+    line = {"metric": "samples/sec (img+query fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (random-init weights, randn images, random token ids)",
+            "config": {"workload": workload_name(B), "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (4 GB of saved activations) exceeds the 126 MB L2; no explicit flush",
+                       "dropout": "off (eval-mode-with-grad parity contract; Philox dropout not fused yet)", "loss": loss_val},
+            "clocks": clocks,
+            "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "what": f"whole step: {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd ({gf_fwd:.1f} fwd) x {B} samples / step time; peak = "
+                                 + ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)")},
+            "cpu_baseline": cpu}
+    if sync is not None:
+        line["allreduce_bytes_per_step"] = sync.bytes_per_step
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -43,8 +43,45 @@ def lib():
             raise RuntimeError("gpvb200_gemm_desc layout mismatch between _C.py and libgpvb200.so")
         L.gpvb200_last_error.argtypes = [ctypes.c_char_p, c_size_t]
         L.gpvb200_pack_item_size.restype = c_size_t
-        _lib = L
+        _lib = _Counting(L)
     return _lib
+
+
+class _Counting:
+    """Thin proxy over the CDLL: counts kernel-launching C-ABI calls (bench.py reports them as `gpu_launches`) and, when
+    `trace` is a list, brackets every call with CUDA events on the launching stream (per-kernel time breakdown)."""
+
+    def __init__(self, L):
+        object.__setattr__(self, "_L", L)
+        object.__setattr__(self, "launches", 0)
+        object.__setattr__(self, "trace", None)
+        object.__setattr__(self, "_cache", {})
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._L, name)
+            if name in ("gpvb200_version", "gpvb200_last_error", "gpvb200_gemm_desc_size", "gpvb200_pack_item_size", "gpvb200_pack_chunk"):
+                fn = raw
+            else:
+                def fn(*a, _raw=raw, _name=name):
+                    object.__setattr__(self, "launches", self.launches + 1)
+                    tr = self.trace
+                    if tr is None:
+                        return _raw(*a)
+                    import torch
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = _raw(*a)
+                    e1.record()
+                    tr.append((_name, a, e0, e1))
+                    return rc
+            self._cache[name] = fn
+        return fn
+
+
+def counters():
+    return lib()
 
 
 def last_error() -> str:

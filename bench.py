@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the captured CUDA graphs")
     ap.add_argument("--profiling", action="store_true", help="under ncu only: allow fewer than 3 warm-up steps, skip the e2e loop")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown of one extra step to this file")
     args = ap.parse_args()
@@ -240,6 +241,11 @@ def main():
     h_images, h_qids, h_ans = images.pin_memory(), qids.pin_memory(), ans.pin_memory()
     h_targets = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
 
+    graph_launches = None
+    if not args.no_graph and not args.breakdown:
+        cap = model.capture_step(d_images, d_qids, d_ans, d_targets)
+        graph_launches = cap.launches_per_step
+
     def step_resident():
         loss = model(d_images, d_qids, d_ans, d_targets)
         loss.backward()
@@ -255,12 +261,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms[0] = 1e3 * (time.perf_counter() - t0) / steps      # host time to ENQUEUE one step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -276,7 +286,8 @@ def main():
         sampler.start()
     n0 = lib.launches
     ms = timed(step_resident, args.steps)
-    launches = (lib.launches - n0) // args.steps
+    launches = graph_launches if graph_launches is not None else (lib.launches - n0) // args.steps
+    host_enqueue_ms = host_ms[0]
     if args.profiling:
         print(json.dumps({"profiling": True, "ms_per_step_under_profiler": ms / args.steps, "launches_per_step": launches}))
         return
@@ -336,12 +347,12 @@ def main():
     line = {"metric": "samples/sec (img+query fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random-init weights, randn images, random token ids)",
-            "config": {"workload": workload_name(B), "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": workload_name(B), "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graph_launches is not None,
                        "l2": "per-step working set (4 GB of saved activations) exceeds the 126 MB L2; no explicit flush",
                        "dropout": "off (eval-mode-with-grad parity contract; Philox dropout not fused yet)", "loss": loss_val},
             "clocks": clocks,
             "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "what": f"whole step: {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd ({gf_fwd:.1f} fwd) x {B} samples / step time; peak = "
                                  + ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)")},

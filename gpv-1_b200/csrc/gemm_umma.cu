@@ -3,7 +3,10 @@
 //
 //   warp 0 (one lane)  TMA producer: 4-D tiled cp.async.bulk.tensor loads, SWIZZLE_128B, zero-filled halo
 //   warp 1 (one lane)  tcgen05.mma issuer (128 x BN x 16 bf16 -> fp32 in TMEM), tcgen05.commit -> mbarriers
-//   warps 2-5          epilogue: tcgen05.ld TMEM -> registers -> bias/residual/activation/mask -> global
+//   warps 2-9          epilogue: tcgen05.ld TMEM -> registers -> bias/residual/activation/mask -> global
+// The kernel is persistent (one CTA per SM walks the tile list) with two TMEM accumulator buffers, so the epilogue
+// of one tile (HBM-bound for the K = 64..256 1x1 convolutions) overlaps the TMA/MMA main loop of the next; epilogue
+// warps prefetch the residual / mask rows of the next 32-column slice while they process the current one.
 //
 // Replaces the cuDNN / cuBLAS calls behind every nn.Conv2d / nn.Linear of the reference hot path
 // (backbone.py:72, detr_roi_head.py:79-84, transformer.py:153-160,218-231, vilbert.py:748-761,847-898,
@@ -21,6 +24,7 @@ namespace gpv {
 
 struct KParams {
   int mode, M, N, a_mn, b_mn, bk, k_iters, splits, nstages, b_batched;
+  int m_tiles, n_tiles, gy, total_work, k_per_split;
   int kc_per_tap;
   int Ho, Wo, th, tw, tiles_h, tiles_w, stride;
   int ntaps;
@@ -37,9 +41,168 @@ struct KParams {
   long long ldd, ldr, ldaux, d_batch_stride;
 };
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int BM = 128;
+constexpr int kChunk = 32;  // accumulator columns per epilogue step
 
+struct Work {
+  int nt, mt, bz, it0, it1;
+};
+
+GPV_DEVINL Work decode_work(const KParams& p, int w) {
+  Work k;
+  k.nt = w % p.n_tiles;
+  int r = w / p.n_tiles;
+  k.mt = r % p.m_tiles;
+  r /= p.m_tiles;
+  k.bz = r % p.gy;
+  const int sp = r / p.gy;
+  k.it0 = sp * p.k_per_split;
+  k.it1 = min(k.it0 + p.k_per_split, p.k_iters);
+  return k;
+}
+
+GPV_DEVINL uint4 ldg_u4(const bf16* ptr) { return __ldg(reinterpret_cast<const uint4*>(ptr)); }
+
+// One 32-column slice of an accumulator row: v = alpha*acc*rowscale + bias + residual; D2 = v; v = act(v);
+// v *= mask(aux) / gelu'(aux); store.  `rr` / `aa` hold the prefetched residual / aux slice when `fast`.
+GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float rs, long long off_d, long long off_r,
+                          long long off_a, int nb, int nvalid, bool fast, const uint4 (&rr)[4], const uint4 (&aa)[4]) {
+  float v[kChunk];
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha * rs;
+  if (p.bias != nullptr) {
+    if (fast) {
+#pragma unroll
+      for (int j = 0; j < kChunk; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j)
+        if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
+    }
+  }
+  if (p.residual != nullptr) {
+    if (p.res_fp32) {
+      const float* rp = reinterpret_cast<const float*>(p.residual) + off_r;
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j)
+        if (j < nvalid) v[j] += rp[j];
+    } else if (fast) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t w[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          v[8 * i + 2 * j] += f.x;
+          v[8 * i + 2 * j + 1] += f.y;
+        }
+      }
+    } else {
+      const bf16* rp = p.residual + off_r;
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j)
+        if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+    }
+  }
+  if (p.D2 != nullptr) {
+    bf16* dp = p.D2 + off_d;
+    if (fast) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);     o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(dp + 8 * i) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j)
+        if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+    }
+  }
+  if (p.act == GPVB200_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (p.act == GPVB200_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == GPVB200_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = 1.0f / (1.0f + __expf(-v[j]));
+  }
+  if (p.aux_mode != GPVB200_AUX_NONE) {
+    float a[kChunk];
+    if (fast) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t w[4] = {aa[i].x, aa[i].y, aa[i].z, aa[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          a[8 * i + 2 * j] = f.x;
+          a[8 * i + 2 * j + 1] = f.y;
+        }
+      }
+    } else {
+      const bf16* ap = p.aux + off_a;
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) a[j] = (j < nvalid) ? __bfloat162float(ap[j]) : 0.0f;
+    }
+    if (p.aux_mode == GPVB200_AUX_RELU_MASK) {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) v[j] *= gelu_erf_grad(a[j]);
+    }
+  }
+  if (p.d_fp32) {
+    float* dp = reinterpret_cast<float*>(p.D) + off_d;
+    if (p.d_atomic) {
+      if (fast) {  // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic requests
+#pragma unroll
+        for (int j = 0; j < kChunk; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(dp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+          if (j < nvalid) atomicAdd(dp + j, v[j]);
+      }
+    } else if (fast) {
+#pragma unroll
+      for (int j = 0; j < kChunk; j += 4)
+        *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j)
+        if (j < nvalid) dp[j] = v[j];
+    }
+  } else {
+    bf16* dp = reinterpret_cast<bf16*>(p.D) + off_d;
+    if (fast) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);     o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(dp + 8 * i) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j)
+        if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+// Persistent kernel: each CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ... (an item = one
+// 128 x BN output tile of one batch/tap and one K split).  Two TMEM accumulator buffers let the epilogue of item j
+// overlap the TMA/MMA main loop of item j+1.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -47,25 +210,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile decode -------------------------------------------------------------------------------
-  const int n_tiles = (p.N + BN - 1) / BN;
-  const int nt = blockIdx.x % n_tiles, mt = blockIdx.x / n_tiles;
-  const int n0 = nt * BN, m0 = mt * BM;
-  const int bz = blockIdx.y;
-  const int per = (p.k_iters + p.splits - 1) / p.splits;
-  const int it0 = blockIdx.z * per;
-  const int it1 = min(it0 + per, p.k_iters);
-  if (it0 >= it1) return;  // uniform over the CTA; nothing allocated yet
-
-  int img = 0, ho0 = 0, wo0 = 0;
-  if (p.mode == 1) {
-    const int tpi = p.tiles_h * p.tiles_w;
-    img = mt / tpi;
-    const int r = mt % tpi;
-    ho0 = (r / p.tiles_w) * p.th;
-    wo0 = (r % p.tiles_w) * p.tw;
-  }
 
   // ---- shared memory carve-up ----------------------------------------------------------------------
   const int rowsA = (p.mode == 1) ? p.th * p.tw : BM;
@@ -76,9 +220,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int S = p.nstages;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)S * stage_bytes);
   uint64_t* empty_bar = full_bar + S;
-  uint64_t* accum_bar = empty_bar + S;
-  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  uint64_t* acc_full = empty_bar + S;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -87,7 +232,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -102,50 +250,62 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ================================================================== TMA producer
     if (lane == 0) {
-      for (int it = it0; it < it1; ++it) {
-        const int li = it - it0;
-        const int s = li % S;
-        const uint32_t ph = (uint32_t)(li / S) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_expect_tx(&full_bar[s], a_tx + b_bytes);
-        if (p.mode == 0) {
-          const int k0 = it * p.bk;
-          const int bzB = p.b_batched ? bz : 0;
-          if (!p.a_mn) {
-            tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, bz, 0);
-          } else {
-            tma_load_4d(sa, &tmA, &full_bar[s], m0, k0, bz, 0);
-            tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, k0, bz, 0);
-          }
-          if (!p.b_mn) {
-            tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, bzB, 0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, k0, bzB, 0);
-          }
-        } else if (p.mode == 1) {
-          const int tap = it / p.kc_per_tap, kc = it % p.kc_per_tap;
-          tma_load_4d(sa, &tmA, &full_bar[s], kc * 64, wo0 * p.stride + p.tap_dw[tap], ho0 * p.stride + p.tap_dh[tap], img);
-          if (!p.b_mn) {
-            tma_load_4d(sb, &tmB, &full_bar[s], kc * 64, n0, p.tap_w[tap], 0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, kc * 64, p.tap_w[tap], 0);
-          }
-        } else {
+      int gi = 0;  // stage-use counter, runs across work items
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const Work wk = decode_work(p, w);
+        const int n0 = wk.nt * BN, m0 = wk.mt * BM, bz = wk.bz;
+        int img = 0, ho0 = 0, wo0 = 0;
+        if (p.mode == 1) {
           const int tpi = p.tiles_h * p.tiles_w;
-          const int im = it / tpi, r = it % tpi;
-          const int h0 = (r / p.tiles_w) * p.th, w0 = (r % p.tiles_w) * p.tw;
-          tma_load_4d(sa, &tmA, &full_bar[s], m0, w0, h0, im);
-          tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, w0, h0, im);
-          const int wi = w0 * p.stride + p.tap_dw[bz], hi = h0 * p.stride + p.tap_dh[bz];
+          img = wk.mt / tpi;
+          const int r = wk.mt % tpi;
+          ho0 = (r / p.tiles_w) * p.th;
+          wo0 = (r % p.tiles_w) * p.tw;
+        }
+        for (int it = wk.it0; it < wk.it1; ++it, ++gi) {
+          const int s = gi % S;
+          const uint32_t ph = (uint32_t)(gi / S) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[s], a_tx + b_bytes);
+          if (p.mode == 0) {
+            const int k0 = it * p.bk;
+            const int bzB = p.b_batched ? bz : 0;
+            if (!p.a_mn) {
+              tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, bz, 0);
+            } else {
+              tma_load_4d(sa, &tmA, &full_bar[s], m0, k0, bz, 0);
+              tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, k0, bz, 0);
+            }
+            if (!p.b_mn) {
+              tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, bzB, 0);
+            } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, wi, hi, im);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, k0, bzB, 0);
+            }
+          } else if (p.mode == 1) {
+            const int tap = it / p.kc_per_tap, kc = it % p.kc_per_tap;
+            tma_load_4d(sa, &tmA, &full_bar[s], kc * 64, wo0 * p.stride + p.tap_dw[tap], ho0 * p.stride + p.tap_dh[tap], img);
+            if (!p.b_mn) {
+              tma_load_4d(sb, &tmB, &full_bar[s], kc * 64, n0, p.tap_w[tap], 0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, kc * 64, p.tap_w[tap], 0);
+            }
+          } else {
+            const int tpi = p.tiles_h * p.tiles_w;
+            const int im = it / tpi, r = it % tpi;
+            const int h0 = (r / p.tiles_w) * p.th, w0 = (r % p.tiles_w) * p.tw;
+            tma_load_4d(sa, &tmA, &full_bar[s], m0, w0, h0, im);
+            tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, w0, h0, im);
+            const int wi = w0 * p.stride + p.tap_dw[bz], hi = h0 * p.stride + p.tap_dh[bz];
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, wi, hi, im);
+          }
         }
       }
     }
@@ -157,170 +317,104 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t a_kstep = p.a_mn ? 2048u : 32u;  // bytes per UMMA_K = 16 step
     const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
     const int ksteps = p.bk / 16;
-    for (int it = it0; it < it1; ++it) {
-      const int li = it - it0;
-      const int s = li % S;
-      const uint32_t ph = (uint32_t)(li / S) & 1u;
-      mbar_wait(&full_bar[s], ph);
+    int gi = 0, j = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
+      const Work wk = decode_work(p, w);
+      const int buf = j & 1;
+      mbar_wait(&acc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = make_sdesc_sw128(sa + k * a_kstep, a_lbo, 1024u);
-          const uint64_t bd = make_sdesc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-          umma_f16(tmem_base, ad, bd, idesc, (li > 0 || k > 0) ? 1u : 0u);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+      for (int it = wk.it0; it < wk.it1; ++it, ++gi) {
+        const int s = gi % S;
+        const uint32_t ph = (uint32_t)(gi / S) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_sdesc_sw128(sa + k * a_kstep, a_lbo, 1024u);
+            const uint64_t bd = make_sdesc_sw128(sb + k * b_kstep, b_lbo, 1024u);
+            umma_f16(tacc, ad, bd, idesc, (it > wk.it0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);                     // frees the smem stage once these MMAs retire
+          if (it == wk.it1 - 1) umma_commit(&acc_full[buf]);  // accumulator complete
         }
-        umma_commit(&empty_bar[s]);               // frees the smem stage once these MMAs retire
-        if (it == it1 - 1) umma_commit(accum_bar); // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ================================================================== epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ================================================================== epilogue (warps 2..9)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;       // which half of the BN columns
     const int r = q * 32 + lane;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-
-    bool row_ok;
-    long long row_off;  // element offset of (row, col 0) in D-indexed tensors, excluding the ld factor
-    long long pix = 0;
-    if (p.mode == 1) {
-      const int dy = r / p.tw, dx = r % p.tw;
-      const int ho = ho0 + dy, wo = wo0 + dx;
-      row_ok = (r < p.th * p.tw) && ho < p.Ho && wo < p.Wo;
-      pix = ((long long)img * p.OH + (ho * p.os + p.ooh)) * p.OW + (wo * p.os + p.oow);
-    } else {
-      row_ok = (m0 + r) < p.M;
-      pix = m0 + r;
-    }
-    row_off = (long long)bz * p.d_batch_stride;  // mode 0: batch, mode 2: tap, mode 1: bz == 0
-    const float rs = (p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[m0 + r] : 1.0f;
-
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= p.N) break;  // warp-uniform
-      uint32_t acc[16];
-      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha * rs;
-      const int nb = n0 + c0;
-      const int nvalid = min(16, p.N - nb);
-      const bool vec_ok = p.vec_ok && nvalid == 16;
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
-      }
-      if (p.residual != nullptr && p.res_fp32) {
-        const float* rp = reinterpret_cast<const float*>(p.residual) + row_off + pix * p.ldr + nb;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) v[j] += rp[j];
-      } else if (p.residual != nullptr) {
-        const bf16* rp = p.residual + row_off + pix * p.ldr + nb;
-        if (vec_ok) {
-          const uint4 t0 = *reinterpret_cast<const uint4*>(rp);
-          const uint4 t1 = *reinterpret_cast<const uint4*>(rp + 8);
-          const uint32_t w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_bf16x2(w[j]);
-            v[2 * j] += f.x;
-            v[2 * j + 1] += f.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) v[j] += __bfloat162float(rp[j]);
-        }
-      }
-      if (p.D2 != nullptr) {
-        bf16* dp = p.D2 + row_off + pix * p.ldd + nb;
-        if (vec_ok) {
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-          *reinterpret_cast<uint4*>(dp) = o0;
-          *reinterpret_cast<uint4*>(dp + 8) = o1;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
-        }
-      }
-      if (p.act == GPVB200_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-      } else if (p.act == GPVB200_ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-      } else if (p.act == GPVB200_ACT_SIGMOID) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 1.0f / (1.0f + __expf(-v[j]));
-      }
-      if (p.aux_mode != GPVB200_AUX_NONE) {
-        const bf16* ap = p.aux + row_off + pix * p.ldaux + nb;
-        float a[16];
-        if (vec_ok) {
-          const uint4 t0 = *reinterpret_cast<const uint4*>(ap);
-          const uint4 t1 = *reinterpret_cast<const uint4*>(ap + 8);
-          const uint32_t w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_bf16x2(w[j]);
-            a[2 * j] = f.x;
-            a[2 * j + 1] = f.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) a[j] = (j < nvalid) ? __bfloat162float(ap[j]) : 0.0f;
-        }
-        if (p.aux_mode == GPVB200_AUX_RELU_MASK) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_grad(a[j]);
-        }
-      }
-      if (p.d_fp32) {
-        float* dp = reinterpret_cast<float*>(p.D) + row_off + pix * p.ldd + nb;
-        if (p.d_atomic) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) atomicAdd(dp + j, v[j]);
-        } else if (vec_ok) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(dp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) dp[j] = v[j];
-        }
+    constexpr int kChunksPerHalf = BN / 2 / kChunk;
+    int j = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
+      const Work wk = decode_work(p, w);
+      const int n0 = wk.nt * BN, m0 = wk.mt * BM, bz = wk.bz;
+      const int buf = j & 1;
+      bool row_ok;
+      long long pix;
+      if (p.mode == 1) {
+        const int tpi = p.tiles_h * p.tiles_w;
+        const int img = wk.mt / tpi;
+        const int rr_ = wk.mt % tpi;
+        const int ho = (rr_ / p.tiles_w) * p.th + r / p.tw, wo = (rr_ % p.tiles_w) * p.tw + r % p.tw;
+        row_ok = (r < p.th * p.tw) && ho < p.Ho && wo < p.Wo;
+        pix = ((long long)img * p.OH + (ho * p.os + p.ooh)) * p.OW + (wo * p.os + p.oow);
       } else {
-        bf16* dp = reinterpret_cast<bf16*>(p.D) + row_off + pix * p.ldd + nb;
-        if (vec_ok) {
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-          *reinterpret_cast<uint4*>(dp) = o0;
-          *reinterpret_cast<uint4*>(dp + 8) = o1;
-        } else {
+        row_ok = (m0 + r) < p.M;
+        pix = m0 + r;
+      }
+      const long long row_off = (long long)bz * p.d_batch_stride;  // mode 0: batch, mode 2: tap, mode 1: bz == 0
+      const float rs = (p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[m0 + r] : 1.0f;
+      const int cbase = half * (BN / 2);
+      const bool pre_r = p.residual != nullptr && !p.res_fp32, pre_a = p.aux_mode != GPVB200_AUX_NONE;
+
+      uint4 rr[4], aa[4];
+      auto prefetch = [&](int c) {
+        const int nb = n0 + cbase + c * kChunk;
+        const bool fast = p.vec_ok && row_ok && (nb + kChunk <= p.N);
+        if (fast && pre_r) {
+          const bf16* rp = p.residual + row_off + pix * p.ldr + nb;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+          for (int i = 0; i < 4; ++i) rr[i] = ldg_u4(rp + 8 * i);
+        }
+        if (fast && pre_a) {
+          const bf16* ap = p.aux + row_off + pix * p.ldaux + nb;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) aa[i] = ldg_u4(ap + 8 * i);
+        }
+      };
+      prefetch(0);  // independent of the accumulator: overlaps the wait below
+      mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kChunksPerHalf; ++c) {
+        const int nb = n0 + cbase + c * kChunk;
+        if (nb < p.N) {  // warp-uniform
+          uint32_t acc[kChunk];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + c * kChunk), acc);
+          uint4 cr[4], ca[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            cr[i] = rr[i];
+            ca[i] = aa[i];
+          }
+          if (c + 1 < kChunksPerHalf && nb + kChunk < p.N) prefetch(c + 1);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int nvalid = min(kChunk, p.N - nb);
+            const bool fast = p.vec_ok && nvalid == kChunk;
+            epi_chunk(p, acc, rs, row_off + pix * p.ldd + nb, row_off + pix * p.ldr + nb, row_off + pix * p.ldaux + nb, nb, nvalid,
+                      fast, cr, ca);
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
 
@@ -449,8 +543,18 @@ static void pick_tile(int H, int W, int limit, bool exact_mult16, int* th_out, i
   *tw_out = btw;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, dim3 grid, size_t smem, cudaStream_t st) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -460,6 +564,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
     }
     configured = true;
   }
+  const int grid = kp.total_work < num_sms() ? kp.total_work : num_sms();
   umma_gemm_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mb, kp);
   return check_launch("umma_gemm_kernel");
 }
@@ -477,8 +582,9 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   GPV_REQUIRE(d->mode >= 0 && d->mode <= 2, "gemm: bad mode %d", d->mode);
   GPV_REQUIRE(d->A && d->B && d->D, "gemm: null operand");
   GPV_REQUIRE(d->N > 0 && d->K >= 0, "gemm: bad N/K");
-  const int splits = d->splits > 1 ? d->splits : 1;
-  GPV_REQUIRE(splits == 1 || (d->d_atomic && d->d_fp32), "gemm: split-K needs fp32 atomic output");
+  const int splits_in = d->splits > 1 ? d->splits : (d->splits == 1 ? 1 : 0);
+  const bool auto_split = d->splits <= 0 && d->d_atomic && d->d_fp32 && d->mode != 2;   // splits 0: choose here
+  GPV_REQUIRE(splits_in <= 1 || (d->d_atomic && d->d_fp32), "gemm: split-K needs fp32 atomic output");
   GPV_REQUIRE(!d->d_atomic || d->d_fp32, "gemm: atomic output must be fp32");
   if (d->aux_mode != GPVB200_AUX_NONE) GPV_REQUIRE(d->aux != nullptr, "gemm: aux_mode set without aux");
 
@@ -489,7 +595,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   kp.N = d->N;
   kp.a_mn = d->a_mn ? 1 : 0;
   kp.b_mn = d->b_mn ? 1 : 0;
-  kp.splits = splits;
+  kp.splits = 1;
   kp.act = d->act;
   kp.aux_mode = d->aux_mode;
   kp.d_fp32 = d->d_fp32;
@@ -509,7 +615,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   {
     auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
     kp.vec_ok = ((kp.ldd & 7) == 0) && ((kp.ldr & 7) == 0) && ((kp.ldaux & 7) == 0) && ((kp.d_batch_stride & 7) == 0) &&
-                al16(d->D) && al16(d->D2) && al16(d->residual) && al16(d->aux);
+                al16(d->D) && al16(d->D2) && al16(d->residual) && al16(d->aux) && al16(d->bias);
   }
   kp.stride = d->stride > 0 ? d->stride : 1;
   kp.os = d->out_stride > 0 ? d->out_stride : 1;
@@ -526,15 +632,48 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
     kp.tap_w[i] = d->tap_w[i];
   }
 
-  // ---- tile width ------------------------------------------------------------------------------------
-  int BN;
-  if (d->N > 128 && !(d->mode == 2)) BN = 256;
-  else if (d->N > 64) BN = 128;
-  else BN = 64;
-  if (d->mode == 2 && d->N > 64) BN = 128;
+  // ---- tile width: the widest BN that still yields about one work item per SM -------------------------------
+  int m_tiles_pre, gy_pre;
+  if (d->mode == 1) {
+    GPV_REQUIRE(d->Ho > 0 && d->Wo > 0 && d->n_img > 0, "gemm: bad conv geometry");
+    int th, tw;
+    pick_tile(d->Ho, d->Wo, 128, false, &th, &tw);
+    m_tiles_pre = d->n_img * ((d->Ho + th - 1) / th) * ((d->Wo + tw - 1) / tw);
+    gy_pre = 1;
+  } else {
+    m_tiles_pre = (d->M + BM - 1) / BM;
+    gy_pre = d->mode == 0 ? (d->batch > 0 ? d->batch : 1) : d->ntaps;
+  }
+  // Cost model (us): a k-iteration is L2->smem bound (A 16 KB + B BN/8 KB at ~68 GB/s per SM), the epilogue moves
+  // 128 x BN outputs (plus residual) at the SM's share of HBM; split-K pays one vector atomic per output per split.
+  const int bn_cap = d->mode == 2 ? 128 : 256;
+  const int k_iters_pre = d->mode == 0 ? (d->K + 63) / 64 : (d->mode == 1 ? d->ntaps * ((d->K + 63) / 64) : 0);
+  int BN = 64, splits = splits_in > 0 ? splits_in : 1;
+  {
+    double best = 1e30;
+    for (int bn = 64; bn <= bn_cap; bn *= 2) {
+      if (bn > 64 && d->N <= bn / 2) break;
+      const long long tiles = (long long)m_tiles_pre * ((d->N + bn - 1) / bn) * gy_pre;
+      int sp = splits_in > 0 ? splits_in : 1;
+      if (auto_split && k_iters_pre > 0) {
+        sp = (int)((num_sms() + tiles - 1) / tiles);
+        if (sp > k_iters_pre) sp = k_iters_pre;
+        if (sp < 1) sp = 1;
+      }
+      const double t_iter = 0.24 + 0.0018 * bn;          // 0.35 / 0.47 / 0.70 us
+      const double t_epi = (d->d_atomic ? 4.0 : 3.0) * bn / 256.0;
+      const int kper = k_iters_pre > 0 ? (k_iters_pre + sp - 1) / sp : 8;
+      const long long waves = (tiles * sp + num_sms() - 1) / num_sms();
+      const double t = waves * (kper * t_iter + t_epi + 1.5);
+      if (t < best - 1e-9) {
+        best = t;
+        BN = bn;
+        splits = sp;
+      }
+    }
+  }
 
   CUtensorMap ma, mb;
-  dim3 grid;
   const uint32_t one4[4] = {1, 1, 1, 1};
 
   if (d->mode == 0) {
@@ -573,8 +712,8 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       rc = make_map(&mb, d->B, dims, str, box, one4);
       if (rc) return rc;
     }
-    const int mt = (d->M + BM - 1) / BM, ntl = (d->N + BN - 1) / BN;
-    grid = dim3(mt * ntl, d->batch, splits);
+    kp.m_tiles = (d->M + BM - 1) / BM;
+    kp.gy = d->batch;
   } else if (d->mode == 1) {
     GPV_REQUIRE(d->n_img > 0 && d->Hi > 0 && d->Wi > 0 && d->Ho > 0 && d->Wo > 0, "gemm: bad conv geometry");
     GPV_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "gemm: ntaps must be 1..9");
@@ -616,8 +755,8 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       if (rc) return rc;
     }
     if (kp.OH == 0) { kp.OH = d->Ho; kp.OW = d->Wo; }
-    const int ntl = (d->N + BN - 1) / BN;
-    grid = dim3(d->n_img * kp.tiles_h * kp.tiles_w * ntl, 1, splits);
+    kp.m_tiles = d->n_img * kp.tiles_h * kp.tiles_w;
+    kp.gy = 1;
   } else {
     GPV_REQUIRE(d->n_img > 0 && d->Hi > 0 && d->Wi > 0 && d->Ho > 0 && d->Wo > 0, "gemm: bad wgrad geometry");
     GPV_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "gemm: ntaps must be 1..9");
@@ -646,28 +785,34 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       rc = make_map(&mb, d->B, dims, str, box, es);
       if (rc) return rc;
     }
-    const int mt = (d->M + BM - 1) / BM, ntl = (d->N + BN - 1) / BN;
-    grid = dim3(mt * ntl, d->ntaps, splits);
+    kp.m_tiles = (d->M + BM - 1) / BM;
+    kp.gy = d->ntaps;
   }
-  if (splits > kp.k_iters) {
-    kp.splits = kp.k_iters;
-    grid.z = kp.k_iters;
+  // K splits: equal chunks of k_per_split iterations, none empty
+  {
+    int sp = splits > kp.k_iters ? kp.k_iters : splits;
+    kp.k_per_split = (kp.k_iters + sp - 1) / sp;
+    kp.splits = (kp.k_iters + kp.k_per_split - 1) / kp.k_per_split;
+  }
+  kp.n_tiles = (d->N + BN - 1) / BN;
+  {
+    const long long tw_ = (long long)kp.m_tiles * kp.n_tiles * kp.gy * kp.splits;
+    GPV_REQUIRE(tw_ > 0 && tw_ < (1ll << 31), "gemm: work list size %lld out of range", tw_);
+    kp.total_work = (int)tw_;
   }
 
   // ---- pipeline depth ---------------------------------------------------------------------------------
   const uint32_t a_bytes = kp.a_mn ? 2u * kp.bk * 128u : 128u * 128u;
   const uint32_t b_bytes = kp.b_mn ? (uint32_t)(BN / 64) * kp.bk * 128u : (uint32_t)BN * 128u;
   const uint32_t stage = a_bytes + b_bytes;
-  const uint32_t budget_two = 110 * 1024, budget_one = 222 * 1024;
-  int nst = (int)(budget_two / stage);
-  if (nst < 3) nst = (int)(budget_one / stage);
+  int nst = (int)((196u * 1024u) / stage);
   if (nst > 6) nst = 6;
   GPV_REQUIRE(nst >= 2, "gemm: stage of %u bytes does not fit twice in shared memory", stage);
   kp.nstages = nst;
-  const size_t smem = (size_t)nst * stage + 1024 /*alignment slack*/ + (2 * nst + 1) * 8 + 16;
+  const size_t smem = (size_t)nst * stage + 1024 /*alignment slack*/ + (2 * nst + 4) * 8 + 16;
 
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 256) return launch<256>(ma, mb, kp, grid, smem, st);
-  if (BN == 128) return launch<128>(ma, mb, kp, grid, smem, st);
-  return launch<64>(ma, mb, kp, grid, smem, st);
+  if (BN == 256) return launch<256>(ma, mb, kp, smem, st);
+  if (BN == 128) return launch<128>(ma, mb, kp, smem, st);
+  return launch<64>(ma, mb, kp, smem, st);
 }

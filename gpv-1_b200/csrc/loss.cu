@@ -124,7 +124,30 @@ __global__ void __launch_bounds__(128) set_criterion_kernel(const float* __restr
                                                             long long lddb) {
   __shared__ int match_t[1024];
   __shared__ float red[3][4];
+  __shared__ float s_norm[2];
   const int b = blockIdx.x;
+  if (inv_wsum <= 0.0f) {
+    // normalisers derived on the device from the ragged target offsets (set_criterion.py:163-168 num_boxes; the
+    // weighted-mean denominator of F.cross_entropy with empty_weight = [1, eos_coef]) so that a captured CUDA graph
+    // can be replayed with different targets
+    if (threadIdx.x == 0) {
+      int n_match = 0, n_loc = 0, sum_t = 0;
+      for (int i = 0; i < (int)gridDim.x; ++i) {
+        if (loc_valid[i]) {
+          const int Ti = toff[i + 1] - toff[i];
+          n_match += min(Q, Ti);
+          sum_t += Ti;
+          ++n_loc;
+        }
+      }
+      const float ws = (float)n_match + eos_coef * (float)(n_loc * Q - n_match);
+      s_norm[0] = 1.0f / fmaxf(ws, 1e-20f);
+      s_norm[1] = 1.0f / (float)max(sum_t, 1);
+    }
+    __syncthreads();
+    inv_wsum = s_norm[0];
+    inv_num_boxes = s_norm[1];
+  }
   const bool valid = loc_valid[b] != 0;
   const int t0 = toff[b], T = toff[b + 1] - t0;
   for (int q = threadIdx.x; q < Q; q += blockDim.x) match_t[q] = -1;
@@ -224,11 +247,13 @@ extern "C" int gpvb200_set_criterion(const float* logits, int64_t ldl, const flo
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(logits && boxes && tgt_offsets && loc_valid && out3 && dlogits && dbox_pre, "set_criterion: null pointer");
-  GPV_REQUIRE(B >= 0 && Q > 0 && Q <= 1024 && weight_sum > 0.f && num_boxes > 0.f, "set_criterion: bad arguments");
+  GPV_REQUIRE(B >= 0 && Q > 0 && Q <= 1024 && ((weight_sum > 0.f && num_boxes > 0.f) || (weight_sum <= 0.f && num_boxes <= 0.f)),
+              "set_criterion: bad arguments");
   GPV_REQUIRE(Kmax == 0 || (idx_q && idx_t && tgt_boxes), "set_criterion: matches without indices");
   if (B == 0) return GPV_OK;
   set_criterion_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(logits, ldl, boxes, ldb, tgt_boxes, tgt_offsets, idx_q, idx_t, Kmax,
-                                                            loc_valid, Q, eos_coef, 1.0f / weight_sum, 1.0f / num_boxes, wt_ce,
+                                                            loc_valid, Q, eos_coef, weight_sum > 0.f ? 1.0f / weight_sum : -1.0f,
+                                                            weight_sum > 0.f ? 1.0f / num_boxes : -1.0f, wt_ce,
                                                             wt_bbox, wt_giou, out3, dlogits, (bf16*)dbox_pre, lddb);
   return check_launch("set_criterion_kernel");
 }

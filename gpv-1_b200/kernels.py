@@ -73,13 +73,11 @@ def linear_dgrad(dy, w, *, aux=None, aux_mode=AUX_NONE, residual=None, out=None,
 
 
 def linear_wgrad(dy, x, dw, *, rowscale=None, splits=0):
-    """dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]; both operands read in place (MN-major), split over M."""
+    """dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]; both operands read in place (MN-major), split over M (splits=0: the
+    library picks tile width and split count from its cost model)."""
     _req(dy, BF16), _req(x, BF16), _req(dw, torch.float32)
     M, N = dy.shape
     K = x.shape[1]
-    if splits <= 0:
-        tiles = ((N + 127) // 128) * ((K + 127) // 128)
-        splits = max(1, min((M + 63) // 64, (2 * 148 + tiles - 1) // tiles))
     return gemm(dy, x, dw, M=N, N=K, K=M, lda=dy.stride(0), ldb=x.stride(0), ldd=dw.stride(0), a_mn=True, b_mn=True,
                 rowscale=rowscale, atomic=True, splits=splits)
 

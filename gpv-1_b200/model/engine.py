@@ -224,6 +224,7 @@ class Engine:
             self.stage_end[st] = max(self.stage_end[st], self.stage_end[st - 1])
         self.stage_end[-1] = total
         self.on_stage_done = None                             # parallel.py: callable(stage) fired as backward finishes a stage
+        self.on_backward_end = None                           # parallel.py: joins the all-reduce stream (inside a graph capture too)
         self.grad_arena = torch.zeros(total, device=self.dev, dtype=F32)
         self.G = {n: self.grad_arena[offs[n]:offs[n] + math.prod(byname[n].shape)].view(byname[n].shape) for n in order}
         self.live_names = order
@@ -656,6 +657,7 @@ class Engine:
                             wt_bbox=self.loss_wts["loss_bbox"], wt_giou=self.loss_wts["loss_giou"], out3=loss_terms[1:4], dlogits=dlg,
                             dbox_pre=dbox)
         loss = (loss_terms * (self._wts_loc if tgt.n_loc else self._wts_noloc)).sum().reshape(1)
+        # (n_loc > 0 always holds for a captured step: the set criterion then yields zeros when no image has boxes)
         s.update(S_ans=S, sv_txt=sv_txt, dlogits_v=dlogits_v, dlg=dlg, dbox=dbox, loss_terms=loss_terms, idx_q=idx_q, idx_t=idx_t)
         self.saved = s
         return loss, s
@@ -739,4 +741,6 @@ class Engine:
         dpre = self._lin_bwd("detr.input_proj", c5f, dx, residual=dc5, aux=c5f, aux_mode=MASK_RELU)
         self._done(3)
         self._backbone_bwd(dpre.view(s["c5"].shape), s["acts"])
+        if self.on_backward_end is not None:
+            self.on_backward_end()
         return self.G

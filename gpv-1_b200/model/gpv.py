@@ -81,9 +81,12 @@ def _init_tensor(name, shape, g):
 
 class HostTargets:
     """Per-step host bookkeeping of the criterion (losses.py:41-138, set_criterion.py:150-168): which rows carry which
-    loss weight, ragged target offsets, normalisers.  Built from Python-side shapes only -- no device sync."""
+    loss weight, ragged target offsets, normalisers.  Built from Python-side shapes only -- no device sync.
 
-    def __init__(self, targets, B, S, Q, loss_wts, eos_coef, device):
+    With `static` (a dict of preallocated device buffers from `alloc_static`) the results are copied into those fixed
+    addresses (CUDA-graph replay) and the normalisers are left to the device (weight_sum = num_boxes = -1)."""
+
+    def __init__(self, targets, B, S, Q, loss_wts, eos_coef, device, static=None):
         self.device = device
         # ---- text losses: CE(reduction none).mean(0).sum(0).sum() per task (losses.py:20-26) -> weight wt/B' per row
         counts = {}
@@ -99,15 +102,11 @@ class HostTargets:
                 ids = t["answer_token_ids"]
                 if ids.shape[0] != S - 1:
                     raise ValueError("targets[i]['answer_token_ids'] must be answer_token_ids[i, 1:] (train_distr.py:410-412)")
-                tg_rows.append(ids.to(device=device, dtype=torch.int64))
+                tg_rows.append(ids.to(device=device, dtype=torch.int64, non_blocking=True))
             else:
                 if zero_row is None:
                     zero_row = torch.zeros(S - 1, dtype=torch.int64, device=device)
                 tg_rows.append(zero_row)
-        tg = torch.zeros((B, S), dtype=torch.int64, device=device)
-        if S > 1:
-            tg[:, :S - 1] = torch.stack(tg_rows)
-        self.ce_targets = tg.view(-1)
         self.n_text = sum(counts.values())
         # ---- localisation: images that have a 'boxes' key (losses.py:101-121); T_b may be 0
         sizes = [int(t["boxes"].shape[0]) if "boxes" in t else 0 for t in targets]
@@ -118,22 +117,55 @@ class HostTargets:
         n_match = sum(min(Q, s) for s in sizes)
         self.weight_sum = float(n_match + eos_coef * (self.n_loc * Q - n_match)) if self.n_loc else 1.0
         self.num_boxes = float(max(sumT, 1))
+        self.sizes = sizes
         host = np.zeros(B + 1 + B, np.int32)
         host[1:B + 1] = np.cumsum(sizes)
         host[B + 1:] = valid
         hb = torch.from_numpy(np.concatenate([host.view(np.float32), roww.reshape(-1)])).pin_memory()
-        dv = hb.to(device, non_blocking=True)
-        self.offsets = dv[:B + 1].view(torch.int32)
-        self.loc_valid = dv[B + 1:2 * B + 1].view(torch.int32).to(torch.uint8)
-        self.ce_row_weight = dv[2 * B + 1:]
-        if sumT:
-            self.boxes = torch.cat([t["boxes"].to(device=device, dtype=torch.float32).reshape(-1, 4) for t in targets if "boxes" in t and t["boxes"].shape[0]])
-            lab = [t["labels"].to(device=device, dtype=torch.int64) for t in targets if "boxes" in t and t["boxes"].shape[0]]
-            self.labels = torch.cat(lab)
+        with_boxes = [t for t in targets if "boxes" in t and t["boxes"].shape[0]]
+        if static is None:
+            dv = hb.to(device, non_blocking=True)
+            tg = torch.zeros((B, S), dtype=torch.int64, device=device)
+            if S > 1:
+                tg[:, :S - 1] = torch.stack(tg_rows)
+            self.ce_targets = tg.view(-1)
+            if sumT:
+                self.boxes = torch.cat([t["boxes"].to(device=device, dtype=torch.float32, non_blocking=True).reshape(-1, 4) for t in with_boxes])
+                self.labels = torch.cat([t["labels"].to(device=device, dtype=torch.int64, non_blocking=True) for t in with_boxes])
+            else:
+                self.boxes = torch.zeros((1, 4), device=device)
+                self.labels = torch.zeros(1, dtype=torch.int64, device=device)
         else:
-            self.boxes = torch.zeros((1, 4), device=device)
-            self.labels = torch.zeros(1, dtype=torch.int64, device=device)
-        self.sizes = sizes
+            if static["ce_targets"].numel() != B * S or self.Tmax > static["Tcap"]:
+                raise ValueError("batch does not fit the captured step (B, S or boxes per image)")
+            dv = static["packed"]
+            dv.copy_(hb, non_blocking=True)
+            if S > 1:
+                static["ce_targets"].view(B, S)[:, :S - 1] = torch.stack(tg_rows)
+            self.ce_targets = static["ce_targets"]
+            if sumT:
+                static["boxes"][:sumT] = torch.cat([t["boxes"].to(device=device, dtype=torch.float32, non_blocking=True).reshape(-1, 4) for t in with_boxes])
+                static["labels"][:sumT] = torch.cat([t["labels"].to(device=device, dtype=torch.int64, non_blocking=True) for t in with_boxes])
+            self.boxes, self.labels = static["boxes"], static["labels"]
+            self.Tmax = static["Tcap"]
+            self.n_loc = max(self.n_loc, 1)            # the graph always runs the localisation kernels
+            self.weight_sum = self.num_boxes = -1.0     # derived on the device from offsets / loc_valid
+        self.offsets = dv[:B + 1].view(torch.int32)
+        self.loc_valid_i32 = dv[B + 1:2 * B + 1].view(torch.int32)
+        if static is None:
+            self.loc_valid = self.loc_valid_i32.to(torch.uint8)
+        else:
+            static["loc_valid"].copy_(self.loc_valid_i32)
+            self.loc_valid = static["loc_valid"]
+        self.ce_row_weight = dv[2 * B + 1:]
+
+    @staticmethod
+    def alloc_static(B, S, Tcap, device):
+        return {"Tcap": Tcap, "packed": torch.zeros(2 * B + 1 + B * S, dtype=torch.float32, device=device),
+                "ce_targets": torch.zeros(B * S, dtype=torch.int64, device=device),
+                "boxes": torch.zeros((B * Tcap, 4), dtype=torch.float32, device=device),
+                "labels": torch.zeros(B * Tcap, dtype=torch.int64, device=device),
+                "loc_valid": torch.zeros(B, dtype=torch.uint8, device=device)}
 
 
 class _Step(torch.autograd.Function):
@@ -191,6 +223,7 @@ class GPV(nn.Module):
         self._anchor_t = None
         self._tokenizer = None
         self.grad_sync = None          # parallel.GradSync installs itself here
+        self._captured = None          # model/graph.py:CapturedStep once capture_step() ran
 
     # ------------------------------------------------------------------------------------------------ plumbing
     @property
@@ -215,11 +248,22 @@ class GPV(nn.Module):
             self._anchor_t = torch.zeros(1, device=dev, requires_grad=True)
         return self._anchor_t
 
+    def capture_step(self, images, queries, answer_token_ids, targets, boxes_per_image_cap=None):
+        """Record the training step for this batch shape into CUDA graphs (model/graph.py).  Later calls of
+        forward(images, queries, answer_token_ids, targets) with the same shapes replay them."""
+        from .graph import CapturedStep
+        images, qids = self._images(images), self._queries(queries)
+        ans = answer_token_ids.to(device=images.device, dtype=torch.int64)
+        self._captured = CapturedStep(self, images, qids, ans, targets, boxes_per_image_cap)
+        return self._captured
+
     def _run_backward(self, g):
         eng = self.engine
-        eng.backward()
-        if self.grad_sync is not None:
-            self.grad_sync.finish()
+        cap = self._captured
+        if cap is not None and cap.pending:
+            cap.backward()
+        else:
+            eng.backward()
         if not eng.unit_upstream_grad:
             eng.grad_arena.mul_(g)
         for n, p in self._live:
@@ -270,8 +314,12 @@ class GPV(nn.Module):
         images, qids = self._images(images), self._queries(queries)
         B, Q = images.shape[0], self.cfg.detr.num_queries
         if answer_token_ids is not None and targets is not None:
-            ans = answer_token_ids.to(device=images.device, dtype=torch.int64)
+            ans = answer_token_ids.to(device=images.device, dtype=torch.int64, non_blocking=True)
             S = ans.shape[1]
+            cap = self._captured
+            if cap is not None and torch.is_grad_enabled() and cap.matches(images, qids, ans):
+                loss = cap.forward(images, qids, ans, targets)
+                return None if loss is None else _Step.apply(self._anchor(), loss, self)
             tgt = HostTargets(targets, B, S, Q, eng.loss_wts, eng.eos_coef, images.device)
             if tgt.n_text == 0 and tgt.n_loc == 0:
                 return None

@@ -1,0 +1,73 @@
+"""CUDA-graph capture of the static-shape training step.
+
+A B=32 step is ~1000 kernel launches of 5-50 us each; issued one by one from Python the host needs ~25 ms to enqueue
+them, which is as long as the GPU needs to run them.  `CapturedStep` records the forward (+ criterion) and the
+backward of `Engine` once into two CUDA graphs that share a memory pool and replays them per step; per-step data
+(images, token ids, ragged targets) is copied into fixed device buffers first, and every batch-dependent scalar
+(normalisers of the set criterion) is derived on the device, so a replay is exact for any batch of the captured shape.
+The reference has no equivalent (its matcher forces a device->host sync in the middle of every forward: matcher.py:73).
+"""
+import torch
+
+from .gpv import HostTargets
+
+
+class CapturedStep:
+    def __init__(self, model, images, qids, ans, targets, boxes_per_image_cap=None, warmup=2):
+        eng = model.engine
+        self.model, self.eng = model, eng
+        dev = eng.dev
+        B, S = ans.shape
+        self.B, self.S, self.Q = B, S, eng.Q
+        self.img_shape, self.Tl = tuple(images.shape), qids.shape[1]
+        cap = boxes_per_image_cap or eng.Q
+        self.static_t = HostTargets.alloc_static(B, S, cap, dev)
+        self.images = torch.empty(self.img_shape, dtype=torch.float32, device=dev)
+        self.qids = torch.empty((B, self.Tl), dtype=torch.int64, device=dev)
+        self.ans = torch.empty((B, S), dtype=torch.int64, device=dev)
+        tgt = self._load(images, qids, ans, targets)
+        eng.refresh()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # first-call work (smem attributes, tensor maps, position table)
+                eng.forward_train(self.images, self.qids, self.ans, tgt)
+                eng.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from .. import _C
+        n0 = _C.lib().launches
+        self.pool = torch.cuda.graph_pool_handle()
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd, pool=self.pool):
+            self.loss, _ = eng.forward_train(self.images, self.qids, self.ans, tgt)
+        self._saved = eng.saved
+        self.g_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bwd, pool=self.pool):
+            eng.backward()
+        self.launches_per_step = _C.lib().launches - n0
+        self.pending = False
+
+    def matches(self, images, qids, ans):
+        return tuple(images.shape) == self.img_shape and qids.shape[1] == self.Tl and tuple(ans.shape) == (self.B, self.S)
+
+    def _load(self, images, qids, ans, targets):
+        self.images.copy_(images, non_blocking=True)
+        self.qids.copy_(qids, non_blocking=True)
+        self.ans.copy_(ans, non_blocking=True)
+        return HostTargets(targets, self.B, self.S, self.Q, self.eng.loss_wts, self.eng.eos_coef, self.eng.dev, static=self.static_t)
+
+    def forward(self, images, qids, ans, targets):
+        """Copies the batch into the captured buffers and replays the forward graph; returns the loss ([1], static)."""
+        tgt = self._load(images, qids, ans, targets)
+        if tgt.n_text == 0 and not any("boxes" in t for t in targets):
+            return None
+        self.eng.refresh()
+        self.g_fwd.replay()
+        self.pending = True
+        return self.loss
+
+    def backward(self):
+        assert self.pending, "backward() without a forward()"
+        self.pending = False
+        self.g_bwd.replay()

@@ -180,7 +180,9 @@ int gpvb200_add_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, voi
 int gpvb200_ce_fwd_bwd(const float* logits, int64_t ldl, const int64_t* targets, const float* row_weight, float* loss_sum,
                        float* row_loss, void* dlogits, int64_t ldd, int32_t rows, int32_t V, void* stream);
 /* out3 += (loss_ce, loss_bbox, loss_giou); dlogits [B*Q][ldl] fp32 and dbox_pre [B*Q][lddb] bf16 (gradient w.r.t.
- * the pre-sigmoid box head output), both already multiplied by the loss weights wt_*. */
+ * the pre-sigmoid box head output), both already multiplied by the loss weights wt_*.  weight_sum = sum of the
+ * class weights over all (valid image, query) pairs and num_boxes = max(sum T_b, 1); pass both <= 0 to have the
+ * kernel derive them from tgt_offsets / loc_valid on the device (CUDA-graph replay with changing targets). */
 int gpvb200_set_criterion(const float* logits, int64_t ldl, const float* boxes, int64_t ldb, const float* tgt_boxes,
                           const int32_t* tgt_offsets, const int64_t* idx_q, const int64_t* idx_t, int32_t Kmax,
                           const uint8_t* loc_valid, int32_t B, int32_t Q, float eos_coef, float weight_sum, float num_boxes,

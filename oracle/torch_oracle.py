@@ -404,7 +404,9 @@ def make_state(specs, seed=0, device="cpu"):
             t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
         elif name in ("answer_head.vocab_embed", "answer_input_embedings.embedding_layer.weight"):
             t = 0.1 * torch.randn(shape, generator=g)
-        elif name.endswith("_embeddings.weight") or name == "detr.query_embed.weight":
+        elif name == "detr.query_embed.weight":
+            t = 3.0 * torch.randn(shape, generator=g)      # large enough that the 100 object queries attend differently
+        elif name.endswith("_embeddings.weight"):
             t = 0.5 * torch.randn(shape, generator=g)
         elif len(shape) == 2 and name != "relevance_tokens":
             t = torch.randn(shape, generator=g) * (1.0 / math.sqrt(shape[1]))

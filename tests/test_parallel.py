@@ -17,6 +17,7 @@ class _FakeEngine:
         self.grad_arena = torch.zeros(n)
         self.stage_end = stage_end
         self.on_stage_done = None
+        self.on_backward_end = None
 
 
 def _worker(rank, world, port, out):
@@ -37,7 +38,7 @@ def _worker(rank, world, port, out):
         lo = ends[st - 1] if st else 0
         eng.grad_arena[lo:ends[st]] = g[lo:ends[st]]
         eng.on_stage_done(st)
-    sync.finish()
+    eng.on_backward_end()
     gathered = [torch.zeros(64) for _ in range(world)]
     dist.all_gather(gathered, g)
     mean = torch.stack(gathered).mean(0)

@@ -241,6 +241,11 @@ def main():
     h_images, h_qids, h_ans = images.pin_memory(), qids.pin_memory(), ans.pin_memory()
     h_targets = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
 
+    def note(msg):
+        if os.environ.get("GPV_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    note("model built, parameters broadcast")
     graph_launches = None
     if not args.no_graph and not args.breakdown:
         cap = model.capture_step(d_images, d_qids, d_ans, d_targets)
@@ -278,14 +283,17 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    note("captured" if graph_launches is not None else "eager")
     for _ in range(args.warmup):
         step_resident()
+    note("warm-up done")
     lib = _C.lib()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = lib.launches
     ms = timed(step_resident, args.steps)
+    note("timed region done")
     launches = graph_launches if graph_launches is not None else (lib.launches - n0) // args.steps
     host_enqueue_ms = host_ms[0]
     if args.profiling:

@@ -70,8 +70,13 @@ GPV_DEVINL uint4 ldg_u4(const bf16* ptr) { return __ldg(reinterpret_cast<const u
 GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float rs, long long off_d, long long off_r,
                           long long off_a, int nb, int nvalid, bool fast, const uint4 (&rr)[4], const uint4 (&aa)[4]) {
   float v[kChunk];
+  if (rs != 1.0f) {  // rs = alpha * rowscale folded by the caller; 1 for most layers
 #pragma unroll
-  for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha * rs;
+    for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]) * rs;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]);
+  }
   if (p.bias != nullptr) {
     if (fast) {
 #pragma unroll
@@ -368,7 +373,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         pix = m0 + r;
       }
       const long long row_off = (long long)bz * p.d_batch_stride;  // mode 0: batch, mode 2: tap, mode 1: bz == 0
-      const float rs = (p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[m0 + r] : 1.0f;
+      const float rs = p.alpha * ((p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[m0 + r] : 1.0f);
       const int cbase = half * (BN / 2);
       const bool pre_r = p.residual != nullptr && !p.res_fp32, pre_a = p.aux_mode != GPVB200_AUX_NONE;
 

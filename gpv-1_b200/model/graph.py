@@ -42,9 +42,35 @@ class CapturedStep:
         with torch.cuda.graph(self.g_fwd, pool=self.pool):
             self.loss, _ = eng.forward_train(self.images, self.qids, self.ans, tgt)
         self._saved = eng.saved
-        self.g_bwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_bwd, pool=self.pool):
-            eng.backward()
+        # Backward: one graph per gradient stage when a data-parallel GradSync is attached, so that each bucket's NCCL
+        # all-reduce is launched (outside any graph, on its side stream) as soon as the stage's graph has been enqueued.
+        self.sync = model.grad_sync if (model.grad_sync is not None and model.grad_sync.world > 1) else None
+        hooks = (eng.on_stage_done, eng.on_backward_end)
+        self.g_bwd = []
+        cap_stream = torch.cuda.Stream(device=dev)
+        cap_stream.wait_stream(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        try:
+            with torch.cuda.stream(cap_stream):
+                g = torch.cuda.CUDAGraph()
+                g.capture_begin(pool=self.pool)
+                self.g_bwd.append(g)
+
+                def split(stage):
+                    if self.sync is None:
+                        return
+                    self.g_bwd[-1].capture_end()
+                    g2 = torch.cuda.CUDAGraph()
+                    g2.capture_begin(pool=self.pool)
+                    self.g_bwd.append(g2)
+
+                eng.on_stage_done, eng.on_backward_end = split, None
+                eng.backward()
+                self.g_bwd[-1].capture_end()
+        finally:
+            eng.on_stage_done, eng.on_backward_end = hooks
+        torch.cuda.current_stream().wait_stream(cap_stream)
+        torch.cuda.synchronize()
         self.launches_per_step = _C.lib().launches - n0
         self.pending = False
 
@@ -70,4 +96,12 @@ class CapturedStep:
     def backward(self):
         assert self.pending, "backward() without a forward()"
         self.pending = False
-        self.g_bwd.replay()
+        if self.sync is None:
+            self.g_bwd[0].replay()
+            return
+        # graph i ends where gradient stage i is complete (the last graph is empty: layer2 finishes the backward)
+        for i, g in enumerate(self.g_bwd):
+            g.replay()
+            if i < len(self.g_bwd) - 1:
+                self.sync.stage_done(i)
+        self.sync.finish()

@@ -64,3 +64,75 @@ def test_grad_stage_covers_every_live_parameter():
     live = [s.name for s in specs if s.kind == "param" and not never_gets_grad(s.name)]
     stages = {grad_stage(n) for n in live}
     assert stages == set(range(N_STAGES))
+
+
+def _nccl_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import json
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gpv1_b200.config import load_config
+    from gpv1_b200.model import GPV
+    from gpv1_b200.parallel import GradSync, broadcast_parameters
+    from oracle import torch_oracle as TO
+    from oracle.make_golden import make_inputs
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "gpv_specs.json")))
+    V = g["V"]
+    P = TO.make_state([tuple(s) for s in g["specs"]], seed=0)
+    vocab = ["__pad__", "__cls__", "__stop__", "__unk__"] + [f"w{i}" for i in range(V - 4)]
+    model = GPV(load_config().model, vocab=vocab, vocab_embed=P["answer_head.vocab_embed"].numpy())
+    model.load_state_dict(P, strict=True)
+    model.to(dev)
+    broadcast_parameters(model)
+    images, qids, ans, targets = make_inputs(2, 192, 256, 6, 5, 100 + rank, ["CocoCaptioning", "CocoVqa"])
+    dt = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
+    batch = (images.to(dev), qids.to(dev), ans.to(dev), dt)
+    names = ["detr_joiner.weight", "text_decoder.layers.0.linear1.weight", "detr.backbone.0.body.layer2.0.conv2.weight",
+             "detr.transformer.encoder.layers.3.self_attn.in_proj_weight", "co_att_transformer.1.biattention.value2.weight"]
+    params = dict(model.named_parameters())
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        model(*batch).backward()
+        torch.cuda.synchronize()
+        return {n: params[n].grad.clone() for n in names}
+
+    local = step()                                            # no GradSync attached: rank-local gradients
+    mean = {}
+    for n in names:
+        parts = [torch.zeros_like(local[n]) for _ in range(world)]
+        dist.all_gather(parts, local[n])
+        mean[n] = torch.stack(parts).mean(0)
+    GradSync(model)
+    ok = True
+    eager = step()
+    for n in names:
+        ok &= bool((eager[n] - mean[n]).norm() <= 2e-3 * mean[n].norm() + 1e-7)
+    model.capture_step(*batch)
+    graphed = step()
+    for n in names:
+        ok &= bool((graphed[n] - mean[n]).norm() <= 2e-3 * mean[n].norm() + 1e-7)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        with open(out, "w") as f:
+            f.write("ok" if flag.item() == 1.0 else "mismatch")
+    dist.destroy_process_group()
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gradsync_nccl_two_gpus(tmp_path):
+    """On a box with >= 2 GPUs: the stage-bucketed all-reduce (eager and under the captured CUDA graphs) leaves every
+    rank with the mean of the rank-local gradients."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "res.txt")
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"

@@ -5,7 +5,7 @@
 // (gpv.py:38-43); BertBiAttention.forward vilbert.py:737-824.  The attention-weight average the reference
 // materialises and discards (need_weights) is never computed.
 //
-// One CTA owns one (batch, head): Q, K, V (and dO for backward) of that head live in shared memory, both
+// One CTA (8-12 warps) owns one (batch, head): Q, K, V (and dO for backward) of that head live in shared memory, both
 // row-major and transposed, so every product is a register-A x shared-B^T warp MMA (mma.sync m16n8k16 bf16,
 // fp32 accumulate) with online softmax kept in registers.  Scores never touch HBM.
 // NOTE: this is the legacy tensor path (HMMA); the sequences are too short to fill a 128-row tcgen05 tile per
@@ -65,8 +65,8 @@ GPV_DEVINL void load_a_frags(const bf16* s, int LD, int r0, int g, int t, uint32
 }
 
 // ======================================================================================== forward
-template <int DH>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+template <int DH, int NT>
+__global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int Sq = p.Sq, Sk = p.Sk;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float sl2 = p.scale * 1.4426950408889634f;
-  for (int r0 = warp * 16; r0 < Sqp; r0 += 64) {
+  for (int r0 = warp * 16; r0 < Sqp; r0 += NT / 2) {
     uint32_t qa[DH / 16][4];
     load_a_frags<DH>(Qs, LD, r0, g, t, qa);
     float o[DH / 8][4];
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 // ======================================================================================== backward
 // Pass 1 (warp owns 16 queries): D = rowsum(dO*O), dQ = scale * [P o (dO V^T - D)] K
 // Pass 2 (warp owns 16 keys):    dV = P^T dO,      dK = scale * [P o (dO V^T - D)]^T Q
-template <int DH>
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
+template <int DH, int NT>
+__global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int Sq = p.Sq, Sk = p.Sk;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
   const float sl2 = p.scale * 1.4426950408889634f;
 
   // ---------------------------------------------------------------- pass 1: D and dQ
-  for (int r0 = warp * 16; r0 < Sqp; r0 += 64) {
+  for (int r0 = warp * 16; r0 < Sqp; r0 += NT / 2) {
     uint32_t qa[DH / 16][4], da[DH / 16][4];
     load_a_frags<DH>(Qs, LD, r0, g, t, qa);
     load_a_frags<DH>(dOs, LD, r0, g, t, da);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
   __syncthreads();  // D_s complete
 
   // ---------------------------------------------------------------- pass 2: dK and dV
-  for (int r0 = warp * 16; r0 < Skp; r0 += 64) {
+  for (int r0 = warp * 16; r0 < Skp; r0 += NT / 2) {
     if (r0 >= ((Sk + 15) & ~15)) break;
     uint32_t ka[DH / 16][4], va[DH / 16][4];
     load_a_frags<DH>(Ks, LD, r0, g, t, ka);
@@ -403,13 +403,16 @@ static int launch_attn(const AttnParams& p, bool bwd, cudaStream_t st) {
     set_last_error("attention: Sq=%d Sk=%d dh=%d needs %zu bytes of shared memory (> 227 KB)", p.Sq, p.Sk, DH, smem);
     return GPV_ERR_ARG;
   }
-  auto kern = bwd ? attn_bwd_kernel<DH> : attn_fwd_kernel<DH>;
+  // 16 query (or key) rows per warp and pass: 12 warps cover the 300-token encoder maps in two rounds; the wide heads
+  // (d_h >= 48) keep 8 warps so that the backward's accumulators stay in registers.
+  constexpr int NTF = 256, NTB = (DH <= 32) ? 384 : 256;
+  auto kern = bwd ? attn_bwd_kernel<DH, NTB> : attn_fwd_kernel<DH, NTF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_last_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return GPV_ERR_CUDA;
   }
-  kern<<<p.B * p.H, 128, smem, st>>>(p);
+  kern<<<p.B * p.H, bwd ? NTB : NTF, smem, st>>>(p);
   return check_launch(bwd ? "attn_bwd_kernel" : "attn_fwd_kernel");
 }
 

@@ -55,6 +55,58 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
   if (threadIdx.x < 64 && col < N) atomicAdd(out + col, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
+// Vector form: a warp reads 32 x 16 bytes = 256 contiguous columns of one row per instruction, 8 warps stride the
+// rows, four rows in flight per thread; the 8 partial rows meet in shared memory and leave as one atomic per column.
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out,
+                                                         long long M, int N, int rows_per_cta) {
+  __shared__ float red[8][256 + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < N) {
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(dy + (r + 8 * u) * ld + c0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + r * ld + c0));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
+}
+
 // out[s][d] += sum_b x[b*S + s][d]   (gradient of a parameter broadcast over the batch, e.g. query_embed)
 __global__ void batch_reduce_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int B, int S, int D) {
   const long long total = (long long)S * D;
@@ -390,6 +442,15 @@ extern "C" int gpvb200_colsum(const void* dy, int64_t ld, float* out, int64_t M,
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(dy && out && N > 0, "colsum: bad arguments");
   if (M == 0) return GPV_OK;
+  if (N % 8 == 0 && ld % 8 == 0 && ((uintptr_t)dy & 15) == 0) {
+    const int gx = (N + 255) / 256;
+    int gy = (int)((2LL * kSMs + gx - 1) / gx);
+    if ((long long)gy * 32 > M) gy = (int)((M + 31) / 32);
+    if (gy < 1) gy = 1;
+    const int rows = (int)((M + gy - 1) / gy);
+    colsum_vec_kernel<<<dim3(gx, gy), 256, 0, ST>>>((const bf16*)dy, ld, out, M, N, rows);
+    return check_launch("colsum_vec_kernel");
+  }
   const int gx = (N + 63) / 64;
   int gy = (int)((2LL * kSMs + gx - 1) / gx);
   if ((long long)gy * 64 > M) gy = (int)((M + 63) / 64);

@@ -30,7 +30,8 @@ struct KParams {
   int ntaps;
   int tap_dh[9], tap_dw[9], tap_w[9];
   int OH, OW, os, ooh, oow;
-  int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32;
+  int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal;
+  uint32_t epi_warp_bytes, epi_aux_off, epi_slot_stride;   // per-warp epilogue slabs (coalesced path), see epi_layout()
   float alpha;
   void* D;
   bf16* D2;
@@ -65,20 +66,123 @@ GPV_DEVINL Work decode_work(const KParams& p, int w) {
 
 GPV_DEVINL uint4 ldg_u4(const bf16* ptr) { return __ldg(reinterpret_cast<const uint4*>(ptr)); }
 
-// One 32-column slice of an accumulator row: v = alpha*acc*rowscale + bias + residual; D2 = v; v = act(v);
-// v *= mask(aux) / gelu'(aux); store.  `rr` / `aa` hold the prefetched residual / aux slice when `fast`.
-GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float rs, long long off_d, long long off_r,
-                          long long off_a, int nb, int nvalid, bool fast, const uint4 (&rr)[4], const uint4 (&aa)[4]) {
-  float v[kChunk];
-  if (rs != 1.0f) {  // rs = alpha * rowscale folded by the caller; 1 for most layers
+// ---- coalesced epilogue -----------------------------------------------------------------------------------
+// Each epilogue warp owns a 32-row x 32-column slab of the tile per step.  A thread's natural view is one ROW
+// (tcgen05.ld 32x32b: lane = row), but one row-slice is only 64 bytes of global memory, so row-per-thread accesses
+// touch 32 cache lines per instruction.  Instead every global access uses the COALESCED arrangement -- access j of
+// lane l is 16-byte chunk (l & 3) of row 8j + (l >> 2): 8 rows x 64 contiguous bytes per warp instruction -- and a
+// swizzled 2 KB shared-memory slab converts between the two views: chunk c of row r lives at slot
+// r*4 + (c ^ ((r >> 1) & 3)) (conflict-free both ways).
+// Residual / aux slices are brought in with cp.async (global -> shared, no registers, no scoreboard) one slab ahead,
+// into a two-slot ring per warp; the TMA producer warp L2-prefetches the tile's residual / aux rows several tiles
+// earlier, so the cp.async traffic hits L2.  (ncu on the first version, which prefetched into registers with LDG:
+// every epilogue warp sat on long-scoreboard stalls because later loads share scoreboards with the prefetch.)
+GPV_DEVINL int slab_slot(int row, int c) { return row * 4 + (c ^ ((row >> 1) & 3)); }
+GPV_DEVINL void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+GPV_DEVINL uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+GPV_DEVINL void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+GPV_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+GPV_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+GPV_DEVINL void prefetch_l2_bulk(const void* g, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
+
+GPV_DEVINL void unpack8(const uint4& q, float* v, bool add) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]) * rs;
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    if (add) {
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    } else {
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  }
+}
+GPV_DEVINL uint4 pack8(const float* v) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  return o;
+}
+
+// Global row (pixel) index of tile row r of work item wk, and whether it exists.
+GPV_DEVINL bool tile_row(const KParams& p, const Work& wk, int r, long long* pix) {
+  if (p.mode == 1) {
+    const int tpi = p.tiles_h * p.tiles_w;
+    const int img = wk.mt / tpi;
+    const int rr_ = wk.mt % tpi;
+    const int ho = (rr_ / p.tiles_w) * p.th + r / p.tw, wo = (rr_ % p.tiles_w) * p.tw + r % p.tw;
+    *pix = ((long long)img * p.OH + (ho * p.os + p.ooh)) * p.OW + (wo * p.os + p.oow);
+    return (r < p.th * p.tw) && ho < p.Ho && wo < p.Wo;
+  }
+  *pix = (long long)wk.mt * BM + r;
+  return *pix < p.M;
+}
+
+// Epilogue variant F: -1 = every flag read from KParams at run time (any combination, any output type);
+// F >= 0 = compile-time flags of the bf16 coalesced path (bit 0 bias, bit 1 bf16 residual, bits 2-3 activation,
+// bits 4-5 aux mode, bit 6 second output D2), so the hot variants carry no flag tests.
+template <int F>
+struct EpiFlags {
+  GPV_DEVINL static bool bias(const KParams& p) { if constexpr (F < 0) return p.bias != nullptr; else return (F & 1) != 0; }
+  GPV_DEVINL static bool res(const KParams& p) { if constexpr (F < 0) return p.residual != nullptr; else return (F & 2) != 0; }
+  GPV_DEVINL static int act(const KParams& p) { if constexpr (F < 0) return p.act; else return (F >> 2) & 3; }
+  GPV_DEVINL static int aux(const KParams& p) { if constexpr (F < 0) return p.aux_mode; else return (F >> 4) & 3; }
+  GPV_DEVINL static bool d2(const KParams& p) { if constexpr (F < 0) return p.D2 != nullptr; else return (F & 64) != 0; }
+  GPV_DEVINL static bool res_fp32(const KParams& p) { if constexpr (F < 0) return p.res_fp32 != 0; else return false; }
+  GPV_DEVINL static bool d_fp32(const KParams& p) { if constexpr (F < 0) return p.d_fp32 != 0; else return false; }
+};
+
+template <int F>
+GPV_DEVINL void epi_activation(const KParams& p, float (&v)[kChunk]) {
+  const int act = EpiFlags<F>::act(p);
+  if (act == GPVB200_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (act == GPVB200_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = gelu_erf(v[j]);
+  } else if (act == GPVB200_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = 1.0f / (1.0f + __expf(-v[j]));
+  }
+}
+template <int F>
+GPV_DEVINL void epi_aux(const KParams& p, float (&v)[kChunk], const float (&a)[kChunk]) {
+  if (EpiFlags<F>::aux(p) == GPVB200_AUX_RELU_MASK) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
   } else {
 #pragma unroll
-    for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]);
+    for (int j = 0; j < kChunk; ++j) v[j] *= gelu_erf_grad(a[j]);
   }
-  if (p.bias != nullptr) {
-    if (fast) {
+}
+
+// One 32-column slice of an accumulator row, the thread's own row addressed directly:
+// v = alpha*acc*rowscale + bias + residual; D2 = v; v = act(v); v *= mask(aux) / gelu'(aux); store.
+//   vec = false  scalar (ragged N edge, unaligned operands);  vec = true  16-byte vectors (fp32 / atomic outputs)
+template <int F>
+GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float rs, long long row_off, long long pix, int nb,
+                          int nvalid, bool vec) {
+  typedef EpiFlags<F> E;
+  const long long off_d = row_off + pix * p.ldd + nb, off_r = row_off + pix * p.ldr + nb, off_a = row_off + pix * p.ldaux + nb;
+  float v[kChunk];
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]) * rs;
+  if (E::bias(p)) {
+    if (vec) {
 #pragma unroll
       for (int j = 0; j < kChunk; j += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
@@ -90,23 +194,15 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
         if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
     }
   }
-  if (p.residual != nullptr) {
-    if (p.res_fp32) {
+  if (E::res(p)) {
+    if (E::res_fp32(p)) {
       const float* rp = reinterpret_cast<const float*>(p.residual) + off_r;
 #pragma unroll
       for (int j = 0; j < kChunk; ++j)
         if (j < nvalid) v[j] += rp[j];
-    } else if (fast) {
+    } else if (vec) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t w[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(w[j]);
-          v[8 * i + 2 * j] += f.x;
-          v[8 * i + 2 * j + 1] += f.y;
-        }
-      }
+      for (int i = 0; i < 4; ++i) unpack8(ldg_u4(p.residual + off_r + 8 * i), v + 8 * i, true);
     } else {
       const bf16* rp = p.residual + off_r;
 #pragma unroll
@@ -114,62 +210,34 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
         if (j < nvalid) v[j] += __bfloat162float(rp[j]);
     }
   }
-  if (p.D2 != nullptr) {
+  if (E::d2(p)) {
     bf16* dp = p.D2 + off_d;
-    if (fast) {
+    if (vec) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 o;
-        o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);     o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        *reinterpret_cast<uint4*>(dp + 8 * i) = o;
-      }
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dp + 8 * i) = pack8(v + 8 * i);
     } else {
 #pragma unroll
       for (int j = 0; j < kChunk; ++j)
         if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
     }
   }
-  if (p.act == GPVB200_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (p.act == GPVB200_ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == GPVB200_ACT_SIGMOID) {
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j) v[j] = 1.0f / (1.0f + __expf(-v[j]));
-  }
-  if (p.aux_mode != GPVB200_AUX_NONE) {
+  epi_activation<F>(p, v);
+  if (E::aux(p) != GPVB200_AUX_NONE) {
     float a[kChunk];
-    if (fast) {
+    if (vec) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t w[4] = {aa[i].x, aa[i].y, aa[i].z, aa[i].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(w[j]);
-          a[8 * i + 2 * j] = f.x;
-          a[8 * i + 2 * j + 1] = f.y;
-        }
-      }
+      for (int i = 0; i < 4; ++i) unpack8(ldg_u4(p.aux + off_a + 8 * i), a + 8 * i, false);
     } else {
       const bf16* ap = p.aux + off_a;
 #pragma unroll
       for (int j = 0; j < kChunk; ++j) a[j] = (j < nvalid) ? __bfloat162float(ap[j]) : 0.0f;
     }
-    if (p.aux_mode == GPVB200_AUX_RELU_MASK) {
-#pragma unroll
-      for (int j = 0; j < kChunk; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < kChunk; ++j) v[j] *= gelu_erf_grad(a[j]);
-    }
+    epi_aux<F>(p, v, a);
   }
-  if (p.d_fp32) {
+  if (E::d_fp32(p)) {
     float* dp = reinterpret_cast<float*>(p.D) + off_d;
     if (p.d_atomic) {
-      if (fast) {  // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic requests
+      if (vec) {  // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic requests
 #pragma unroll
         for (int j = 0; j < kChunk; j += 4)
           atomicAdd(reinterpret_cast<float4*>(dp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
@@ -178,7 +246,7 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
         for (int j = 0; j < kChunk; ++j)
           if (j < nvalid) atomicAdd(dp + j, v[j]);
       }
-    } else if (fast) {
+    } else if (vec) {
 #pragma unroll
       for (int j = 0; j < kChunk; j += 4)
         *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -189,14 +257,9 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
     }
   } else {
     bf16* dp = reinterpret_cast<bf16*>(p.D) + off_d;
-    if (fast) {
+    if (vec) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 o;
-        o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);     o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        *reinterpret_cast<uint4*>(dp + 8 * i) = o;
-      }
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dp + 8 * i) = pack8(v + 8 * i);
     } else {
 #pragma unroll
       for (int j = 0; j < kChunk; ++j)
@@ -205,10 +268,74 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
   }
 }
 
+// ---- coalesced bf16 path.  Per work item and lane: the global addresses of this lane's four coalesced 16-byte chunks
+// (slab row 8j + (lane >> 2), chunk lane & 3, first column of the warp's half) of the residual, aux, D and D2.
+struct CoalRows {
+  const bf16* r[4];
+  const bf16* a[4];
+  bf16* d[4];
+  bf16* d2[4];
+  uint32_t ok;   // bit j: slab row 8j + (lane >> 2) exists
+};
+// Byte offsets inside a 2 KB slab: co = this lane's coalesced chunk of row-group 0 (row-group j is 512 B further),
+// own[i] = chunk i of this lane's own row.
+struct SlabOffs {
+  uint32_t co, own[4];
+};
+
+// Own-row bf16 slice (4 x 16 bytes) -> swizzled slab -> coalesced global store at column offset `col` (elements).
+GPV_DEVINL void store_slab(bf16* const (&dst)[4], uint32_t ok, int col, const float* v, uint32_t slab, const SlabOffs& so) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sts128(slab + so.own[i], pack8(v + 8 * i));
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 o = lds128(slab + so.co + 512u * j);
+    if ((ok >> j) & 1u) *reinterpret_cast<uint4*>(dst[j] + col) = o;
+  }
+  __syncwarp();
+}
+
+// Same arithmetic as epi_chunk for one full 32-column slab of a warp; residual / aux slices wait in the slabs res_s /
+// aux_s (cp.async), outputs leave through out_s (the slab of an input already consumed, or a slab of its own).
+template <int F>
+GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], float rs, const float* bias, int col,
+                               uint32_t res_s, uint32_t aux_s, uint32_t out_s, const CoalRows& cr, const SlabOffs& so) {
+  typedef EpiFlags<F> E;
+  float v[kChunk];
+  if (rs != 1.0f) {  // rs = alpha * rowscale; 1 for most layers
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]) * rs;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+  if (E::bias(p)) {
+#pragma unroll
+    for (int j = 0; j < kChunk; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (E::res(p)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack8(lds128(res_s + so.own[i]), v + 8 * i, true);
+  }
+  if (E::d2(p)) store_slab(cr.d2, cr.ok, col, v, out_s, so);
+  epi_activation<F>(p, v);
+  if (E::aux(p) != GPVB200_AUX_NONE) {
+    float a[kChunk];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack8(lds128(aux_s + so.own[i]), a + 8 * i, false);
+    epi_aux<F>(p, v, a);
+  }
+  store_slab(cr.d, cr.ok, col, v, out_s, so);
+}
+
 // Persistent kernel: each CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ... (an item = one
 // 128 x BN output tile of one batch/tap and one K split).  Two TMEM accumulator buffers let the epilogue of item j
 // overlap the TMA/MMA main loop of item j+1.
-template <int BN>
+template <int BN, int F>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ KParams p) {
@@ -228,6 +355,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc_full = empty_bar + S;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  // per epilogue warp: residual ring 2 x 2 KB (also the output transposition slab), aux ring 2 x 2 KB, bias slice 512 B
+  const uint32_t stg_base = (smem_u32(tmem_slot + 4) + 127u) & ~127u;
   constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
 
   if (warp == 0 && lane == 0) {
@@ -254,11 +383,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ================================================================== TMA producer
-    if (lane == 0) {
-      int gi = 0;  // stage-use counter, runs across work items
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const Work wk = decode_work(p, w);
-        const int n0 = wk.nt * BN, m0 = wk.mt * BM, bz = wk.bz;
+    // Lane 0 issues the TMA loads; before that, all 32 lanes L2-prefetch the residual / aux rows the epilogue of this
+    // work item will read (the producer runs 2+ tiles ahead of the epilogue, so they are L2 hits by then).
+    const bool pf_r = p.coal && p.residual != nullptr, pf_a = p.coal && p.aux_mode != GPVB200_AUX_NONE;
+    int gi = 0;  // stage-use counter, runs across work items
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const Work wk = decode_work(p, w);
+      const int n0 = wk.nt * BN, m0 = wk.mt * BM, bz = wk.bz;
+      if (pf_r || pf_a) {
+        const uint32_t bytes = (uint32_t)(min(BN, p.N - n0) * 2) & ~15u;
+        const long long row_off = (long long)bz * p.d_batch_stride + n0;
+        if (bytes > 0) {
+#pragma unroll
+          for (int r = lane; r < BM; r += 32) {
+            long long pix;
+            if (tile_row(p, wk, r, &pix)) {
+              if (pf_r) prefetch_l2_bulk(p.residual + row_off + pix * p.ldr, bytes);
+              if (pf_a) prefetch_l2_bulk(p.aux + row_off + pix * p.ldaux, bytes);
+            }
+          }
+        }
+      }
+      if (lane == 0) {
         int img = 0, ho0 = 0, wo0 = 0;
         if (p.mode == 1) {
           const int tpi = p.tiles_h * p.tiles_w;
@@ -312,7 +458,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, wi, hi, im);
           }
         }
+      } else {
+        gi += wk.it1 - wk.it0;
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
@@ -350,49 +499,64 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ================================================================== epilogue (warps 2..9)
+    typedef EpiFlags<F> E;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;       // which half of the BN columns
     const int r = q * 32 + lane;
     constexpr int kChunksPerHalf = BN / 2 / kChunk;
+    const int cbase = half * (BN / 2);
+    const bool coal = F >= 0 || p.coal != 0;
+    const uint32_t res_ring = stg_base + (uint32_t)(warp - 2) * p.epi_warp_bytes, aux_ring = res_ring + p.epi_aux_off;
+    const uint32_t slot_stride = p.epi_slot_stride;
+    const bool pre_r = E::res(p) && !E::res_fp32(p), pre_a = E::aux(p) != GPVB200_AUX_NONE;
+    const uint32_t out_ring = (pre_r || !pre_a) ? res_ring : aux_ring;
+    SlabOffs so;
+    so.co = 16u * slab_slot(lane >> 2, lane & 3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) so.own[i] = 16u * slab_slot(lane, i);
+    const long long ldd = p.ldd, ldr = p.ldr, lda = p.ldaux;
     int j = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
       const Work wk = decode_work(p, w);
-      const int n0 = wk.nt * BN, m0 = wk.mt * BM, bz = wk.bz;
+      const int n0 = wk.nt * BN, bz = wk.bz;
       const int buf = j & 1;
-      bool row_ok;
       long long pix;
-      if (p.mode == 1) {
-        const int tpi = p.tiles_h * p.tiles_w;
-        const int img = wk.mt / tpi;
-        const int rr_ = wk.mt % tpi;
-        const int ho = (rr_ / p.tiles_w) * p.th + r / p.tw, wo = (rr_ % p.tiles_w) * p.tw + r % p.tw;
-        row_ok = (r < p.th * p.tw) && ho < p.Ho && wo < p.Wo;
-        pix = ((long long)img * p.OH + (ho * p.os + p.ooh)) * p.OW + (wo * p.os + p.oow);
-      } else {
-        row_ok = (m0 + r) < p.M;
-        pix = m0 + r;
-      }
+      const bool row_ok = tile_row(p, wk, r, &pix);
       const long long row_off = (long long)bz * p.d_batch_stride;  // mode 0: batch, mode 2: tap, mode 1: bz == 0
-      const float rs = p.alpha * ((p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[m0 + r] : 1.0f);
-      const int cbase = half * (BN / 2);
-      const bool pre_r = p.residual != nullptr && !p.res_fp32, pre_a = p.aux_mode != GPVB200_AUX_NONE;
+      const float rs = p.alpha * ((p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[wk.mt * BM + r] : 1.0f);
+      CoalRows cr;
+      cr.ok = 0;
+      if (coal) {
+        const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+        const long long cofs = row_off + n0 + cbase + (lane & 3) * 8;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int row = 8 * jj + (lane >> 2);
+          const long long pj = __shfl_sync(0xffffffffu, pix, row);
+          cr.ok |= ((okmask >> row) & 1u) << jj;
+          cr.d[jj] = reinterpret_cast<bf16*>(p.D) + pj * ldd + cofs;
+          if (E::d2(p)) cr.d2[jj] = p.D2 + pj * ldd + cofs;
+          if (pre_r) cr.r[jj] = p.residual + pj * ldr + cofs;
+          if (pre_a) cr.a[jj] = p.aux + pj * lda + cofs;
+        }
+      }
+      const float* bias_t = p.bias + n0 + cbase;
 
-      uint4 rr[4], aa[4];
-      auto prefetch = [&](int c) {
-        const int nb = n0 + cbase + c * kChunk;
-        const bool fast = p.vec_ok && row_ok && (nb + kChunk <= p.N);
-        if (fast && pre_r) {
-          const bf16* rp = p.residual + row_off + pix * p.ldr + nb;
+      // cp.async the residual / aux slices of chunk c into ring slot c & 1 (coalesced arrangement); one commit per call
+      auto issue = [&](int c) {
+        if (n0 + cbase + (c + 1) * kChunk <= p.N) {
+          const uint32_t so_c = (uint32_t)(c & 1) * slot_stride + so.co;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) rr[i] = ldg_u4(rp + 8 * i);
+          for (int jj = 0; jj < 4; ++jj) {
+            if ((cr.ok >> jj) & 1u) {
+              if (pre_r) cp_async16(res_ring + so_c + 512u * jj, cr.r[jj] + c * kChunk);
+              if (pre_a) cp_async16(aux_ring + so_c + 512u * jj, cr.a[jj] + c * kChunk);
+            }
+          }
         }
-        if (fast && pre_a) {
-          const bf16* ap = p.aux + row_off + pix * p.ldaux + nb;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) aa[i] = ldg_u4(ap + 8 * i);
-        }
+        cp_async_commit();
       };
-      prefetch(0);  // independent of the accumulator: overlaps the wait below
+      if (coal) issue(0);  // independent of the accumulator: overlaps the wait below
       mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
@@ -401,21 +565,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (nb < p.N) {  // warp-uniform
           uint32_t acc[kChunk];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + c * kChunk), acc);
-          uint4 cr[4], ca[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            cr[i] = rr[i];
-            ca[i] = aa[i];
+          if (coal) {
+            if (c + 1 < kChunksPerHalf) issue(c + 1);
+            else cp_async_commit();
+            cp_async_wait<1>();   // everything but the slab just requested has landed (this thread's copies) ...
+            __syncwarp();         // ... and every other lane's
           }
-          if (c + 1 < kChunksPerHalf && nb + kChunk < p.N) prefetch(c + 1);
           tmem_ld_wait();
-          if (row_ok) {
-            const int nvalid = min(kChunk, p.N - nb);
-            const bool fast = p.vec_ok && nvalid == kChunk;
-            epi_chunk(p, acc, rs, row_off + pix * p.ldd + nb, row_off + pix * p.ldr + nb, row_off + pix * p.ldaux + nb, nb, nvalid,
-                      fast, cr, ca);
+          const int nvalid = min(kChunk, p.N - nb);
+          const bool full = nvalid == kChunk;
+          if (coal && full) {                     // whole warp takes part (shared-memory slabs)
+            const uint32_t sc = (uint32_t)(c & 1) * slot_stride;
+            epi_chunk_coal<F>(p, acc, rs, bias_t, c * kChunk, res_ring + sc, aux_ring + sc, out_ring + sc, cr, so);
+          } else if (row_ok) {
+            epi_chunk<F>(p, acc, rs, row_off, pix, nb, nvalid, p.vec_ok && full);
           }
         }
+      }
+      if (coal) {
+        cp_async_wait<0>();
+        __syncwarp();           // the slabs are free for the next work item
       }
       tc_fence_before();
       __syncwarp();
@@ -558,11 +727,11 @@ static int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, int F>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
       return GPV_ERR_CUDA;
@@ -570,8 +739,22 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
     configured = true;
   }
   const int grid = kp.total_work < num_sms() ? kp.total_work : num_sms();
-  umma_gemm_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mb, kp);
+  umma_gemm_kernel<BN, F><<<grid, kThreads, smem, st>>>(ma, mb, kp);
   return check_launch("umma_gemm_kernel");
+}
+
+// Epilogue variants compiled with their flags fixed (the bf16 coalesced path of the hot layers); anything else runs
+// the run-time-flag kernel (F = -1).  bit 0 bias, bit 1 residual, bits 2-3 act, bits 4-5 aux, bit 6 D2.
+#define GPV_EPI_VARIANTS(X) X(0) X(1) X(2) X(3) X(5) X(7) X(16) X(18) X(32) X(73)
+
+template <int BN>
+static int launch_bn(int f, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, size_t smem, cudaStream_t st) {
+  switch (f) {
+#define GPV_CASE(V) case V: return launch<BN, V>(ma, mb, kp, smem, st);
+    GPV_EPI_VARIANTS(GPV_CASE)
+#undef GPV_CASE
+    default: return launch<BN, -1>(ma, mb, kp, smem, st);
+  }
 }
 
 }  // namespace gpv
@@ -621,6 +804,16 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
     auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
     kp.vec_ok = ((kp.ldd & 7) == 0) && ((kp.ldr & 7) == 0) && ((kp.ldaux & 7) == 0) && ((kp.d_batch_stride & 7) == 0) &&
                 al16(d->D) && al16(d->D2) && al16(d->residual) && al16(d->aux) && al16(d->bias);
+  }
+  // coalesced epilogue: bf16 outputs (and bf16 residual / aux) move as 8 rows x 64 bytes per warp instruction
+  kp.coal = kp.vec_ok && !kp.d_fp32 && !kp.res_fp32 && !(d->D2 && d->aux_mode != GPVB200_AUX_NONE);
+  {
+    // per-warp slabs: a 2-slot cp.async ring (2 x 2 KB) per streamed input (residual, aux); the output is transposed
+    // through the slot of an input that has been consumed, or through a 2 KB slab of its own when there is none
+    const int rings = (kp.coal && d->residual ? 1 : 0) + (kp.coal && d->aux_mode != GPVB200_AUX_NONE ? 1 : 0);
+    kp.epi_warp_bytes = rings ? 4096u * rings : 2048u;
+    kp.epi_aux_off = (d->residual && rings == 2) ? 4096u : 0u;
+    kp.epi_slot_stride = rings ? 2048u : 0u;
   }
   kp.stride = d->stride > 0 ? d->stride : 1;
   kp.os = d->out_stride > 0 ? d->out_stride : 1;
@@ -810,14 +1003,18 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   const uint32_t a_bytes = kp.a_mn ? 2u * kp.bk * 128u : 128u * 128u;
   const uint32_t b_bytes = kp.b_mn ? (uint32_t)(BN / 64) * kp.bk * 128u : (uint32_t)BN * 128u;
   const uint32_t stage = a_bytes + b_bytes;
-  int nst = (int)((196u * 1024u) / stage);
+  const uint32_t epi_smem = kEpiWarps * kp.epi_warp_bytes + 128;     // 16 / 32 / 64 KB of epilogue slabs
+  int nst = (int)((227u * 1024u - 1024u - 256u - epi_smem) / stage);
   if (nst > 6) nst = 6;
   GPV_REQUIRE(nst >= 2, "gemm: stage of %u bytes does not fit twice in shared memory", stage);
   kp.nstages = nst;
-  const size_t smem = (size_t)nst * stage + 1024 /*alignment slack*/ + (2 * nst + 4) * 8 + 16;
+  const size_t smem = (size_t)nst * stage + 1024 /*alignment slack*/ + (2 * nst + 4) * 8 + 32 + epi_smem;
 
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 256) return launch<256>(ma, mb, kp, smem, st);
-  if (BN == 128) return launch<128>(ma, mb, kp, smem, st);
-  return launch<64>(ma, mb, kp, smem, st);
+  int f = -1;
+  if (kp.coal)
+    f = (d->bias ? 1 : 0) | (d->residual ? 2 : 0) | ((d->act & 3) << 2) | ((d->aux_mode & 3) << 4) | (d->D2 ? 64 : 0);
+  if (BN == 256) return launch_bn<256>(f, ma, mb, kp, smem, st);
+  if (BN == 128) return launch_bn<128>(f, ma, mb, kp, smem, st);
+  return launch_bn<64>(f, ma, mb, kp, smem, st);
 }

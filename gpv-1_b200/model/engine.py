@@ -17,6 +17,7 @@ Backbone backbone.py:71-79, Transformer transformer.py:46-58 -> BertConnectionLa
 decode_text gpv.py:449-466 -> GPVCriterion losses.py:155-176 -> SetCriterion set_criterion.py:150-191 ->
 HungarianMatcher matcher.py:32-77, and autograd's backward of all of it.
 """
+import contextlib
 import math
 
 import torch
@@ -79,6 +80,8 @@ class Engine:
         self._versions = None
         self._pos_cache = {}
         self.saved = None
+        self.concurrent = True                                # run independent branches on side streams (lanes)
+        self._lanes, self._dirty, self._keep = {}, set(), []
 
     # ================================================================================================ weights
     def _setup_weights(self):
@@ -249,8 +252,34 @@ class Engine:
 
     # ================================================================================================ small helpers
     def _done(self, stage):
+        self._join()
         if self.on_stage_done is not None:
             self.on_stage_done(stage)
+
+    # ---- concurrent branches.  Most GEMMs of the transformer stacks cover 15-75 of the 148 SMs, so independent
+    # branches (weight/bias gradients beside the data-gradient chain, BERT beside the backbone, K/V projections of a
+    # fixed memory beside the decoder's self-attention) are enqueued on side streams ("lanes"); inside a captured
+    # step they become parallel branches of the CUDA graph.  Rule that keeps the caching allocator safe: every tensor
+    # allocated on the issuing stream and read on a lane is passed to _aside() and stays referenced until _join().
+    def _aside(self, *keep, lane=0):
+        if not self.concurrent or self.dev.type != "cuda":
+            return contextlib.nullcontext()
+        st = self._lanes.get(lane)
+        if st is None:
+            st = self._lanes[lane] = torch.cuda.Stream(device=self.dev)
+        st.wait_stream(torch.cuda.current_stream())
+        self._keep.extend(t for t in keep if t is not None)
+        self._dirty.add(lane)
+        return torch.cuda.stream(st)
+
+    def _join(self, lane=None):
+        lanes = list(self._dirty) if lane is None else ([lane] if lane in self._dirty else [])
+        cur = torch.cuda.current_stream() if lanes else None
+        for ln in lanes:
+            cur.wait_stream(self._lanes[ln])
+            self._dirty.discard(ln)
+        if not self._dirty:
+            self._keep.clear()
 
     def _pos(self, H, W):
         key = (H, W)
@@ -262,9 +291,10 @@ class Engine:
                  bias=True):
         """dW += dy^T x, db += colsum(dy), returns dx = (dy W + residual) (*) mask."""
         g = gkey or name
-        k.linear_wgrad(dy, x, self.G[g + ".weight"].view(dy.shape[1], -1))
-        if bias:
-            k.colsum(dy, self.G[g + ".bias"])
+        with self._aside(dy, x):
+            k.linear_wgrad(dy, x, self.G[g + ".weight"].view(dy.shape[1], -1))
+            if bias:
+                k.colsum(dy, self.G[g + ".bias"])
         if need_dx:
             return k.linear_dgrad(dy, self.W[wkey or (name + ".weight")], aux=aux, aux_mode=aux_mode, residual=residual)
         return None
@@ -317,27 +347,33 @@ class Engine:
         h2f, h1f, xf = h2.view(-1, planes), h1.view(-1, planes), x.view(-1, inp)
         # conv3 (1x1)
         dh2 = k.linear_dgrad(dpre2, W[p + ".conv3.weight"][0], aux=h2f, aux_mode=MASK_RELU)
-        k.linear_wgrad(dpre2, h2f, G[p + ".conv3.weight"].view(planes * 4, planes), rowscale=sc[p + ".bn3"])
+        with self._aside(dpre):
+            k.linear_wgrad(dpre2, h2f, G[p + ".conv3.weight"].view(planes * 4, planes), rowscale=sc[p + ".bn3"])
+            if ds:
+                gds = G[p + ".downsample.0.weight"].view(1, planes * 4, inp)
+                if s == 1:
+                    k.linear_wgrad(dpre2, xf, gds[0], rowscale=sc[p + ".downsample.1"])
+                else:
+                    k.conv_wgrad(dpre, x, gds, ksize=1, stride=s, rowscale=sc[p + ".downsample.1"])
         # conv2 (3x3, stride s)
         dh2 = dh2.view(h2.shape)
         dh1 = conv_dgrad(dh2, W[p + ".conv2.weight"], ksize=3, stride=s, in_hw=(H, Wd), aux=h1, aux_mode=MASK_RELU)
-        k.conv_wgrad(dh2, h1, self.Gp[p + ".conv2.weight"], ksize=3, stride=s, rowscale=sc[p + ".bn2"])
+        with self._aside(dh2):
+            k.conv_wgrad(dh2, h1, self.Gp[p + ".conv2.weight"], ksize=3, stride=s, rowscale=sc[p + ".bn2"])
         # identity / downsample branch
         if ds:
-            gds = G[p + ".downsample.0.weight"].view(1, planes * 4, inp)
-            if s == 1:
-                k.linear_wgrad(dpre2, xf, gds[0], rowscale=sc[p + ".downsample.1"])
-            else:
-                k.conv_wgrad(dpre, x, gds, ksize=1, stride=s, rowscale=sc[p + ".downsample.1"])
             didn = conv_dgrad(dpre, W[p + ".downsample.0.weight"], ksize=1, stride=s, in_hw=(H, Wd)) if need_dx else None
         else:
             didn = dpre
         # conv1 (1x1): dx = (dh1 W1 + didn) * relu'(x)  -> already the masked gradient of the previous block
-        k.linear_wgrad(dh1.view(-1, planes), xf, G[p + ".conv1.weight"].view(planes, inp), rowscale=sc[p + ".bn1"])
-        if not need_dx:
-            return None
-        return k.linear_dgrad(dh1.view(-1, planes), W[p + ".conv1.weight"][0], residual=didn.view(-1, inp), aux=xf,
-                              aux_mode=MASK_RELU).view(x.shape)
+        with self._aside(dh1):
+            k.linear_wgrad(dh1.view(-1, planes), xf, G[p + ".conv1.weight"].view(planes, inp), rowscale=sc[p + ".bn1"])
+        dx = None
+        if need_dx:
+            dx = k.linear_dgrad(dh1.view(-1, planes), W[p + ".conv1.weight"][0], residual=didn.view(-1, inp), aux=xf,
+                                aux_mode=MASK_RELU).view(x.shape)
+        self._join()            # the saved activations of this block are released by the caller
+        return dx
 
     def _backbone_bwd(self, dpre, acts):
         """dpre: gradient w.r.t. the pre-ReLU output of the last block (already masked), NHWC bf16."""
@@ -387,12 +423,15 @@ class Engine:
                         B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5, causal=causal)
         wi = W[f"{p}.{attn}.in_proj_weight"]
         gw, gb = G[f"{p}.{attn}.in_proj_weight"], G[f"{p}.{attn}.in_proj_bias"]
-        k.colsum(dqkv, gb)
+        with self._aside(dqkv):
+            k.colsum(dqkv, gb)
+            if not has_pos:
+                k.linear_wgrad(dqkv, x, gw)
+            else:
+                k.linear_wgrad(dqkv[:, :2 * D], qk_in, gw[:2 * D])
+                k.linear_wgrad(dqkv[:, 2 * D:], x, gw[2 * D:])
         if not has_pos:
-            k.linear_wgrad(dqkv, x, gw)
             return k.linear_dgrad(dqkv, wi, residual=dpre)
-        k.linear_wgrad(dqkv[:, :2 * D], qk_in, gw[:2 * D])
-        k.linear_wgrad(dqkv[:, 2 * D:], x, gw[2 * D:])
         dx = k.linear_dgrad(dqkv[:, 2 * D:], wi[2 * D:], residual=dpre)
         if pos_grad is None:
             return k.linear_dgrad(dqkv[:, :2 * D], wi[:2 * D], residual=dx)
@@ -400,19 +439,29 @@ class Engine:
         k.batch_reduce(dqk_in, pos_grad, B, S)
         return k.add(dx, dqk_in, out=dx)
 
-    def _cross_attn_fwd(self, p, x, qpos, kmem, vmem, B, Sq, Sk, H, *, eps=1e-5, norm="norm2"):
-        """y = LN(x + out_proj(MHA(q = x + qpos, k = kmem, v = vmem)))  (kmem already carries its position)."""
+    def _cross_kv(self, p, kmem, vmem):
+        """K/V projections of a cross-attention memory: independent of the decoder state, so the callers enqueue them
+        for every layer at once on a lane, beside the first layers of the decoder."""
         W, Pm = self.W, self.P
-        D = x.shape[1]
+        D = kmem.shape[1]
         wi, bi_ = W[f"{p}.multihead_attn.in_proj_weight"], Pm[f"{p}.multihead_attn.in_proj_bias"]
-        q_in = k.add_rowbcast(x, qpos) if qpos is not None else x
-        q = k.linear(q_in, wi[:D], bi_[:D])
         kv = torch.empty((kmem.shape[0], 2 * D), device=self.dev, dtype=BF16)
         if kmem is vmem:
             k.linear(kmem, wi[D:], bi_[D:], out=kv)
         else:
             k.linear(kmem, wi[D:2 * D], bi_[D:2 * D], out=kv[:, :D])
             k.linear(vmem, wi[2 * D:], bi_[2 * D:], out=kv[:, D:])
+        return kv
+
+    def _cross_attn_fwd(self, p, x, qpos, kmem, vmem, B, Sq, Sk, H, *, eps=1e-5, norm="norm2", kv=None):
+        """y = LN(x + out_proj(MHA(q = x + qpos, k = kmem, v = vmem)))  (kmem already carries its position)."""
+        W, Pm = self.W, self.P
+        D = x.shape[1]
+        wi, bi_ = W[f"{p}.multihead_attn.in_proj_weight"], Pm[f"{p}.multihead_attn.in_proj_bias"]
+        q_in = k.add_rowbcast(x, qpos) if qpos is not None else x
+        q = k.linear(q_in, wi[:D], bi_[:D])
+        if kv is None:
+            kv = self._cross_kv(p, kmem, vmem)
         dh = D // H
         o, lse = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=dh ** -0.5)
         pre = k.linear(o, W[f"{p}.multihead_attn.out_proj.weight"], Pm[f"{p}.multihead_attn.out_proj.bias"], residual=x)
@@ -433,15 +482,18 @@ class Engine:
         k.attention_bwd(q, kv[:, :D], kv[:, D:], o, do, lse, dq, dkv[:, :D], dkv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh,
                         scale=dh ** -0.5)
         wi, gw, gb = W[a + ".in_proj_weight"], G[a + ".in_proj_weight"], G[a + ".in_proj_bias"]
-        k.colsum(dq, gb[:D])
-        k.colsum(dkv, gb[D:])
-        k.linear_wgrad(dq, q_in, gw[:D])
+        with self._aside(dq, dkv):
+            k.colsum(dq, gb[:D])
+            k.colsum(dkv, gb[D:])
+            k.linear_wgrad(dq, q_in, gw[:D])
+            if kmem is vmem:
+                k.linear_wgrad(dkv, kmem, gw[D:])
+            else:
+                k.linear_wgrad(dkv[:, :D], kmem, gw[D:2 * D])
+                k.linear_wgrad(dkv[:, D:], vmem, gw[2 * D:])
         if kmem is vmem:
-            k.linear_wgrad(dkv, kmem, gw[D:])
             dmem = k.linear_dgrad(dkv, wi[D:], residual=dmem)
         else:
-            k.linear_wgrad(dkv[:, :D], kmem, gw[D:2 * D])
-            k.linear_wgrad(dkv[:, D:], vmem, gw[2 * D:])
             dmem = k.linear_dgrad(dkv[:, :D], wi[D:2 * D], residual=dmem)
             dmem = k.linear_dgrad(dkv[:, D:], wi[2 * D:], residual=dmem)
         if pos_grad is None:
@@ -501,16 +553,20 @@ class Engine:
         D, H = self.D, self.h_co
         dh = D // H
         sc = 1.0 / math.sqrt(dh)
-        qkv1 = k.linear(lang, W[p + ".qkv1"], self.Bcat[p + ".qkv1"])
+        with self._aside(lang, lane=1):
+            qkv1 = k.linear(lang, W[p + ".qkv1"], self.Bcat[p + ".qkv1"])
         qkv2 = k.linear(vis, W[p + ".qkv2"], self.Bcat[p + ".qkv2"])
+        self._join(1)
+        with self._aside(lang, qkv2, lane=1):                 # language stream (attends to vision) beside the vision stream
+            ctx2, lse2 = k.attention_fwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
+            pa1 = k.linear(ctx2, W[p + ".biOutput.dense1.weight"], Pm[p + ".biOutput.dense1.bias"], residual=lang)
+            att1, sa1 = k.layernorm_fwd(pa1, Pm[p + ".biOutput.LayerNorm1.weight"], Pm[p + ".biOutput.LayerNorm1.bias"], 1e-12)
+            o1, f1 = self._ffn_fwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", att1, 1e-12, GELU)
         ctx1, lse1 = k.attention_fwd(qkv2[:, :D], qkv1[:, D:2 * D], qkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc)
-        ctx2, lse2 = k.attention_fwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
-        pa1 = k.linear(ctx2, W[p + ".biOutput.dense1.weight"], Pm[p + ".biOutput.dense1.bias"], residual=lang)
-        att1, sa1 = k.layernorm_fwd(pa1, Pm[p + ".biOutput.LayerNorm1.weight"], Pm[p + ".biOutput.LayerNorm1.bias"], 1e-12)
         pa2 = k.linear(ctx1, W[p + ".biOutput.dense2.weight"], Pm[p + ".biOutput.dense2.bias"], residual=vis)
         att2, sa2 = k.layernorm_fwd(pa2, Pm[p + ".biOutput.LayerNorm2.weight"], Pm[p + ".biOutput.LayerNorm2.bias"], 1e-12)
-        o1, f1 = self._ffn_fwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", att1, 1e-12, GELU)
         o2, f2 = self._ffn_fwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", att2, 1e-12, GELU)
+        self._join(1)
         return o1, o2, (lang, vis, qkv1, qkv2, ctx1, lse1, ctx2, lse2, pa1, sa1, pa2, sa2, f1, f2)
 
     def _coatt_bwd(self, p, do1, do2, sv, B, Tl, Q, need_dlang=True):
@@ -519,21 +575,27 @@ class Engine:
         dh = D // H
         sc = 1.0 / math.sqrt(dh)
         lang, vis, qkv1, qkv2, ctx1, lse1, ctx2, lse2, pa1, sa1, pa2, sa2, f1, f2 = sv
-        datt1 = self._ffn_bwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", do1, f1, GELU)
+        with self._aside(do1, lane=1):                        # language stream beside the vision stream
+            datt1 = self._ffn_bwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", do1, f1, GELU)
+            dpa1 = k.layernorm_bwd(datt1, pa1, sa1, Pm[p + ".biOutput.LayerNorm1.weight"], G[p + ".biOutput.LayerNorm1.weight"],
+                                   G[p + ".biOutput.LayerNorm1.bias"])
+            dctx2 = self._lin_bwd(p + ".biOutput.dense1", ctx2, dpa1)
         datt2 = self._ffn_bwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", do2, f2, GELU)
-        dpa1 = k.layernorm_bwd(datt1, pa1, sa1, Pm[p + ".biOutput.LayerNorm1.weight"], G[p + ".biOutput.LayerNorm1.weight"],
-                               G[p + ".biOutput.LayerNorm1.bias"])
         dpa2 = k.layernorm_bwd(datt2, pa2, sa2, Pm[p + ".biOutput.LayerNorm2.weight"], G[p + ".biOutput.LayerNorm2.weight"],
                                G[p + ".biOutput.LayerNorm2.bias"])
-        dctx2 = self._lin_bwd(p + ".biOutput.dense1", ctx2, dpa1)
         dctx1 = self._lin_bwd(p + ".biOutput.dense2", ctx1, dpa2)
         dqkv1, dqkv2 = torch.empty_like(qkv1), torch.empty_like(qkv2)
+        self._join(1)
+        with self._aside(dqkv1, dqkv2, lane=1):
+            k.attention_bwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], ctx2, dctx2, lse2, dqkv1[:, :D], dqkv2[:, D:2 * D],
+                            dqkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
         k.attention_bwd(qkv2[:, :D], qkv1[:, D:2 * D], qkv1[:, 2 * D:], ctx1, dctx1, lse1, dqkv2[:, :D], dqkv1[:, D:2 * D],
                         dqkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc)
-        k.attention_bwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], ctx2, dctx2, lse2, dqkv1[:, :D], dqkv2[:, D:2 * D],
-                        dqkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
-        dlang = self._lin_bwd(p + ".qkv1", lang, dqkv1, residual=dpa1, wkey=p + ".qkv1", need_dx=need_dlang)
+        self._join(1)
+        with self._aside(dqkv1, lane=1):
+            dlang = self._lin_bwd(p + ".qkv1", lang, dqkv1, residual=dpa1, wkey=p + ".qkv1", need_dx=need_dlang)
         dvis = self._lin_bwd(p + ".qkv2", vis, dqkv2, residual=dpa2, wkey=p + ".qkv2")
+        self._join(1)
         return dlang, dvis
 
     # ================================================================================================ trunk forward
@@ -545,6 +607,9 @@ class Engine:
         B = images.shape[0]
         d, D, Q = self.d, self.D, self.Q
         s = {"B": B}
+        with self._aside(qids, lane=2):                       # BERT (~100 small launches) runs beside the backbone
+            qe_b = self._bert_fwd(qids)
+            lang = k.linear(qe_b, W["bert_joiner.weight"], Pm["bert_joiner.bias"])
         c5, acts = self._backbone_fwd(images, save)
         _, Hf, Wf, C5 = c5.shape
         S = Hf * Wf
@@ -563,10 +628,14 @@ class Engine:
         qe = W["detr.query_embed.weight"]
         t = torch.zeros((B * Q, d), device=self.dev, dtype=BF16)
         dec = []
+        with self._aside(mem, mem_pos, lane=1):
+            kvs = [self._cross_kv(f"detr.transformer.decoder.layers.{i}", mem_pos, mem) for i in range(self.n_dec)]
         for i in range(self.n_dec):
             p = f"detr.transformer.decoder.layers.{i}"
             t, sa = self._self_attn_fwd(p, t, qe, Q, B, Q, self.h_detr)
-            t, sc = self._cross_attn_fwd(p, t, qe, mem_pos, mem, B, Q, S, self.h_detr)
+            if i == 0:
+                self._join(1)
+            t, sc = self._cross_attn_fwd(p, t, qe, mem_pos, mem, B, Q, S, self.h_detr, kv=kvs[i])
             t, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm3", t, 1e-5)
             dec.append((sa, sc, sf))
         # heads (detr_roi_head.py:81-92).  detr_hs = [LN(roi) | hs] is written in place, no cat.
@@ -587,10 +656,8 @@ class Engine:
         _, st_roi = k.layernorm_fwd(roi_raw, None, None, 1e-5, out=detr_hs[:, :C5])
         vis = k.linear(detr_hs, W["detr_joiner.weight"], Pm["detr_joiner.bias"])
         s["detr_hs_joined"] = vis
-        # language stream
-        qe_b = self._bert_fwd(qids)
         Tl = qids.shape[1]
-        lang = k.linear(qe_b, W["bert_joiner.weight"], Pm["bert_joiner.bias"])
+        self._join(2)
         co = []
         for i in range(self.n_co):
             lang, vis, sv = self._coatt_fwd(f"co_att_transformer.{i}", lang, vis, B, Tl, Q)
@@ -617,13 +684,17 @@ class Engine:
         emb = k.gather_rows(Pm["answer_input_embedings.embedding_layer.weight"], tok_ids)
         x = k.linear(emb, W["answer_input_embedings.transform.weight"], Pm["answer_input_embedings.transform.bias"])
         layers = []
+        with self._aside(memory, lane=1):
+            kvs = [self._cross_kv(f"text_decoder.layers.{i}", memory, memory) for i in range(self.n_txt)]
+            wc = k.linear(W["answer_head.vocab_embed"], W["answer_head.classifier_transform.weight"], Pm["answer_head.classifier_transform.bias"])
         for i in range(self.n_txt):
             p = f"text_decoder.layers.{i}"
             x, sa = self._self_attn_fwd(p, x, None, 0, B, Sx, self.h_txt, causal=True)
-            x, sc = self._cross_attn_fwd(p, x, None, memory, memory, B, Sx, Tm, self.h_txt)
+            if i == 0:
+                self._join(1)
+            x, sc = self._cross_attn_fwd(p, x, None, memory, memory, B, Sx, Tm, self.h_txt, kv=kvs[i])
             x, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm3", x, 1e-5)
             layers.append((sa, sc, sf))
-        wc = k.linear(W["answer_head.vocab_embed"], W["answer_head.classifier_transform.weight"], Pm["answer_head.classifier_transform.bias"])
         logits = torch.empty((B * Sx, self.Vp), device=self.dev, dtype=F32)
         k.gemm(x, wc, logits, M=B * Sx, N=self.V, K=self.D, lda=x.stride(0), ldb=wc.stride(0), ldd=self.Vp)
         return logits, (emb, layers, x, wc)
@@ -676,9 +747,10 @@ class Engine:
         # ---- answer head + text decoder
         emb, layers, xf, wc = s["sv_txt"]
         dlv = s["dlogits_v"]
-        dwc = torch.empty((self.V, D), device=self.dev, dtype=BF16)
-        k.gemm(dlv, xf, dwc, M=self.V, N=D, K=B * Sx, lda=dlv.stride(0), ldb=xf.stride(0), ldd=D, a_mn=True, b_mn=True)
-        self._lin_bwd("answer_head.classifier_transform", W["answer_head.vocab_embed"], dwc, need_dx=False)
+        with self._aside(dlv, xf):                            # classifier-transform branch: beside the text decoder's backward
+            dwc = torch.empty((self.V, D), device=self.dev, dtype=BF16)
+            k.gemm(dlv, xf, dwc, M=self.V, N=D, K=B * Sx, lda=dlv.stride(0), ldb=xf.stride(0), ldd=D, a_mn=True, b_mn=True)
+            self._lin_bwd("answer_head.classifier_transform", W["answer_head.vocab_embed"], dwc, need_dx=False)
         dx = k.gemm(dlv, wc, torch.empty((B * Sx, D), device=self.dev, dtype=BF16), M=B * Sx, N=D, K=self.V, lda=dlv.stride(0),
                     ldb=wc.stride(0), ldd=D, b_mn=True)
         dmemory = None
@@ -688,6 +760,7 @@ class Engine:
             dx = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm3", dx, sf)
             dx, dmemory = self._cross_attn_bwd(p, dx, sc, s["memory"], s["memory"], dmemory, None, B, Sx, Tm, self.h_txt)
             dx = self._self_attn_bwd(p, dx, sa, None, B, Sx, self.h_txt, causal=True, has_pos=False)
+            self._join()
         self._lin_bwd("answer_input_embedings.transform", emb, dx, need_dx=False)
         self._done(0)
         # ---- memory split, relevance conditioning
@@ -703,6 +776,7 @@ class Engine:
         # ---- co-attention
         for i in range(self.n_co - 1, -1, -1):
             dlang, dvis = self._coatt_bwd(f"co_att_transformer.{i}", dlang, dvis, s["co"][i], B, Tl, Q)
+            self._join()
         self._lin_bwd("bert_joiner", s["qe_b"], dlang, need_dx=False)
         self._done(1)
         # ---- detr_joiner, ROI head, box / class heads
@@ -729,6 +803,7 @@ class Engine:
             dt = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm3", dt, sf)
             dt, dmem = self._cross_attn_bwd(p, dt, sc, s["mem_pos"], s["mem"], dmem, gq, B, Q, S, self.h_detr)
             dt = self._self_attn_bwd(p, dt, sa, gq, B, Q, self.h_detr)
+            self._join()
         self._done(2)
         dx = dmem
         for i in range(self.n_enc - 1, -1, -1):
@@ -736,6 +811,7 @@ class Engine:
             sa, sf = s["enc"][i]
             dx = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm2", dx, sf)
             dx = self._self_attn_bwd(p, dx, sa, None, B, S, self.h_detr)
+            self._join()
         # ---- input_proj: dC5 = (dx Wip + dC5_roi) * relu'(c5)  -> masked gradient of the last bottleneck
         c5f = s["c5"].view(B * S, C5)
         dpre = self._lin_bwd("detr.input_proj", c5f, dx, residual=dc5, aux=c5f, aux_mode=MASK_RELU)

@@ -24,9 +24,11 @@ SHAPES = [  # (tag, M, N, K, residual, act)
 ]
 
 
-def main(reps=3):
+def main(reps=3, only=None):
     torch.manual_seed(0)
     for tag, M, N, K, res, act in SHAPES:
+        if only and tag not in only:
+            continue
         x = torch.randn(M, K, device=dev).to(BF)
         w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF)
         b = torch.randn(N, device=dev)
@@ -62,4 +64,9 @@ def main(reps=3):
 
 
 if __name__ == "__main__":
-    main()
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--only", nargs="*", default=None)
+    a = ap.parse_args()
+    main(a.reps, a.only)

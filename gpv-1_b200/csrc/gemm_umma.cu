@@ -12,6 +12,7 @@
 // (backbone.py:72, detr_roi_head.py:79-84, transformer.py:153-160,218-231, vilbert.py:748-761,847-898,
 //  gpv.py:140,145,162, answer_head.py:31-33) and their autograd backward.
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 #include <string>
@@ -30,8 +31,9 @@ struct KParams {
   int ntaps;
   int tap_dh[9], tap_dw[9], tap_w[9];
   int OH, OW, os, ooh, oow;
-  int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal;
-  uint32_t epi_warp_bytes, epi_aux_off, epi_slot_stride;   // per-warp epilogue slabs (coalesced path), see epi_layout()
+  int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal, pf_mode;
+  uint32_t epi_warp_bytes, epi_aux_off, epi_slot_stride;   // per-warp epilogue slabs (coalesced path)
+  int epi_full;   // 1: every slab of a work item is requested up front (one slot per chunk); 0: two-slot ring, one slab ahead
   float alpha;
   void* D;
   bf16* D2;
@@ -92,8 +94,23 @@ GPV_DEVINL void cp_async16(uint32_t saddr, const void* g) {
 GPV_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 GPV_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+GPV_DEVINL void cp_async_wait_n(int n) {   // n is a compile-time value after unrolling
+  if (n <= 0) cp_async_wait<0>();
+  else if (n == 1) cp_async_wait<1>();
+  else if (n == 2) cp_async_wait<2>();
+  else cp_async_wait<3>();
+}
 GPV_DEVINL void prefetch_l2_bulk(const void* g, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
+GPV_DEVINL void prefetch_l2_line(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g) : "memory"); }
+// One row slice of `bytes` bytes into L2: mode 1 = one bulk (TMA-engine) request, mode 2 = one LSU prefetch per 128-byte line.
+GPV_DEVINL void prefetch_l2_row(const bf16* g, uint32_t bytes, int mode) {
+  if (mode == 1) {
+    prefetch_l2_bulk(g, bytes);
+  } else {
+    for (uint32_t b = 0; b < bytes; b += 128) prefetch_l2_line(reinterpret_cast<const uint8_t*>(g) + b);
+  }
 }
 
 GPV_DEVINL void unpack8(const uint4& q, float* v, bool add) {
@@ -299,7 +316,7 @@ GPV_DEVINL void store_slab(bf16* const (&dst)[4], uint32_t ok, int col, const fl
 // Same arithmetic as epi_chunk for one full 32-column slab of a warp; residual / aux slices wait in the slabs res_s /
 // aux_s (cp.async), outputs leave through out_s (the slab of an input already consumed, or a slab of its own).
 template <int F>
-GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], float rs, const float* bias, int col,
+GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], float rs, const float4 (&b4)[kChunk / 4], int col,
                                uint32_t res_s, uint32_t aux_s, uint32_t out_s, const CoalRows& cr, const SlabOffs& so) {
   typedef EpiFlags<F> E;
   float v[kChunk];
@@ -313,8 +330,7 @@ GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], 
   if (E::bias(p)) {
 #pragma unroll
     for (int j = 0; j < kChunk; j += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + j));
-      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      v[j] += b4[j / 4].x; v[j + 1] += b4[j / 4].y; v[j + 2] += b4[j / 4].z; v[j + 3] += b4[j / 4].w;
     }
   }
   if (E::res(p)) {
@@ -385,7 +401,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================================================== TMA producer
     // Lane 0 issues the TMA loads; before that, all 32 lanes L2-prefetch the residual / aux rows the epilogue of this
     // work item will read (the producer runs 2+ tiles ahead of the epilogue, so they are L2 hits by then).
-    const bool pf_r = p.coal && p.residual != nullptr, pf_a = p.coal && p.aux_mode != GPVB200_AUX_NONE;
+    const bool pf_r = p.pf_mode && p.coal && p.residual != nullptr, pf_a = p.pf_mode && p.coal && p.aux_mode != GPVB200_AUX_NONE;
     int gi = 0;  // stage-use counter, runs across work items
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const Work wk = decode_work(p, w);
@@ -398,8 +414,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int r = lane; r < BM; r += 32) {
             long long pix;
             if (tile_row(p, wk, r, &pix)) {
-              if (pf_r) prefetch_l2_bulk(p.residual + row_off + pix * p.ldr, bytes);
-              if (pf_a) prefetch_l2_bulk(p.aux + row_off + pix * p.ldaux, bytes);
+              if (pf_r) prefetch_l2_row(p.residual + row_off + pix * p.ldr, bytes, p.pf_mode);
+              if (pf_a) prefetch_l2_row(p.aux + row_off + pix * p.ldaux, bytes, p.pf_mode);
             }
           }
         }
@@ -508,6 +524,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool coal = F >= 0 || p.coal != 0;
     const uint32_t res_ring = stg_base + (uint32_t)(warp - 2) * p.epi_warp_bytes, aux_ring = res_ring + p.epi_aux_off;
     const uint32_t slot_stride = p.epi_slot_stride;
+    const bool full_pf = p.epi_full != 0;
     const bool pre_r = E::res(p) && !E::res_fp32(p), pre_a = E::aux(p) != GPVB200_AUX_NONE;
     const uint32_t out_ring = (pre_r || !pre_a) ? res_ring : aux_ring;
     SlabOffs so;
@@ -542,10 +559,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const float* bias_t = p.bias + n0 + cbase;
 
-      // cp.async the residual / aux slices of chunk c into ring slot c & 1 (coalesced arrangement); one commit per call
+      // cp.async the residual / aux slices of chunk c into its slot (coalesced arrangement); one commit per call
       auto issue = [&](int c) {
         if (n0 + cbase + (c + 1) * kChunk <= p.N) {
-          const uint32_t so_c = (uint32_t)(c & 1) * slot_stride + so.co;
+          const uint32_t so_c = (uint32_t)(full_pf ? c : (c & 1)) * slot_stride + so.co;
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             if ((cr.ok >> jj) & 1u) {
@@ -556,7 +573,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         cp_async_commit();
       };
-      if (coal) issue(0);  // independent of the accumulator: overlaps the wait below
+      if (coal) {  // independent of the accumulator: overlaps the wait below
+        issue(0);
+        if (full_pf) {
+#pragma unroll
+          for (int c = 1; c < kChunksPerHalf; ++c) issue(c);
+        }
+      }
       mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
@@ -565,18 +588,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (nb < p.N) {  // warp-uniform
           uint32_t acc[kChunk];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + c * kChunk), acc);
+          float4 b4[kChunk / 4];
+          if (coal && E::bias(p) && nb + kChunk <= p.N) {   // bias slice of this slab: in flight across the waits below
+#pragma unroll
+            for (int i = 0; i < kChunk / 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias_t + c * kChunk) + i);
+          }
           if (coal) {
-            if (c + 1 < kChunksPerHalf) issue(c + 1);
-            else cp_async_commit();
-            cp_async_wait<1>();   // everything but the slab just requested has landed (this thread's copies) ...
-            __syncwarp();         // ... and every other lane's
+            if (full_pf) {
+              cp_async_wait_n(kChunksPerHalf - 1 - c);   // slabs 0..c have landed (this thread's copies) ...
+            } else {
+              if (c + 1 < kChunksPerHalf) issue(c + 1);
+              else cp_async_commit();
+              cp_async_wait<1>();   // everything but the slab just requested has landed
+            }
+            __syncwarp();           // ... and every other lane's
           }
           tmem_ld_wait();
           const int nvalid = min(kChunk, p.N - nb);
           const bool full = nvalid == kChunk;
           if (coal && full) {                     // whole warp takes part (shared-memory slabs)
-            const uint32_t sc = (uint32_t)(c & 1) * slot_stride;
-            epi_chunk_coal<F>(p, acc, rs, bias_t, c * kChunk, res_ring + sc, aux_ring + sc, out_ring + sc, cr, so);
+            const uint32_t sc = (uint32_t)(full_pf ? c : (c & 1)) * slot_stride;
+            epi_chunk_coal<F>(p, acc, rs, b4, c * kChunk, res_ring + sc, aux_ring + sc, out_ring + sc, cr, so);
           } else if (row_ok) {
             epi_chunk<F>(p, acc, rs, row_off, pix, nb, nvalid, p.vec_ok && full);
           }
@@ -806,15 +838,15 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
                 al16(d->D) && al16(d->D2) && al16(d->residual) && al16(d->aux) && al16(d->bias);
   }
   // coalesced epilogue: bf16 outputs (and bf16 residual / aux) move as 8 rows x 64 bytes per warp instruction
-  kp.coal = kp.vec_ok && !kp.d_fp32 && !kp.res_fp32 && !(d->D2 && d->aux_mode != GPVB200_AUX_NONE);
   {
-    // per-warp slabs: a 2-slot cp.async ring (2 x 2 KB) per streamed input (residual, aux); the output is transposed
-    // through the slot of an input that has been consumed, or through a 2 KB slab of its own when there is none
-    const int rings = (kp.coal && d->residual ? 1 : 0) + (kp.coal && d->aux_mode != GPVB200_AUX_NONE ? 1 : 0);
-    kp.epi_warp_bytes = rings ? 4096u * rings : 2048u;
-    kp.epi_aux_off = (d->residual && rings == 2) ? 4096u : 0u;
-    kp.epi_slot_stride = rings ? 2048u : 0u;
+    static int pf = -1;
+    if (pf < 0) {
+      const char* e = getenv("GPVB200_PF");
+      pf = e ? atoi(e) : 0;
+    }
+    kp.pf_mode = pf;
   }
+  kp.coal = kp.vec_ok && !kp.d_fp32 && !kp.res_fp32 && !(d->D2 && d->aux_mode != GPVB200_AUX_NONE);
   kp.stride = d->stride > 0 ? d->stride : 1;
   kp.os = d->out_stride > 0 ? d->out_stride : 1;
   kp.ooh = d->out_off_h;
@@ -870,6 +902,9 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       }
     }
   }
+
+  if (BN == 256 && d->residual && d->aux_mode != GPVB200_AUX_NONE && k_iters_pre > 0 && k_iters_pre <= 4 && splits == 1)
+    BN = 128;   // both epilogue input streams on a shallow-K item: full slab prefetch fits only with two chunks per warp
 
   CUtensorMap ma, mb;
   const uint32_t one4[4] = {1, 1, 1, 1};
@@ -997,6 +1032,22 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
     const long long tw_ = (long long)kp.m_tiles * kp.n_tiles * kp.gy * kp.splits;
     GPV_REQUIRE(tw_ > 0 && tw_ < (1ll << 31), "gemm: work list size %lld out of range", tw_);
     kp.total_work = (int)tw_;
+  }
+
+  // ---- epilogue slabs (coalesced path) -----------------------------------------------------------------
+  // One 2 KB slot per warp, streamed input (residual, aux) and slab in flight.  Shallow-K work items (the 1x1
+  // convolutions with K = 64..256) are epilogue-bound and need every slab of the item requested up front to cover the
+  // HBM latency (one slot per chunk); deep-K items hide it under the main loop and keep a two-slot ring, which leaves
+  // room for a fourth pipeline stage.  The output is transposed through the slot of an input already consumed, or
+  // through a slot of its own when there is none.
+  {
+    const int rings = (kp.coal && d->residual ? 1 : 0) + (kp.coal && d->aux_mode != GPVB200_AUX_NONE ? 1 : 0);
+    const int chunks = BN / 2 / kChunk;
+    kp.epi_full = rings > 0 && kp.k_per_split <= 4 && rings * chunks <= 4;
+    const int depth = kp.epi_full ? chunks : 2;
+    kp.epi_warp_bytes = rings ? 2048u * depth * rings : 2048u;
+    kp.epi_aux_off = (d->residual && rings == 2) ? 2048u * depth : 0u;
+    kp.epi_slot_stride = rings ? 2048u : 0u;
   }
 
   // ---- pipeline depth ---------------------------------------------------------------------------------

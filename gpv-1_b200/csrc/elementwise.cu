@@ -241,6 +241,51 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, bf16* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem space-to-depth: NCHW fp32 image -> zero-bordered bf16 [B][Ho+4][Wo+4][16] with
+//   out[b][I][J][dy*6 + dx*3 + c] = img[b][c][2(I-2)+dy][2(J-2)+dx]   (channels 12..15 and out-of-image taps = 0).
+// The 7x7 stride-2 pad-3 stem convolution (backbone.py:72, torchvision resnet conv1) is then a 4x4 stride-1
+// convolution over this map: input row 2ho-3+r = 2(ho-2+a)+dy with r = 2a+dy-1.  Four horizontally adjacent pixels
+// are 64 contiguous bf16, so the implicit-GEMM kernel reads it as an NHWC map with 64 "channels" whose pixel stride
+// is 16 elements (overlapping TMA rows) and 4 vertical taps: no im2col buffer (which was 747 MB at batch 32).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W,
+                                                       int Hp, int Wp) {
+  const long long total = (long long)B * Hp * Wp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int J = (int)(idx % Wp);
+    const long long t = idx / Wp;
+    const int I = (int)(t % Hp), b = (int)(t / Hp);
+    const int h0 = 2 * (I - 2), w0 = 2 * (J - 2);
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int h = h0 + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* row = img + (((long long)b * 3 + c) * H + h) * W;
+        if (w0 >= 0 && w0 + 1 < W && (W & 1) == 0) {
+          const float2 x2 = __ldg(reinterpret_cast<const float2*>(row + w0));
+          v[dy * 6 + c] = x2.x;
+          v[dy * 6 + 3 + c] = x2.y;
+        } else {
+          if (w0 >= 0 && w0 < W) v[dy * 6 + c] = __ldg(row + w0);
+          if (w0 + 1 >= 0 && w0 + 1 < W) v[dy * 6 + 3 + c] = __ldg(row + w0 + 1);
+        }
+      }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);   o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ROI-align-mean weights (detr_roi_head.py:44-56 + torchvision roi_align, output 7x7, aligned=True,
 // sampling_ratio=-1, then mean over the 49 bins).  The mean is linear in the feature map with rank-1 separable
 // weights w_y (x) w_x per box; this kernel writes Wroi[b][q][y*W + x] (bf16, row stride ldw, zero padded) so that
@@ -506,6 +551,16 @@ extern "C" int gpvb200_stem_im2col(const float* img, void* col, int32_t B, int32
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   stem_im2col_kernel<<<grid_for((long long)B * Ho * Wo * 19, 256), 256, 0, ST>>>(img, (bf16*)col, B, H, W, Ho, Wo);
   return check_launch("stem_im2col_kernel");
+}
+
+extern "C" int gpvb200_stem_s2d(const float* img, void* out, int32_t B, int32_t H, int32_t W, void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "stem_s2d: bad arguments");
+  GPV_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)img & 7) == 0, "stem_s2d: unaligned buffers");
+  const int Hp = (H - 1) / 2 + 1 + 4, Wp = (W - 1) / 2 + 1 + 4;
+  stem_s2d_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, ST>>>(img, (bf16*)out, B, H, W, Hp, Wp);
+  return check_launch("stem_s2d_kernel");
 }
 
 extern "C" int gpvb200_roi_weights(const float* boxes, int64_t ldb, void* wroi, int64_t ldw, int32_t BQ, int32_t H, int32_t W,

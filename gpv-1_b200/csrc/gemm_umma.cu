@@ -879,10 +879,16 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   const int bn_cap = d->mode == 2 ? 128 : 256;
   const int k_iters_pre = d->mode == 0 ? (d->K + 63) / 64 : (d->mode == 1 ? d->ntaps * ((d->K + 63) / 64) : 0);
   int BN = 64, splits = splits_in > 0 ? splits_in : 1;
+  static int force_bn = -1;   // developer override (tools/sweep_bn.py): GPVB200_FORCE_BN=64|128|256
+  if (force_bn < 0) {
+    const char* e = getenv("GPVB200_FORCE_BN");
+    force_bn = e ? atoi(e) : 0;
+  }
   {
     double best = 1e30;
     for (int bn = 64; bn <= bn_cap; bn *= 2) {
       if (bn > 64 && d->N <= bn / 2) break;
+      if (force_bn && bn != force_bn && !(force_bn > bn_cap && bn == bn_cap)) continue;
       const long long tiles = (long long)m_tiles_pre * ((d->N + bn - 1) / bn) * gy_pre;
       int sp = splits_in > 0 ? splits_in : 1;
       if (auto_split && k_iters_pre > 0) {

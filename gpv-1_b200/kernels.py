@@ -284,6 +284,42 @@ def stem_im2col(img, out=None):
     return col, Ho, Wo
 
 
+def stem_s2d(img):
+    """img NCHW fp32 -> (virtual NHWC view [B, Ho+4, Wo+4, 64] bf16 with pixel stride 16, Ho, Wo): the space-to-depth
+    map of the 7x7/s2 stem; pixel (I, J) of the view = the 4 adjacent s2d pixels J..J+3 of row I (see elementwise.cu)."""
+    B, C, H, W = img.shape
+    assert C == 3
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    Hp, Wp = Ho + 4, Wo + 4
+    buf = torch.empty(B * Hp * Wp * 16 + 64, device=img.device, dtype=BF16)   # + 64: view pixels J > Wo (never stored) read up to 48 past the map
+    _C.check(_C.lib().gpvb200_stem_s2d(_C.ptr(_req(img.contiguous(), torch.float32)), _C.ptr(buf), B, H, W, _C.stream_ptr()),
+             "stem_s2d")
+    view = torch.as_strided(buf, (B, Hp, Wp, 64), (Hp * Wp * 16, Wp * 16, 16, 1))
+    return view, Ho, Wo
+
+
+STEM_TAPS = [(0, 0), (1, 0), (2, 0), (3, 0)]
+
+
+def stem_weight_s2d(w_fold):
+    """[64,3,7,7] (BN-folded, any float dtype) -> [4 taps a][64][64 = b*16 + dy*6 + dx*3 + c] bf16 for the s2d stem:
+    r = 2a + dy - 1, s = 2b + dx - 1, zero where r or s falls outside 0..6 and in channels 12..15."""
+    O = w_fold.shape[0]
+    out = torch.zeros((4, O, 4, 16), device=w_fold.device, dtype=torch.float32)
+    for a in range(4):
+        for dy in range(2):
+            r = 2 * a + dy - 1
+            if not 0 <= r <= 6:
+                continue
+            for b in range(4):
+                for dx in range(2):
+                    s = 2 * b + dx - 1
+                    if not 0 <= s <= 6:
+                        continue
+                    out[a, :, b, dy * 6 + dx * 3:dy * 6 + dx * 3 + 3] = w_fold[:, :, r, s].float()
+    return out.reshape(4, O, 64).to(BF16).contiguous()
+
+
 def roi_weights(boxes, H, W, ldw):
     """boxes [BQ, >=4] fp32 (cx,cy,w,h normalised) -> [BQ, ldw] bf16 separable ROI-mean weights."""
     BQ = boxes.shape[0]

@@ -190,6 +190,7 @@ class Engine:
             k.bn_fold(P[b + ".weight"], P[b + ".bias"], P[b + ".running_mean"], P[b + ".running_var"], self.bn_scale[b],
                       self.bn_bias[b])
         self._plan.run()
+        self.W["stem.s2d"] = k.stem_weight_s2d(P[f"{BB}.conv1.weight"] * self.bn_scale[f"{BB}.bn1"].view(-1, 1, 1, 1))
         for key, srcs in self.Bcat_src.items():
             torch.cat(srcs, out=self.Bcat[key])
         self._versions = sum(t._version for t in self.P.values())
@@ -303,9 +304,9 @@ class Engine:
     def _backbone_fwd(self, images, save):
         W, bb = self.W, self.bn_bias
         B = images.shape[0]
-        col, Ho, Wo = k.stem_im2col(images)
-        x = k.linear(col, W[f"{BB}.conv1.weight"], bb[f"{BB}.bn1"], act=RELU).view(B, Ho, Wo, 64)
-        del col
+        xv, Ho, Wo = k.stem_s2d(images)                       # 7x7/s2 stem as a 4-tap K=64 implicit GEMM over the s2d map
+        x = k.conv(xv, W["stem.s2d"], ksize=7, taps=k.STEM_TAPS, Ho=Ho, Wo=Wo, N=64, K=64, bias=bb[f"{BB}.bn1"], act=RELU)
+        del xv
         x = k.maxpool3x3s2(x)
         acts = []
         for blk in self.blocks:

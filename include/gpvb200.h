@@ -154,6 +154,9 @@ int gpvb200_bn_fold(const float* w, const float* b, const float* rm, const float
 /* torchvision resnet stem pieces (backbone.py:72): 3x3/s2 max-pool on NHWC bf16; 7x7/s2 im2col from NCHW fp32 */
 int gpvb200_maxpool3x3s2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 int gpvb200_stem_im2col(const float* img, void* col, int32_t B, int32_t H, int32_t W, void* stream);
+/* stem space-to-depth: NCHW fp32 -> zero-bordered bf16 [B][Ho+4][Wo+4][16] (Ho = ceil(H/2)), channel = dy*6 + dx*3 + c;
+ * with it the 7x7/s2 stem (backbone.py:72) is a 4-tap K=64 implicit GEMM of gpvb200_gemm mode 1 (pixel stride 16) */
+int gpvb200_stem_s2d(const float* img, void* out, int32_t B, int32_t H, int32_t W, void* stream);
 /* ROI-align(7x7, aligned, adaptive sampling)+mean as separable weights (detr_roi_head.py:44-56): wroi[bq][y*W+x] */
 int gpvb200_roi_weights(const float* boxes, int64_t ldb, void* wroi, int64_t ldw, int32_t BQ, int32_t H, int32_t W, void* stream);
 /* relevance conditioning gpv.py:364-375 (+ the memory concat gpv.py:175 through the output row remap) */

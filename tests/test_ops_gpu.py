@@ -269,3 +269,22 @@ def test_set_criterion(cuda):
     _close(out3, ref3, tol=1e-4, name="set losses")
     _close(dl[:, :2], lf.grad.view(B * Q, 2), tol=1e-3, name="set dlogits")
     _close(dbp[:, :4], pf.grad.view(B * Q, 4), tol=1e-2, name="set dbox")
+
+
+@pytest.mark.parametrize("H,W", [(37, 50), (64, 96), (33, 47)])
+def test_stem_s2d_conv_matches_conv2d(cuda, H, W):
+    """7x7/s2/p3 stem (backbone.py:72 -> torchvision conv1) as space-to-depth + 4-tap K=64 implicit GEMM over
+    overlapping TMA rows, against F.conv2d on the same bf16-rounded operands (even, odd and ragged sizes)."""
+    import torch.nn.functional as F
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(3)
+    im = torch.randn(2, 3, H, W, device=cuda)
+    w = torch.randn(64, 3, 7, 7, device=cuda) * 0.1
+    b = torch.randn(64, device=cuda)
+    xv, Ho, Wo = k.stem_s2d(im)
+    ws = k.stem_weight_s2d(w)
+    y = k.conv(xv, ws, ksize=7, taps=k.STEM_TAPS, Ho=Ho, Wo=Wo, N=64, K=64, bias=b, act=k.ACT_RELU)
+    ref = F.relu(F.conv2d(im.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), b, stride=2, padding=3)).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, err

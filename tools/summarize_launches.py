@@ -1,5 +1,5 @@
 """Developer tool: aggregate an ncu `--metrics gpu__time_duration.sum --csv` launch list over the LAST training step
-(from the last stem_im2col launch onward) into a per-kernel table (markdown)."""
+(one stem-to-stem period at the end of the list) into a per-kernel table (markdown)."""
 import collections
 import csv
 import re
@@ -10,11 +10,12 @@ def main(path):
     with open(path) as f:
         rows = list(csv.DictReader([l for l in f if l.startswith('"')]))
     idx = [i for i, x in enumerate(rows) if "stem_im2col" in x["Kernel Name"]]
-    step = rows[idx[-1]:] if idx else rows
+    # one step = the launches between two consecutive stem kernels (BERT is enqueued ahead of the stem on its own lane)
+    step = rows[-(idx[-1] - idx[-2]):] if len(idx) >= 2 else rows
     tot = sum(float(x["Metric Value"]) for x in step) / 1e3
     agg = collections.OrderedDict()
     for x in step:
-        n = re.sub(r"\(.*", "", x["Kernel Name"])[:70]
+        n = re.sub(r"\(.*", "", x["Kernel Name"].replace("(int)", ""))[:70]
         a = agg.setdefault(n, [0, 0.0])
         a[0] += 1
         a[1] += float(x["Metric Value"]) / 1e3

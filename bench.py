@@ -305,6 +305,21 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     loss_val = step_e2e()
 
+    # second number: the full training step = forward + backward (+ all-reduce) + clip_grad_norm_ + AdamW +
+    # re-derivation of the packed bf16 weights, with the reference's hyper-parameters (train_distr.py:228-253, 414-428)
+    from gpv1_b200.optim import ClipAdamW
+    opt = ClipAdamW.for_model(model, cfg.training if hasattr(cfg, "training") else None)
+
+    def step_full():
+        loss = model(d_images, d_qids, d_ans, d_targets)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step_full()
+    ms_full = timed(step_full, args.steps)
+
     breakdown = None
     if rank == 0 and args.breakdown:
         lib.trace = []
@@ -361,6 +376,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
+            "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
+                          "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "what": f"whole step: {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd ({gf_fwd:.1f} fwd) x {B} samples / step time; peak = "
                                  + ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)")},

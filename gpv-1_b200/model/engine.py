@@ -179,21 +179,32 @@ class Engine:
         self.W = W
         self._plan = k.PackPlan(items, dev)
 
+    def mark_dirty(self):
+        """The trainable parameters were updated behind torch's version counters (optim.ClipAdamW writes them through raw
+        pointers): re-derive the packed bf16 copies at the next forward."""
+        self._versions = None
+
     @torch.no_grad()
     def refresh(self, force=False):
-        """Re-derive the packed bf16 weights when any parameter changed (optimizer step, load_state_dict)."""
-        ver = sum(t._version for t in self.P.values())
+        """Re-derive the packed bf16 weights when any parameter changed (optimizer step, load_state_dict).  The frozen
+        pieces (FrozenBatchNorm buffers -> folded scale / bias, the stem convolution) are tracked separately so that an
+        optimizer step costs one multi-tensor pack launch, not 53 BN folds."""
+        P = self.P
+        ver = sum(t._version for t in P.values())
         if not force and ver == self._versions:
             return
-        P = self.P
-        for b in self.bns:
-            k.bn_fold(P[b + ".weight"], P[b + ".bias"], P[b + ".running_mean"], P[b + ".running_var"], self.bn_scale[b],
-                      self.bn_bias[b])
+        frozen = [P[b + sfx] for b in self.bns for sfx in (".weight", ".bias", ".running_mean", ".running_var")] + [P[f"{BB}.conv1.weight"]]
+        fver = sum(t._version for t in frozen)
+        if force or fver != getattr(self, "_frozen_versions", None):
+            for b in self.bns:
+                k.bn_fold(P[b + ".weight"], P[b + ".bias"], P[b + ".running_mean"], P[b + ".running_var"], self.bn_scale[b],
+                          self.bn_bias[b])
+            self.W["stem.s2d"] = k.stem_weight_s2d(P[f"{BB}.conv1.weight"] * self.bn_scale[f"{BB}.bn1"].view(-1, 1, 1, 1))
+            self._frozen_versions = fver
         self._plan.run()
-        self.W["stem.s2d"] = k.stem_weight_s2d(P[f"{BB}.conv1.weight"] * self.bn_scale[f"{BB}.bn1"].view(-1, 1, 1, 1))
         for key, srcs in self.Bcat_src.items():
             torch.cat(srcs, out=self.Bcat[key])
-        self._versions = sum(t._version for t in self.P.values())
+        self._versions = sum(t._version for t in P.values())
 
     # ================================================================================================ gradients
     def _setup_grads(self, specs):

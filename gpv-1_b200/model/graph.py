@@ -10,6 +10,7 @@ The reference has no equivalent (its matcher forces a device->host sync in the m
 import torch
 
 from .gpv import HostTargets
+from .spec import N_STAGES
 
 
 class CapturedStep:
@@ -56,17 +57,23 @@ class CapturedStep:
                 g.capture_begin(pool=self.pool)
                 self.g_bwd.append(g)
 
+                open_capture = [True]
+
                 def split(stage):
                     if self.sync is None:
                         return
                     self.g_bwd[-1].capture_end()
+                    if stage == N_STAGES - 1:             # nothing is launched after the last stage: no empty trailing graph
+                        open_capture[0] = False
+                        return
                     g2 = torch.cuda.CUDAGraph()
                     g2.capture_begin(pool=self.pool)
                     self.g_bwd.append(g2)
 
                 eng.on_stage_done, eng.on_backward_end = split, None
                 eng.backward()
-                self.g_bwd[-1].capture_end()
+                if open_capture[0]:
+                    self.g_bwd[-1].capture_end()
         finally:
             eng.on_stage_done, eng.on_backward_end = hooks
         torch.cuda.current_stream().wait_stream(cap_stream)
@@ -99,9 +106,8 @@ class CapturedStep:
         if self.sync is None:
             self.g_bwd[0].replay()
             return
-        # graph i ends where gradient stage i is complete (the last graph is empty: layer2 finishes the backward)
+        # graph i ends where gradient stage i is complete
         for i, g in enumerate(self.g_bwd):
             g.replay()
-            if i < len(self.g_bwd) - 1:
-                self.sync.stage_done(i)
+            self.sync.stage_done(i)
         self.sync.finish()

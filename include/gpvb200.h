@@ -192,6 +192,20 @@ int gpvb200_set_criterion(const float* logits, int64_t ldl, const float* boxes, 
                           float wt_ce, float wt_bbox, float wt_giou, float* out3, float* dlogits, void* dbox_pre, int64_t lddb,
                           void* stream);
 
+/* ---- optimizer: clip_grad_norm_ + AdamW over the flat gradient arena (exp/gpv/train_distr.py:414-428, 228-253).
+ * items: device array of {float* p; int64 goff; int32 n, group, clip, pad} (gpvb200_optim_item_size() bytes each);
+ * blk_item / blk_chunk: one entry per CTA = (tensor index, chunk of gpvb200_optim_chunk() elements).
+ * grad_sqnorm: out_sq[0] = sum of squares over the listed chunks.  clip_adamw: gradients of items with clip = 1 are
+ * scaled by min(1, max_norm / (sqrt(total_sq[0]) + 1e-6)) in place, then p, m, v follow torch.optim.AdamW at step `step`
+ * (>= 1) with the learning rate of the item's group. */
+size_t gpvb200_optim_item_size(void);
+int gpvb200_optim_chunk(void);
+int gpvb200_grad_sqnorm(const void* items, const int32_t* blk_item, const int32_t* blk_chunk, int32_t n_blocks, const float* grads,
+                        float* out_sq, void* stream);
+int gpvb200_clip_adamw(const void* items, const int32_t* blk_item, const int32_t* blk_chunk, int32_t n_blocks, float* grads, float* m,
+                       float* v, const float* total_sq, float max_norm, float lr0, float lr1, float lr2, float lr3, float beta1,
+                       float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,3 +288,44 @@ def test_stem_s2d_conv_matches_conv2d(cuda, H, W):
     assert y.shape == ref.shape
     err = (y.float() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item() + 1e-3, err
+
+
+def test_clip_adamw_matches_torch(cuda):
+    """optim.ClipAdamW (two launches over a flat gradient arena) against torch.nn.utils.clip_grad_norm_ +
+    torch.optim.AdamW with the reference's groups (exp/gpv/train_distr.py:228-253, 414-428) over three steps."""
+    from gpv1_b200.optim import ClipAdamW
+    torch.manual_seed(5)
+    shapes = {"detr.backbone.0.body.layer2.0.conv1.weight": (128, 256, 1, 1), "detr.transformer.encoder.layers.0.linear1.bias": (2048,),
+              "detr_joiner.weight": (768, 2304), "bert_joiner.bias": (768,), "relevance_tokens": (2, 768), "odd.tensor": (5, 7, 3)}
+    total = sum((math.prod(s) + 7) // 8 * 8 for s in shapes.values())
+    arena = torch.zeros(total + 3, device=cuda)
+    named, ref_params, off = [], {}, 0
+    for n, s in shapes.items():
+        num = math.prod(s)
+        p = torch.randn(s, device=cuda)
+        g = arena[off:off + num].view(s)
+        off += (num + 7) // 8 * 8
+        if n == "odd.tensor":
+            off += 3                                            # an unaligned gradient offset: scalar path
+        named.append((n, p, g))
+        ref_params[n] = torch.nn.Parameter(p.clone())
+    named[-1] = ("odd.tensor", named[-1][1], arena[total - 105 + 3 - 8:total - 8 + 3].view(5, 7, 3)) if False else named[-1]
+    opt = ClipAdamW(named, arena, lr=1e-3, lr_backbone=1e-4, weight_decay=1e-2, clip_max_norm=0.1)
+    groups = [[], [], [], []]
+    from gpv1_b200.optim import group_of
+    for n in shapes:
+        groups[group_of(n)].append(ref_params[n])
+    ref = torch.optim.AdamW([{"params": groups[0], "lr": 1e-4}, {"params": groups[1]}, {"params": groups[2]}, {"params": groups[3]}],
+                            lr=1e-3, weight_decay=1e-2)
+    for step in range(3):
+        for n, p, g in named:
+            g.copy_(torch.randn_like(g) * (0.01 if step == 1 else 1.0))   # step 1: norm below the threshold -> no clipping
+            ref_params[n].grad = g.clone()
+        norm = torch.nn.utils.clip_grad_norm_(groups[0] + groups[1], 0.1)
+        ref.step()
+        opt.step()
+        torch.cuda.synchronize()
+        assert abs(opt.grad_norm().item() - norm.item()) <= 1e-4 * norm.item()
+        for n, p, g in named:
+            assert torch.allclose(g, ref_params[n].grad, rtol=1e-5, atol=1e-8), (step, n, "clipped grad")
+            assert torch.allclose(p, ref_params[n].data, rtol=2e-5, atol=2e-6), (step, n, (p - ref_params[n].data).abs().max().item())

@@ -22,6 +22,7 @@ struct AttnParams {
   float* lse;                 // [B,H,Sq], log2 domain
   const uint8_t* kmask;       // [B,Sk] 1 = masked key, or null
   long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;  // token-row strides (elements)
+  long long bsq, bsk, bsv, bso;   // batch strides (elements) of q, k, v, o in the forward; S*ld unless a KV cache is read in place
   int B, H, Sq, Sk, causal;
   float scale;
 };
@@ -78,9 +79,9 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
   bf16* Vt = Ks + Skp * LD;
   uint8_t* msk = reinterpret_cast<uint8_t*>(Vt + DH * LDT);
 
-  stage<DH>(p.q + ((long long)b * Sq) * p.ldq + h * DH, p.ldq, Sq, Sqp, Qs, LD, nullptr, 0);
-  stage<DH>(p.k + ((long long)b * Sk) * p.ldk + h * DH, p.ldk, Sk, Skp, Ks, LD, nullptr, 0);
-  stage<DH>(p.v + ((long long)b * Sk) * p.ldv + h * DH, p.ldv, Sk, Skp, nullptr, 0, Vt, LDT);
+  stage<DH>(p.q + b * p.bsq + h * DH, p.ldq, Sq, Sqp, Qs, LD, nullptr, 0);
+  stage<DH>(p.k + b * p.bsk + h * DH, p.ldk, Sk, Skp, Ks, LD, nullptr, 0);
+  stage<DH>(p.v + b * p.bsv + h * DH, p.ldv, Sk, Skp, nullptr, 0, Vt, LDT);
   for (int j = threadIdx.x; j < Skp; j += blockDim.x)
     msk[j] = (j >= Sk) ? 1 : (p.kmask ? p.kmask[(long long)b * Sk + j] : 0);
   __syncthreads();
@@ -162,13 +163,13 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     if (row0 < Sq) {
-      bf16* op = p.o + ((long long)b * Sq + row0) * p.ldo + h * DH + 2 * t;
+      bf16* op = p.o + b * p.bso + (long long)row0 * p.ldo + h * DH + 2 * t;
 #pragma unroll
       for (int nd = 0; nd < DH / 8; ++nd) *reinterpret_cast<uint32_t*>(op + nd * 8) = pack_bf16x2(o[nd][0] * i0, o[nd][1] * i0);
       if (p.lse && t == 0) p.lse[((long long)b * p.H + h) * Sq + row0] = m0 * sl2 + log2f(l0);
     }
     if (row1 < Sq) {
-      bf16* op = p.o + ((long long)b * Sq + row1) * p.ldo + h * DH + 2 * t;
+      bf16* op = p.o + b * p.bso + (long long)row1 * p.ldo + h * DH + 2 * t;
 #pragma unroll
       for (int nd = 0; nd < DH / 8; ++nd) *reinterpret_cast<uint32_t*>(op + nd * 8) = pack_bf16x2(o[nd][2] * i1, o[nd][3] * i1);
       if (p.lse && t == 0) p.lse[((long long)b * p.H + h) * Sq + row1] = m1 * sl2 + log2f(l1);
@@ -432,21 +433,33 @@ static int dispatch(const AttnParams& p, int dh, bool bwd, cudaStream_t st) {
 
 using namespace gpv;
 
-extern "C" int gpvb200_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
-                                     const uint8_t* key_mask, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                                     int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale,
-                                     void* stream) {
+extern "C" int gpvb200_attention_fwd_bs(const void* q, const void* k, const void* v, void* o, float* lse,
+                                        const uint8_t* key_mask, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                        int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, int32_t B, int32_t H, int32_t Sq,
+                                        int32_t Sk, int32_t dh, int32_t causal, float scale, void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(q && k && v && o, "attention_fwd: null pointer");
   GPV_REQUIRE(B > 0 && H > 0 && Sq > 0 && Sk > 0, "attention_fwd: bad shape");
   GPV_REQUIRE((ldq % 8 == 0) && (ldk % 8 == 0) && (ldv % 8 == 0) && (ldo % 2 == 0), "attention_fwd: row strides must be multiples of 8");
+  GPV_REQUIRE((bsq % 8 == 0) && (bsk % 8 == 0) && (bsv % 8 == 0) && (bso % 2 == 0), "attention_fwd: batch strides must be multiples of 8");
   AttnParams p = {};
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
   p.lse = lse; p.kmask = key_mask;
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+  p.bsq = bsq > 0 ? bsq : (long long)Sq * ldq;
+  p.bsk = bsk > 0 ? bsk : (long long)Sk * ldk;
+  p.bsv = bsv > 0 ? bsv : (long long)Sk * ldv;
+  p.bso = bso > 0 ? bso : (long long)Sq * ldo;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
   return dispatch(p, dh, false, (cudaStream_t)stream);
+}
+
+extern "C" int gpvb200_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                                     const uint8_t* key_mask, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                     int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale,
+                                     void* stream) {
+  return gpvb200_attention_fwd_bs(q, k, v, o, lse, key_mask, ldq, ldk, ldv, ldo, 0, 0, 0, 0, B, H, Sq, Sk, dh, causal, scale, stream);
 }
 
 extern "C" int gpvb200_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,

@@ -194,16 +194,17 @@ def lsap(cost, tgt_offsets):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def attention_fwd(q, k, v, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None, need_lse=True, out=None):
+def attention_fwd(q, k, v, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None, need_lse=True, out=None, bs_k=0, bs_v=0):
     """q/k/v: bf16 2-D views [B*S, >=H*dh] (row stride = tokens' leading dimension; may be slices of a packed QKV).
+    bs_k / bs_v: batch strides in elements when K / V are read in place from a cache [B][S_max][...] with Sk <= S_max.
     Returns (o [B*Sq, H*dh] bf16, lse [B,H,Sq] fp32 log2-domain or None)."""
     o = out if out is not None else torch.empty((B * Sq, H * dh), device=q.device, dtype=BF16)
     lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32) if need_lse else None
-    _C.check(_C.lib().gpvb200_attention_fwd(
+    i64 = ctypes.c_int64
+    _C.check(_C.lib().gpvb200_attention_fwd_bs(
         _C.ptr(_req(q, BF16)), _C.ptr(_req(k, BF16)), _C.ptr(_req(v, BF16)), _C.ptr(o), _C.ptr(lse),
-        _C.ptr(_req(key_mask, torch.uint8)), ctypes.c_int64(q.stride(0)), ctypes.c_int64(k.stride(0)),
-        ctypes.c_int64(v.stride(0)), ctypes.c_int64(o.stride(0)), B, H, Sq, Sk, dh, int(causal), ctypes.c_float(scale),
-        _C.stream_ptr()), "attention_fwd")
+        _C.ptr(_req(key_mask, torch.uint8)), i64(q.stride(0)), i64(k.stride(0)), i64(v.stride(0)), i64(o.stride(0)),
+        i64(0), i64(bs_k), i64(bs_v), i64(0), B, H, Sq, Sk, dh, int(causal), ctypes.c_float(scale), _C.stream_ptr()), "attention_fwd")
     return o, lse
 
 

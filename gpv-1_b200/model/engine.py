@@ -711,6 +711,69 @@ class Engine:
         k.gemm(x, wc, logits, M=B * Sx, N=self.V, K=self.D, lda=x.stride(0), ldb=wc.stride(0), ldd=self.Vp)
         return logits, (emb, layers, x, wc)
 
+    # ================================================================================================ KV-cached decoding
+    @torch.no_grad()
+    def decode_begin(self, memory, B, Tm, max_len, rep=1):
+        """Start autoregressive decoding against `memory` [B*Tm, D] with `rep` hypotheses per sample (beams folded into
+        the batch: row b*rep + r).  What the reference recomputes for every generated token (gpv.py:178-196 runs the
+        whole decode_text on the growing prefix, i.e. 210 token-decodes for 20 tokens, and the V x 768 x 768 classifier
+        transform 20 times) is computed once here: the cross-attention K/V of `memory` for every text-decoder layer and
+        the classifier matrix.  Self-attention K/V go to caches [B*rep, max_len, D] that decode_step() appends to."""
+        W, Pm, D = self.W, self.P, self.D
+        Bp = B * rep
+        kv_mem = []
+        for i in range(self.n_txt):
+            kv = self._cross_kv(f"text_decoder.layers.{i}", memory, memory)
+            if rep > 1:
+                kv = kv.view(B, 1, Tm, 2 * D).expand(B, rep, Tm, 2 * D).reshape(Bp * Tm, 2 * D)
+            kv_mem.append(kv)
+        wc = k.linear(W["answer_head.vocab_embed"], W["answer_head.classifier_transform.weight"], Pm["answer_head.classifier_transform.bias"])
+        mk = lambda: [torch.empty((Bp, max_len, D), device=self.dev, dtype=BF16) for _ in range(self.n_txt)]
+        return {"Bp": Bp, "Tm": Tm, "L": max_len, "t": 0, "kv_mem": kv_mem, "wc": wc, "kc": mk(), "vc": mk()}
+
+    @torch.no_grad()
+    def decode_step(self, st, tok_ids):
+        """tok_ids [Bp] int64 = the token at position st['t'] of every hypothesis -> logits fp32 [Bp, Vp] of the next
+        position.  One query row per hypothesis: 13 launches per layer on [Bp, D] activations."""
+        W, Pm, D, H = self.W, self.P, self.D, self.h_txt
+        Bp, Tm, L, t = st["Bp"], st["Tm"], st["L"], st["t"]
+        assert t < L, "decode_step past max_len"
+        dh = D // H
+        sc = dh ** -0.5
+        emb = k.gather_rows(Pm["answer_input_embedings.embedding_layer.weight"], tok_ids)
+        x = k.linear(emb, W["answer_input_embedings.transform.weight"], Pm["answer_input_embedings.transform.bias"])
+        for i in range(self.n_txt):
+            p = f"text_decoder.layers.{i}"
+            wi, bi_ = W[f"{p}.self_attn.in_proj_weight"], Pm[f"{p}.self_attn.in_proj_bias"]
+            kc, vc = st["kc"][i], st["vc"][i]
+            q = k.linear(x, wi[:D], bi_[:D])
+            k.linear(x, wi[D:2 * D], bi_[D:2 * D], out=kc[:, t])          # appended in place: row stride L*D
+            k.linear(x, wi[2 * D:], bi_[2 * D:], out=vc[:, t])
+            o, _ = k.attention_fwd(q, kc.view(Bp * L, D), vc.view(Bp * L, D), B=Bp, H=H, Sq=1, Sk=t + 1, dh=dh, scale=sc,
+                                   need_lse=False, bs_k=L * D, bs_v=L * D)
+            pre = k.linear(o, W[f"{p}.self_attn.out_proj.weight"], Pm[f"{p}.self_attn.out_proj.bias"], residual=x)
+            x, _ = k.layernorm_fwd(pre, Pm[f"{p}.norm1.weight"], Pm[f"{p}.norm1.bias"], 1e-5, need_stats=False)
+            wi, bi_ = W[f"{p}.multihead_attn.in_proj_weight"], Pm[f"{p}.multihead_attn.in_proj_bias"]
+            q = k.linear(x, wi[:D], bi_[:D])
+            kv = st["kv_mem"][i]
+            o, _ = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=Bp, H=H, Sq=1, Sk=Tm, dh=dh, scale=sc, need_lse=False)
+            pre = k.linear(o, W[f"{p}.multihead_attn.out_proj.weight"], Pm[f"{p}.multihead_attn.out_proj.bias"], residual=x)
+            x, _ = k.layernorm_fwd(pre, Pm[f"{p}.norm2.weight"], Pm[f"{p}.norm2.bias"], 1e-5, need_stats=False)
+            h = k.linear(x, W[f"{p}.linear1.weight"], Pm[f"{p}.linear1.bias"], act=RELU)
+            pre = k.linear(h, W[f"{p}.linear2.weight"], Pm[f"{p}.linear2.bias"], residual=x)
+            x, _ = k.layernorm_fwd(pre, Pm[f"{p}.norm3.weight"], Pm[f"{p}.norm3.bias"], 1e-5, need_stats=False)
+        wc = st["wc"]
+        logits = torch.empty((Bp, self.Vp), device=self.dev, dtype=F32)
+        k.gemm(x, wc, logits, M=Bp, N=self.V, K=D, lda=x.stride(0), ldb=wc.stride(0), ldd=self.Vp)
+        st["t"] = t + 1
+        return logits
+
+    @torch.no_grad()
+    def decode_reorder(self, st, parent):
+        """Beam search: hypothesis r continues hypothesis parent[r] (int64 [Bp]) -> permute the self-attention caches."""
+        st["kc"] = [c.index_select(0, parent) for c in st["kc"]]
+        st["vc"] = [c.index_select(0, parent) for c in st["vc"]]
+
     # ================================================================================================ training step
     @torch.no_grad()
     def forward_train(self, images, qids, ans_ids, tgt):

@@ -348,21 +348,25 @@ class GPV(nn.Module):
                 "detr_hs": s["detr_hs_joined"].float().view(1, B, Q, -1)}
 
     def _greedy(self, s, vocab_mask):
-        """gpv.py:178-196: append the arg-max token max_text_len-1 times, then return the logits of the full sequence."""
+        """gpv.py:178-196: append the arg-max token max_text_len-1 times and return the logits of every position.  The
+        reference re-runs decode_text on the growing prefix and once more on the full sequence; with the decoder's
+        self-attention K/V cached the per-step logits ARE the logits of that final pass (causal mask), so each token is
+        decoded once (Engine.decode_step).  vocab_mask ([V], 0 / -10000) is added before every arg-max and to the
+        returned logits (gpv.py:186-187, 193-194)."""
         eng = self.engine
-        B = s["B"]
-        ids = torch.full((B, 1), self.word_to_idx["__cls__"], dtype=torch.int64, device=eng.dev)
+        B, L = s["B"], self.cfg.max_text_len
+        st = eng.decode_begin(s["memory"], B, s["Tm"], L)
+        tok = torch.full((B,), self.word_to_idx["__cls__"], dtype=torch.int64, device=eng.dev)
         vm = vocab_mask.to(eng.dev).float() if vocab_mask is not None else None
-        lg = None
-        for t in range(self.cfg.max_text_len):
-            lg, _ = eng.decode_text(ids.reshape(-1), s["memory"], B, ids.shape[1], s["Tm"], save=False)
-            lg = lg.view(B, ids.shape[1], -1)[:, :, :eng.V]
+        out = torch.empty((B, L, eng.V), device=eng.dev, dtype=torch.float32)
+        for t in range(L):
+            lg = eng.decode_step(st, tok)[:, :eng.V]
             if vm is not None:
                 lg = lg + vm
-            if t == self.cfg.max_text_len - 1:
-                break
-            ids = torch.cat((ids, lg[:, -1].argmax(-1, keepdim=True)), 1)
-        return lg.unsqueeze(0)
+            out[:, t] = lg
+            if t < L - 1:
+                tok = lg.argmax(-1)
+        return out.unsqueeze(0)
 
     def forward_beam_search(self, images, queries, beam_size=1):
         eng = self.engine
@@ -389,17 +393,19 @@ class GPV(nn.Module):
         return outputs
 
     def _beam(self, s, K):
-        """gpv.py:256-328 with the beams folded into the batch (row b*K + k); bookkeeping stays on the device.
-        Candidate order (k1 major, k2 minor), first-occurrence tie break, beam 0 only at t = 0, __stop__ never ends a beam."""
+        """gpv.py:256-328 with the beams folded into the batch (row b*K + k), one KV-cached decode step per token and
+        the bookkeeping on the device.  Candidate order (k1 major, k2 minor), first-occurrence tie break (stable sort),
+        beam 0 only at t = 0, __stop__ never ends a beam -- as the reference."""
         eng = self.engine
-        B, Tm, D = s["B"], s["Tm"], eng.D
-        mem = s["memory"].view(B, 1, Tm, D).expand(B, K, Tm, D).reshape(B * K * Tm, D).contiguous()
+        B, Tm, L = s["B"], s["Tm"], self.cfg.max_text_len
+        st = eng.decode_begin(s["memory"], B, Tm, L, rep=K)
         ids = torch.full((B, K, 1), self.word_to_idx["__cls__"], dtype=torch.int64, device=eng.dev)
         score = torch.zeros((B, K), device=eng.dev)
-        for t in range(self.cfg.max_text_len - 1):
-            L = ids.shape[2]
-            lg, _ = eng.decode_text(ids.reshape(-1), mem, B * K, L, Tm, save=False)
-            last = lg.view(B, K, L, -1)[:, :, -1, :eng.V]
+        base = torch.arange(B, device=eng.dev)[:, None] * K
+        tok = ids[:, :, 0].reshape(-1)
+        for t in range(L - 1):
+            lg = eng.decode_step(st, tok)
+            last = lg.view(B, K, -1)[:, :, :eng.V]
             top = torch.log_softmax(last, -1).topk(K, -1)
             cand = score[:, :, None] + top.values
             if t == 0:
@@ -408,8 +414,11 @@ class GPV(nn.Module):
             order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, :K]
             k1 = torch.div(order, K, rounding_mode="floor")
             new_last = torch.gather(top.indices.reshape(B, K * K), 1, order)
-            ids = torch.cat((torch.gather(ids, 1, k1[:, :, None].expand(-1, -1, L)), new_last[:, :, None]), 2)
+            ids = torch.cat((torch.gather(ids, 1, k1[:, :, None].expand(-1, -1, ids.shape[2])), new_last[:, :, None]), 2)
             score = torch.gather(flat, 1, order)
+            if t < L - 2:
+                eng.decode_reorder(st, (base + k1).reshape(-1))
+                tok = new_last.reshape(-1)
         return ids[:, :, 1:], score
 
     # ------------------------------------------------------------------------------------------------ answers (host)

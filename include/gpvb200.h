@@ -118,6 +118,12 @@ int gpvb200_lsap(const float* cost /*[B,Q,Tmax]*/, const int32_t* tgt_offsets /*
 int gpvb200_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const uint8_t* key_mask,
                           int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int32_t B, int32_t H, int32_t Sq,
                           int32_t Sk, int32_t dh, int32_t causal, float scale, void* stream);
+/* same with explicit batch strides (elements; 0 = S*ld): lets a decode step read a preallocated KV cache
+ * [B][S_max][H*dh] in place with Sk = tokens written so far (the KV-cached text decoder, gpv.py:178-196, 256-328) */
+int gpvb200_attention_fwd_bs(const void* q, const void* k, const void* v, void* o, float* lse, const uint8_t* key_mask,
+                             int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t bsq, int64_t bsk, int64_t bsv,
+                             int64_t bso, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale,
+                             void* stream);
 int gpvb200_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                           const uint8_t* key_mask, void* dq, void* dk, void* dv, int64_t ldq, int64_t ldk, int64_t ldv,
                           int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, int32_t B, int32_t H,

@@ -320,6 +320,23 @@ def main():
         step_full()
     ms_full = timed(step_full, args.steps)
 
+    # third number: the same end-to-end step fed with the loader's raw format, uint8 NHWC pixels, whose
+    # ToTensor + Normalize (coco_generic_dataset.py:31-32) are folded into the stem's read: a quarter of the H2D bytes
+    ms_e2e_u8 = None
+    if not args.no_graph and not args.breakdown:
+        g8 = torch.Generator().manual_seed(2000 + rank)
+        h_u8 = torch.randint(0, 256, (B, H_IMG, W_IMG, 3), generator=g8, dtype=torch.uint8).pin_memory()
+        model.capture_step(h_u8.to(dev), d_qids, d_ans, d_targets)
+
+        def step_e2e_u8():
+            loss = model(h_u8, h_qids, h_ans, h_targets)
+            loss.backward()
+            return loss.item()
+
+        for _ in range(2):
+            step_e2e_u8()
+        ms_e2e_u8 = timed(step_e2e_u8, args.steps)
+
     breakdown = None
     if rank == 0 and args.breakdown:
         lib.trace = []
@@ -375,6 +392,9 @@ def main():
                        "dropout": "off (eval-mode-with-grad parity contract; Philox dropout not fused yet)", "loss": loss_val},
             "clocks": clocks,
             "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "e2e_uint8": None if ms_e2e_u8 is None else {
+                "value": world * B * args.steps / (ms_e2e_u8 / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e_u8 / args.steps,
+                "h2d_bytes_per_step": h2d - h_images.numel() * 3, "what": "e2e with uint8 NHWC host images, normalisation fused into the stem"},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
                           "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},

@@ -285,6 +285,45 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__
   }
 }
 
+// Same map from the loader's raw format: uint8 NHWC [B][H][W][3] with the reference's normalisation
+// (ToTensor + Normalize, datasets/coco_generic_dataset.py:31-32: x = (u8 / 255 - mean[c]) / std[c]) folded into the read.
+// A quarter of the fp32 NCHW bytes over PCIe / HBM.
+struct Norm3 {
+  float scale[3], shift[3];   // x = u8 * scale[c] + shift[c]
+};
+__global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int B, int H, int W,
+                                                          int Hp, int Wp, const Norm3 nm) {
+  const long long total = (long long)B * Hp * Wp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int J = (int)(idx % Wp);
+    const long long t = idx / Wp;
+    const int I = (int)(t % Hp), b = (int)(t / Hp);
+    const int h0 = 2 * (I - 2), w0 = 2 * (J - 2);
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int h = h0 + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int w = w0 + dx;
+        if (w < 0 || w >= W) continue;
+        const uint8_t* px = img + (((long long)b * H + h) * W + w) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[dy * 6 + dx * 3 + c] = (float)__ldg(px + c) * nm.scale[c] + nm.shift[c];
+      }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);   o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ROI-align-mean weights (detr_roi_head.py:44-56 + torchvision roi_align, output 7x7, aligned=True,
 // sampling_ratio=-1, then mean over the 49 bins).  The mean is linear in the feature map with rank-1 separable
@@ -561,6 +600,23 @@ extern "C" int gpvb200_stem_s2d(const float* img, void* out, int32_t B, int32_t 
   const int Hp = (H - 1) / 2 + 1 + 4, Wp = (W - 1) / 2 + 1 + 4;
   stem_s2d_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, ST>>>(img, (bf16*)out, B, H, W, Hp, Wp);
   return check_launch("stem_s2d_kernel");
+}
+
+extern "C" int gpvb200_stem_s2d_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t W, const float* mean3,
+                                   const float* std3, void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(img && out && mean3 && std3 && B > 0 && H > 0 && W > 0, "stem_s2d_u8: bad arguments");
+  GPV_REQUIRE(((uintptr_t)out & 15) == 0, "stem_s2d_u8: unaligned output");
+  Norm3 nm;
+  for (int c = 0; c < 3; ++c) {   // mean3 / std3 are HOST arrays (three floats each)
+    GPV_REQUIRE(std3[c] > 0.f, "stem_s2d_u8: std must be positive");
+    nm.scale[c] = 1.0f / (255.0f * std3[c]);
+    nm.shift[c] = -mean3[c] / std3[c];
+  }
+  const int Hp = (H - 1) / 2 + 1 + 4, Wp = (W - 1) / 2 + 1 + 4;
+  stem_s2d_u8_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, ST>>>(img, (bf16*)out, B, H, W, Hp, Wp, nm);
+  return check_launch("stem_s2d_u8_kernel");
 }
 
 extern "C" int gpvb200_roi_weights(const float* boxes, int64_t ldb, void* wroi, int64_t ldw, int32_t BQ, int32_t H, int32_t W,

@@ -285,16 +285,28 @@ def stem_im2col(img, out=None):
     return col, Ho, Wo
 
 
-def stem_s2d(img):
-    """img NCHW fp32 -> (virtual NHWC view [B, Ho+4, Wo+4, 64] bf16 with pixel stride 16, Ho, Wo): the space-to-depth
-    map of the 7x7/s2 stem; pixel (I, J) of the view = the 4 adjacent s2d pixels J..J+3 of row I (see elementwise.cu)."""
-    B, C, H, W = img.shape
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)   # coco_generic_dataset.py:32
+
+
+def stem_s2d(img, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """img NCHW fp32 (already normalised) or NHWC uint8 (raw pixels; normalised here) -> (virtual NHWC view
+    [B, Ho+4, Wo+4, 64] bf16 with pixel stride 16, Ho, Wo): the space-to-depth map of the 7x7/s2 stem; pixel (I, J) of
+    the view = the 4 adjacent s2d pixels J..J+3 of row I (see elementwise.cu)."""
+    if img.dtype == torch.uint8:
+        B, H, W, C = img.shape
+    else:
+        B, C, H, W = img.shape
     assert C == 3
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     Hp, Wp = Ho + 4, Wo + 4
     buf = torch.empty(B * Hp * Wp * 16 + 64, device=img.device, dtype=BF16)   # + 64: view pixels J > Wo (never stored) read up to 48 past the map
-    _C.check(_C.lib().gpvb200_stem_s2d(_C.ptr(_req(img.contiguous(), torch.float32)), _C.ptr(buf), B, H, W, _C.stream_ptr()),
-             "stem_s2d")
+    if img.dtype == torch.uint8:
+        f3 = ctypes.c_float * 3
+        _C.check(_C.lib().gpvb200_stem_s2d_u8(_C.ptr(_req(img.contiguous())), _C.ptr(buf), B, H, W, f3(*mean), f3(*std), _C.stream_ptr()),
+                 "stem_s2d_u8")
+    else:
+        _C.check(_C.lib().gpvb200_stem_s2d(_C.ptr(_req(img.contiguous(), torch.float32)), _C.ptr(buf), B, H, W, _C.stream_ptr()),
+                 "stem_s2d")
     view = torch.as_strided(buf, (B, Hp, Wp, 64), (Hp * Wp * 16, Wp * 16, 16, 1))
     return view, Ho, Wo
 

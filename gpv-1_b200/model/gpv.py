@@ -294,6 +294,11 @@ class GPV(nn.Module):
             if len({tuple(i.shape) for i in images}) != 1:
                 raise NotImplementedError("padded (mixed-size) image batches are not built yet")
             images = torch.stack(list(images))
+        if images.dtype == torch.uint8:
+            # raw loader format [B,H,W,3]: ToTensor + Normalize (coco_generic_dataset.py:31-32) are folded into the stem's read
+            if images.dim() != 4 or images.shape[-1] != 3:
+                raise ValueError("uint8 images must be NHWC [B,H,W,3]")
+            return images.to(device=dev, non_blocking=True).contiguous()
         return images.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
     def _queries(self, queries):

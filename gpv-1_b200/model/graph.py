@@ -23,7 +23,7 @@ class CapturedStep:
         self.img_shape, self.Tl = tuple(images.shape), qids.shape[1]
         cap = boxes_per_image_cap or eng.Q
         self.static_t = HostTargets.alloc_static(B, S, cap, dev)
-        self.images = torch.empty(self.img_shape, dtype=torch.float32, device=dev)
+        self.images = torch.empty(self.img_shape, dtype=images.dtype, device=dev)      # fp32 NCHW or uint8 NHWC
         self.qids = torch.empty((B, self.Tl), dtype=torch.int64, device=dev)
         self.ans = torch.empty((B, S), dtype=torch.int64, device=dev)
         tgt = self._load(images, qids, ans, targets)
@@ -82,7 +82,8 @@ class CapturedStep:
         self.pending = False
 
     def matches(self, images, qids, ans):
-        return tuple(images.shape) == self.img_shape and qids.shape[1] == self.Tl and tuple(ans.shape) == (self.B, self.S)
+        return (tuple(images.shape) == self.img_shape and images.dtype == self.images.dtype and qids.shape[1] == self.Tl
+                and tuple(ans.shape) == (self.B, self.S))
 
     def _load(self, images, qids, ans, targets):
         self.images.copy_(images, non_blocking=True)

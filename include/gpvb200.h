@@ -163,6 +163,10 @@ int gpvb200_stem_im2col(const float* img, void* col, int32_t B, int32_t H, int32
 /* stem space-to-depth: NCHW fp32 -> zero-bordered bf16 [B][Ho+4][Wo+4][16] (Ho = ceil(H/2)), channel = dy*6 + dx*3 + c;
  * with it the 7x7/s2 stem (backbone.py:72) is a 4-tap K=64 implicit GEMM of gpvb200_gemm mode 1 (pixel stride 16) */
 int gpvb200_stem_s2d(const float* img, void* out, int32_t B, int32_t H, int32_t W, void* stream);
+/* same map from uint8 NHWC [B][H][W][3] with x = (u8/255 - mean[c]) / std[c] folded in (ToTensor + Normalize of
+ * datasets/coco_generic_dataset.py:31-32); mean3 / std3 are HOST arrays of three floats */
+int gpvb200_stem_s2d_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t W, const float* mean3, const float* std3,
+                        void* stream);
 /* ROI-align(7x7, aligned, adaptive sampling)+mean as separable weights (detr_roi_head.py:44-56): wroi[bq][y*W+x] */
 int gpvb200_roi_weights(const float* boxes, int64_t ldb, void* wroi, int64_t ldw, int32_t BQ, int32_t H, int32_t W, void* stream);
 /* relevance conditioning gpv.py:364-375 (+ the memory concat gpv.py:175 through the output row remap) */

@@ -329,3 +329,21 @@ def test_clip_adamw_matches_torch(cuda):
         for n, p, g in named:
             assert torch.allclose(g, ref_params[n].grad, rtol=1e-5, atol=1e-8), (step, n, "clipped grad")
             assert torch.allclose(p, ref_params[n].data, rtol=2e-5, atol=2e-6), (step, n, (p - ref_params[n].data).abs().max().item())
+
+
+def test_stem_s2d_uint8_equals_normalised_fp32(cuda):
+    """uint8 NHWC ingest: (u8/255 - mean)/std folded into the stem's read gives the same s2d map as the
+    fp32 NCHW path fed with the reference's ToTensor + Normalize output (coco_generic_dataset.py:31-32)."""
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(9)
+    u8 = torch.randint(0, 256, (2, 37, 50, 3), device=cuda, dtype=torch.uint8)
+    mean = torch.tensor(k.IMAGENET_MEAN, device=cuda).view(1, 3, 1, 1)
+    std = torch.tensor(k.IMAGENET_STD, device=cuda).view(1, 3, 1, 1)
+    f32 = (u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    a, Ho, Wo = k.stem_s2d(u8)
+    b, Ho2, Wo2 = k.stem_s2d(f32.contiguous())
+    assert (Ho, Wo) == (Ho2, Wo2)
+    # compare the underlying [B, Hp, Wp, 16] maps (the 64-wide views overlap)
+    ma, mb = a[..., :16].float(), b[..., :16].float()
+    assert (ma - mb).abs().max().item() <= 2e-2        # one bf16 ulp at |x| <= 2.7 where the two fp32 roundings differ
+    assert (ma != mb).float().mean().item() < 0.05

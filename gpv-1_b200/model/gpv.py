@@ -224,6 +224,8 @@ class GPV(nn.Module):
         self._tokenizer = None
         self.grad_sync = None          # parallel.GradSync installs itself here
         self._captured = None          # model/graph.py:CapturedStep once capture_step() ran
+        self.inference_graphs = False  # True: greedy / beam inference of a repeated input shape replays one CUDA graph
+        self._inf_graphs = {}
 
     # ------------------------------------------------------------------------------------------------ plumbing
     @property
@@ -333,6 +335,8 @@ class GPV(nn.Module):
                 return _Step.apply(self._anchor(), loss, self)
             eng.saved = None
             return loss.view(())
+        if answer_token_ids is None and targets is None and self.inference_graphs:
+            return self._graphed("greedy", images, qids, vocab_mask, None)
         with torch.no_grad():
             s = eng.encode(images, qids, save=False)
             outputs = self._outputs(s)
@@ -373,13 +377,60 @@ class GPV(nn.Module):
                 tok = lg.argmax(-1)
         return out.unsqueeze(0)
 
+    def _graphed(self, kind, images, qids, vocab_mask, beam_size):
+        """Whole-call CUDA graph of the inference path (encode + every KV-cached decode step + the on-device arg-max /
+        beam bookkeeping): ~1600 launches of 3-10 us each are otherwise issued one by one from Python.  One graph per
+        (kind, image shape / dtype, query length, max_text_len, beam size, mask presence); inputs are copied into the
+        graph's static buffers, outputs are returned as copies."""
+        eng = self.engine
+        dev = eng.dev
+        key = (kind, tuple(images.shape), images.dtype, tuple(qids.shape), self.cfg.max_text_len, beam_size, vocab_mask is not None)
+        g = self._inf_graphs.get(key)
+        if g is None:
+            st_img, st_q = images.clone(), qids.clone()
+            st_vm = vocab_mask.to(dev).float().clone() if vocab_mask is not None else None
+
+            def run():
+                s = eng.encode(st_img, st_q, save=False)
+                out = self._outputs(s)
+                if kind == "greedy":
+                    out["answer_logits"] = self._greedy(s, st_vm)
+                else:
+                    out["beam_token_ids"], out["beam_scores"] = self._beam(s, beam_size)
+                return out
+
+            eng.refresh()
+            with torch.no_grad():
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    run()                                     # first-call work outside the capture
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = run()
+            g = self._inf_graphs[key] = (graph, st_img, st_q, st_vm, outs)
+        graph, st_img, st_q, st_vm, outs = g
+        st_img.copy_(images, non_blocking=True)
+        st_q.copy_(qids, non_blocking=True)
+        if st_vm is not None:
+            st_vm.copy_(vocab_mask.to(dev).float(), non_blocking=True)
+        eng.refresh()
+        graph.replay()
+        return {k_: v.clone() for k_, v in outs.items()}
+
     def forward_beam_search(self, images, queries, beam_size=1):
         eng = self.engine
         images, qids = self._images(images), self._queries(queries)
         with torch.no_grad():
-            s = eng.encode(images, qids, save=False)
-            outputs = self._outputs(s)
-            seqs, logp = self._beam(s, beam_size)
+            if self.inference_graphs:
+                outputs = self._graphed("beam", images, qids, None, beam_size)
+                seqs, logp = outputs.pop("beam_token_ids"), outputs.pop("beam_scores")
+            else:
+                s = eng.encode(images, qids, save=False)
+                outputs = self._outputs(s)
+                seqs, logp = self._beam(s, beam_size)
         seqs_h, p_h = seqs.cpu().tolist(), logp.exp().cpu().tolist()
         stop = {self.word_to_idx["__stop__"], self.word_to_idx["__pad__"]}
         answers = []

@@ -68,6 +68,7 @@ GPV_DEVINL void load_a_frags(const bf16* s, int LD, int r0, int g, int t, uint32
 // ======================================================================================== forward
 template <int DH, int NT>
 __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int Sq = p.Sq, Sk = p.Sk;
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
 // Pass 2 (warp owns 16 keys):    dV = P^T dO,      dK = scale * [P o (dO V^T - D)]^T Q
 template <int DH, int NT>
 __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int Sq = p.Sq, Sk = p.Sk;
@@ -413,7 +415,7 @@ static int launch_attn(const AttnParams& p, bool bwd, cudaStream_t st) {
     set_last_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return GPV_ERR_CUDA;
   }
-  kern<<<p.B * p.H, bwd ? NTB : NTF, smem, st>>>(p);
+  launch_k(kern, dim3(p.B * p.H), dim3(bwd ? NTB : NTF), smem, st, p);
   return check_launch(bwd ? "attn_bwd_kernel" : "attn_fwd_kernel");
 }
 

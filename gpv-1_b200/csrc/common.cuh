@@ -132,6 +132,14 @@ GPV_DEVINL uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_
   return d;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// First statement of every kernel launched through launch_k(): wait until the previous kernel of the stream has
+// completed (no-op without the launch attribute), then let the next kernel start its own prologue.
+GPV_DEVINL void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- misc math
 GPV_DEVINL float warp_sum(float v) {
 #pragma unroll

@@ -15,6 +15,7 @@ constexpr int kSMs = 148;
 // ------------------------------------------------------------------------------------------------
 __global__ void add_rowbcast_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ pe, long long ldp,
                                     bf16* __restrict__ out, long long ldo, long long M, int D, int P) {
+  pdl_sync();
   const int nch = D >> 3;
   const long long total = M * nch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -42,6 +43,7 @@ __global__ void add_rowbcast_kernel(const bf16* __restrict__ x, long long ldx, c
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out,
                                                      long long M, int N, int rows_per_cta) {
+  pdl_sync();
   __shared__ float red[4][64];
   const int col = blockIdx.x * 64 + (threadIdx.x & 63);
   const int rgrp = threadIdx.x >> 6;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
 // rows, four rows in flight per thread; the 8 partial rows meet in shared memory and leave as one atomic per column.
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out,
                                                          long long M, int N, int rows_per_cta) {
+  pdl_sync();
   __shared__ float red[8][256 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const bf16* __restrict_
 
 // out[s][d] += sum_b x[b*S + s][d]   (gradient of a parameter broadcast over the batch, e.g. query_embed)
 __global__ void batch_reduce_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int B, int S, int D) {
+  pdl_sync();
   const long long total = (long long)S * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(i / D), d = (int)(i % D);
@@ -174,6 +178,7 @@ __global__ void bn_fold_kernel(const float* w, const float* b, const float* rm, 
 // 3x3 stride-2 pad-1 max-pool on NHWC bf16 (torchvision resnet stem, backbone.py:72)
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
+  pdl_sync();
   const int nch = C >> 3;
   const long long total = (long long)B * Ho * Wo * nch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -250,6 +255,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, bf16* __restri
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W,
                                                        int Hp, int Wp) {
+  pdl_sync();
   const long long total = (long long)B * Hp * Wp;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int J = (int)(idx % Wp);
@@ -293,6 +299,7 @@ struct Norm3 {
 };
 __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int B, int H, int W,
                                                           int Hp, int Wp, const Norm3 nm) {
+  pdl_sync();
   const long long total = (long long)B * Hp * Wp;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int J = (int)(idx % Wp);
@@ -357,6 +364,7 @@ GPV_DEVINL void roi_axis_weights(float start, float size, int n, float* w /*[n]*
 
 __global__ void __launch_bounds__(64) roi_weights_kernel(const float* __restrict__ boxes, long long ldb, bf16* __restrict__ wroi,
                                                          long long ldw, int BQ, int H, int W) {
+  pdl_sync();
   __shared__ float wy[64], wx[64];
   const int bq = blockIdx.x;
   if (bq >= BQ) return;
@@ -385,6 +393,7 @@ __global__ void __launch_bounds__(256) relevance_mix_fwd_kernel(const bf16* __re
                                                                 const float* __restrict__ tok, bf16* __restrict__ out,
                                                                 long long ldo, int M, int D, int G, int out_gstride,
                                                                 int out_off) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long m = (long long)blockIdx.x * 8 + warp; m < M; m += (long long)gridDim.x * 8) {
     const float l0 = logits[m * ldl], l1 = logits[m * ldl + 1];
@@ -415,6 +424,7 @@ __global__ void __launch_bounds__(256) relevance_mix_bwd_kernel(const bf16* __re
                                                                 const float* __restrict__ tok, float* __restrict__ dlogits,
                                                                 long long lddl, float* __restrict__ dtok, int M, int D, int G,
                                                                 int gstride, int off) {
+  pdl_sync();
   extern __shared__ float acc[];  // [2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) acc[i] = 0.f;
@@ -451,6 +461,7 @@ __global__ void __launch_bounds__(256) relevance_mix_bwd_kernel(const bf16* __re
 // ------------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, const float* __restrict__ pos,
                                    const float* __restrict__ cst, bf16* __restrict__ out, long long ldo, long long M, int D, int T) {
+  pdl_sync();
   const int nch = D >> 2;
   const long long total = M * nch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -475,6 +486,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const int64_
 // dst[remap_d(m)][:] = src[remap_s(m)][:]   with remap(m) = (m / G) * gstride + off + m % G     (memory concat, gpv.py:175)
 __global__ void copy_rows_kernel(const bf16* __restrict__ src, long long lds, int sG, int sgs, int soff, bf16* __restrict__ dst,
                                  long long ldd, int dG, int dgs, int doff, long long M, int D) {
+  pdl_sync();
   const int nch = D >> 3;
   const long long total = M * nch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -486,6 +498,7 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ src, long long lds, in
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_sync();
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
@@ -517,7 +530,7 @@ extern "C" int gpvb200_add_rowbcast(const void* x, int64_t ldx, const void* p, i
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(p && out && D % 8 == 0 && P > 0 && ldp % 8 == 0 && ldo % 8 == 0 && (x == nullptr || ldx % 8 == 0), "add_rowbcast: bad arguments");
   if (M == 0) return GPV_OK;
-  add_rowbcast_kernel<<<grid_for(M * (D / 8), 256), 256, 0, ST>>>((const bf16*)x, ldx, (const bf16*)p, ldp, (bf16*)out, ldo, M, D, P);
+  launch_k(add_rowbcast_kernel, dim3(grid_for(M * (D / 8), 256)), dim3(256), 0, ST, (const bf16*)x, ldx, (const bf16*)p, ldp, (bf16*)out, ldo, M, D, P);
   return check_launch("add_rowbcast_kernel");
 }
 
@@ -532,7 +545,7 @@ extern "C" int gpvb200_colsum(const void* dy, int64_t ld, float* out, int64_t M,
     if ((long long)gy * 32 > M) gy = (int)((M + 31) / 32);
     if (gy < 1) gy = 1;
     const int rows = (int)((M + gy - 1) / gy);
-    colsum_vec_kernel<<<dim3(gx, gy), 256, 0, ST>>>((const bf16*)dy, ld, out, M, N, rows);
+    launch_k(colsum_vec_kernel, dim3(gx, gy), dim3(256), 0, ST, (const bf16*)dy, ld, out, M, N, rows);
     return check_launch("colsum_vec_kernel");
   }
   const int gx = (N + 63) / 64;
@@ -540,7 +553,7 @@ extern "C" int gpvb200_colsum(const void* dy, int64_t ld, float* out, int64_t M,
   if ((long long)gy * 64 > M) gy = (int)((M + 63) / 64);
   if (gy < 1) gy = 1;
   const int rows = (int)((M + gy - 1) / gy);
-  colsum_kernel<<<dim3(gx, gy), 256, 0, ST>>>((const bf16*)dy, ld, out, M, N, rows);
+  launch_k(colsum_kernel, dim3(gx, gy), dim3(256), 0, ST, (const bf16*)dy, ld, out, M, N, rows);
   return check_launch("colsum_kernel");
 }
 
@@ -548,7 +561,7 @@ extern "C" int gpvb200_batch_reduce(const void* x, int64_t ld, float* out, int32
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(x && out && B > 0 && S > 0 && D > 0, "batch_reduce: bad arguments");
-  batch_reduce_kernel<<<grid_for((long long)S * D, 256), 256, 0, ST>>>((const bf16*)x, ld, out, B, S, D);
+  launch_k(batch_reduce_kernel, dim3(grid_for((long long)S * D, 256)), dim3(256), 0, ST, (const bf16*)x, ld, out, B, S, D);
   return check_launch("batch_reduce_kernel");
 }
 
@@ -579,7 +592,7 @@ extern "C" int gpvb200_maxpool3x3s2(const void* x, void* y, int32_t B, int32_t H
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C % 8 == 0, "maxpool: bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  maxpool_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, ST>>>((const bf16*)x, (bf16*)y, B, H, W, C, Ho, Wo);
+  launch_k(maxpool_kernel, dim3(grid_for((long long)B * Ho * Wo * (C / 8), 256)), dim3(256), 0, ST, (const bf16*)x, (bf16*)y, B, H, W, C, Ho, Wo);
   return check_launch("maxpool_kernel");
 }
 
@@ -598,7 +611,7 @@ extern "C" int gpvb200_stem_s2d(const float* img, void* out, int32_t B, int32_t 
   GPV_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "stem_s2d: bad arguments");
   GPV_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)img & 7) == 0, "stem_s2d: unaligned buffers");
   const int Hp = (H - 1) / 2 + 1 + 4, Wp = (W - 1) / 2 + 1 + 4;
-  stem_s2d_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, ST>>>(img, (bf16*)out, B, H, W, Hp, Wp);
+  launch_k(stem_s2d_kernel, dim3(grid_for((long long)B * Hp * Wp, 256)), dim3(256), 0, ST, img, (bf16*)out, B, H, W, Hp, Wp);
   return check_launch("stem_s2d_kernel");
 }
 
@@ -615,7 +628,7 @@ extern "C" int gpvb200_stem_s2d_u8(const uint8_t* img, void* out, int32_t B, int
     nm.shift[c] = -mean3[c] / std3[c];
   }
   const int Hp = (H - 1) / 2 + 1 + 4, Wp = (W - 1) / 2 + 1 + 4;
-  stem_s2d_u8_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, ST>>>(img, (bf16*)out, B, H, W, Hp, Wp, nm);
+  launch_k(stem_s2d_u8_kernel, dim3(grid_for((long long)B * Hp * Wp, 256)), dim3(256), 0, ST, img, (bf16*)out, B, H, W, Hp, Wp, nm);
   return check_launch("stem_s2d_u8_kernel");
 }
 
@@ -625,7 +638,7 @@ extern "C" int gpvb200_roi_weights(const float* boxes, int64_t ldb, void* wroi, 
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(boxes && wroi && BQ >= 0 && H > 0 && W > 0 && H <= 64 && W <= 64 && ldw >= (int64_t)H * W, "roi_weights: bad arguments");
   if (BQ == 0) return GPV_OK;
-  roi_weights_kernel<<<BQ, 64, 0, ST>>>(boxes, ldb, (bf16*)wroi, ldw, BQ, H, W);
+  launch_k(roi_weights_kernel, dim3(BQ), dim3(64), 0, ST, boxes, ldb, (bf16*)wroi, ldw, BQ, H, W);
   return check_launch("roi_weights_kernel");
 }
 
@@ -636,7 +649,7 @@ extern "C" int gpvb200_relevance_mix_fwd(const void* x, int64_t ldx, const float
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(x && logits && tok && out && D % 8 == 0 && G > 0, "relevance_mix_fwd: bad arguments");
   if (M == 0) return GPV_OK;
-  relevance_mix_fwd_kernel<<<grid_for(M, 8), 256, 0, ST>>>((const bf16*)x, ldx, logits, ldl, tok, (bf16*)out, ldo, M, D, G, out_gstride, out_off);
+  launch_k(relevance_mix_fwd_kernel, dim3(grid_for(M, 8)), dim3(256), 0, ST, (const bf16*)x, ldx, logits, ldl, tok, (bf16*)out, ldo, M, D, G, out_gstride, out_off);
   return check_launch("relevance_mix_fwd_kernel");
 }
 
@@ -649,7 +662,7 @@ extern "C" int gpvb200_relevance_mix_bwd(const void* dy, int64_t lddy, const flo
   if (M == 0) return GPV_OK;
   int grid = (M + 7) / 8;
   if (grid > kSMs) grid = kSMs;
-  relevance_mix_bwd_kernel<<<grid, 256, (size_t)2 * D * sizeof(float), ST>>>((const bf16*)dy, lddy, logits, ldl, tok, dlogits, lddl, dtok, M, D, G,
+  launch_k(relevance_mix_bwd_kernel, dim3(grid), dim3(256), (size_t)2 * D * sizeof(float), ST, (const bf16*)dy, lddy, logits, ldl, tok, dlogits, lddl, dtok, M, D, G,
                                                                             gstride, off);
   return check_launch("relevance_mix_bwd_kernel");
 }
@@ -660,7 +673,7 @@ extern "C" int gpvb200_gather_rows(const float* table, const int64_t* ids, const
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(table && ids && out && D % 4 == 0 && ldo % 4 == 0, "gather_rows: bad arguments");
   if (M == 0) return GPV_OK;
-  gather_rows_kernel<<<grid_for(M * (D / 4), 256), 256, 0, ST>>>(table, ids, pos, cst, (bf16*)out, ldo, M, D, T > 0 ? T : 1);
+  launch_k(gather_rows_kernel, dim3(grid_for(M * (D / 4), 256)), dim3(256), 0, ST, table, ids, pos, cst, (bf16*)out, ldo, M, D, T > 0 ? T : 1);
   return check_launch("gather_rows_kernel");
 }
 
@@ -670,7 +683,7 @@ extern "C" int gpvb200_copy_rows(const void* src, int64_t lds, int32_t sG, int32
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(src && dst && D % 8 == 0 && sG > 0 && dG > 0 && lds % 8 == 0 && ldd % 8 == 0, "copy_rows: bad arguments");
   if (M == 0) return GPV_OK;
-  copy_rows_kernel<<<grid_for(M * (D / 8), 256), 256, 0, ST>>>((const bf16*)src, lds, sG, sgs, soff, (bf16*)dst, ldd, dG, dgs, doff, M, D);
+  launch_k(copy_rows_kernel, dim3(grid_for(M * (D / 8), 256)), dim3(256), 0, ST, (const bf16*)src, lds, sG, sgs, soff, (bf16*)dst, ldd, dG, dgs, doff, M, D);
   return check_launch("copy_rows_kernel");
 }
 
@@ -679,7 +692,7 @@ extern "C" int gpvb200_cast_f32_bf16(const float* src, void* dst, int64_t n, voi
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(src && dst && n >= 0, "cast: bad arguments");
   if (n == 0) return GPV_OK;
-  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST>>>(src, (bf16*)dst, n);
+  launch_k(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, ST, src, (bf16*)dst, n);
   return check_launch("cast_f32_bf16_kernel");
 }
 
@@ -689,6 +702,7 @@ extern "C" int gpvb200_cast_f32_bf16(const float* src, void* dst, int64_t n, voi
 // ------------------------------------------------------------------------------------------------
 namespace gpv {
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int taps, int accumulate) {
+  pdl_sync();
   const long long OI = (long long)O * I, n = OI * taps;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const long long oi = e / taps;
@@ -701,6 +715,7 @@ __global__ void unpack_conv_grad_kernel(const float* __restrict__ src, float* __
 // out = a + b (bf16, row strides), vectorised 16 B
 __global__ void add_bf16_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ b, long long ldb,
                                 bf16* __restrict__ out, long long ldo, long long M, int D) {
+  pdl_sync();
   const int nch = D >> 3;
   const long long total = M * nch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -725,7 +740,7 @@ extern "C" int gpvb200_unpack_conv_grad(const float* src, float* dst, int32_t O,
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(src && dst && O > 0 && I > 0 && taps > 0, "unpack_conv_grad: bad arguments");
-  unpack_conv_grad_kernel<<<grid_for((long long)O * I * taps, 256), 256, 0, ST>>>(src, dst, O, I, taps, accumulate);
+  launch_k(unpack_conv_grad_kernel, dim3(grid_for((long long)O * I * taps, 256)), dim3(256), 0, ST, src, dst, O, I, taps, accumulate);
   return check_launch("unpack_conv_grad_kernel");
 }
 
@@ -735,6 +750,6 @@ extern "C" int gpvb200_add_bf16(const void* a, int64_t lda, const void* b, int64
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(a && b && out && D % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "add_bf16: bad arguments");
   if (M == 0) return GPV_OK;
-  add_bf16_kernel<<<grid_for(M * (D / 8), 256), 256, 0, ST>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out, ldo, M, D);
+  launch_k(add_bf16_kernel, dim3(grid_for(M * (D / 8), 256)), dim3(256), 0, ST, (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out, ldo, M, D);
   return check_launch("add_bf16_kernel");
 }

@@ -396,6 +396,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run while
+  // the previous kernel of the stream is still draining; global memory is touched only after this point.  Dependents
+  // are released at once -- their own prologue then overlaps this kernel's work.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ================================================================== TMA producer
@@ -771,7 +776,26 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
     configured = true;
   }
   const int grid = kp.total_work < num_sms() ? kp.total_work : num_sms();
-  umma_gemm_kernel<BN, F><<<grid, kThreads, smem, st>>>(ma, mb, kp);
+  static int pdl = -1;   // GPVB200_PDL=0 disables programmatic dependent launch
+  if (pdl < 0) {
+    const char* e = getenv("GPVB200_PDL");
+    pdl = e ? atoi(e) : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, F>, ma, mb, kp);
+  if (e != cudaSuccess) {
+    set_last_error("umma_gemm_kernel launch failed: %s", cudaGetErrorString(e));
+    return GPV_ERR_CUDA;
+  }
   return check_launch("umma_gemm_kernel");
 }
 

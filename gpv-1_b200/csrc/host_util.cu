@@ -1,5 +1,6 @@
 // Error plumbing and device checks shared by every C-ABI entry point.
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/gpvb200.h"
@@ -25,6 +26,15 @@ int check_launch(const char* what) {
     return GPV_ERR_CUDA;
   }
   return GPV_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPVB200_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
 }
 
 int ensure_arch() {

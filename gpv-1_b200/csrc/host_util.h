@@ -19,6 +19,26 @@ void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError -> error code
 int ensure_arch();                   // GPV_OK only on sm_100
 
+// Kernel launch with programmatic dependent launch allowed (GPVB200_PDL=0 turns it off): the kernel may start while the
+// previous kernel of the stream drains; every kernel launched this way begins with pdl_sync() (common.cuh), so global
+// memory is only touched once the predecessor has completed and flushed.  Inside a stream capture this becomes a
+// programmatic edge of the CUDA graph.
+bool pdl_enabled();
+template <typename K, typename... A>
+inline void launch_k(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);   // errors surface through check_launch() (cudaGetLastError)
+}
+
 #define GPV_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

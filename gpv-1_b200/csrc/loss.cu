@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict
                                                          const int64_t* __restrict__ targets, const float* __restrict__ w,
                                                          float* __restrict__ loss_sum, float* __restrict__ row_loss,
                                                          bf16* __restrict__ dlogits, long long ldd, int V) {
+  pdl_sync();
   __shared__ float red[8];
   __shared__ float bcast;
   const long long row = blockIdx.x;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(128) set_criterion_kernel(const float* __restr
                                                             float wt_bbox, float wt_giou, float* __restrict__ out,
                                                             float* __restrict__ dlogits, bf16* __restrict__ dbox_pre,
                                                             long long lddb) {
+  pdl_sync();
   __shared__ int match_t[1024];
   __shared__ float red[3][4];
   __shared__ float s_norm[2];
@@ -234,7 +236,7 @@ extern "C" int gpvb200_ce_fwd_bwd(const float* logits, int64_t ldl, const int64_
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(logits && targets && row_weight && loss_sum && rows >= 0 && V > 0, "ce: bad arguments");
   if (rows == 0) return GPV_OK;
-  ce_fwd_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ldl, targets, row_weight, loss_sum, row_loss, (bf16*)dlogits,
+  launch_k(ce_fwd_bwd_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, logits, ldl, targets, row_weight, loss_sum, row_loss, (bf16*)dlogits,
                                                             ldd, V);
   return check_launch("ce_fwd_bwd_kernel");
 }
@@ -251,7 +253,7 @@ extern "C" int gpvb200_set_criterion(const float* logits, int64_t ldl, const flo
               "set_criterion: bad arguments");
   GPV_REQUIRE(Kmax == 0 || (idx_q && idx_t && tgt_boxes), "set_criterion: matches without indices");
   if (B == 0) return GPV_OK;
-  set_criterion_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(logits, ldl, boxes, ldb, tgt_boxes, tgt_offsets, idx_q, idx_t, Kmax,
+  launch_k(set_criterion_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, logits, ldl, boxes, ldb, tgt_boxes, tgt_offsets, idx_q, idx_t, Kmax,
                                                             loc_valid, Q, eos_coef, weight_sum > 0.f ? 1.0f / weight_sum : -1.0f,
                                                             weight_sum > 0.f ? 1.0f / num_boxes : -1.0f, wt_ce,
                                                             wt_bbox, wt_giou, out3, dlogits, (bf16*)dbox_pre, lddb);

@@ -18,6 +18,7 @@ __global__ void matcher_cost_kernel(const float* __restrict__ logits, const floa
                                     const float* __restrict__ tboxes, const int64_t* __restrict__ tlabels,
                                     const int32_t* __restrict__ toff, int Q, int C, int Tmax, long long ldl, long long ldb,
                                     float w_class, float w_bbox, float w_giou, float* __restrict__ cost) {
+  pdl_sync();
   const int b = blockIdx.x;
   const int t0 = toff[b], T = toff[b + 1] - t0;
   for (int idx = threadIdx.x; idx < Q * T; idx += blockDim.x) {
@@ -73,6 +74,7 @@ __global__ void matcher_cost_kernel(const float* __restrict__ logits, const floa
 __global__ void __launch_bounds__(32) lsap_kernel(const float* __restrict__ cost, const int32_t* __restrict__ toff,
                                                   int Q, int Tmax, int Kmax, int64_t* __restrict__ out_q,
                                                   int64_t* __restrict__ out_t) {
+  pdl_sync();
   extern __shared__ double smem_d[];
   const int b = blockIdx.x, lane = threadIdx.x;
   const int T = toff[b + 1] - toff[b];
@@ -228,7 +230,7 @@ extern "C" int gpvb200_matcher_cost(const float* logits, int64_t ldl, const floa
   if (B == 0 || Tmax == 0) return GPV_OK;
   GPV_REQUIRE(logits && boxes && tgt_boxes && tgt_labels && tgt_offsets && cost, "matcher_cost: null pointer");
   GPV_REQUIRE(ldl >= C && ldb >= 4 && ldb % 4 == 0 && ((uintptr_t)boxes & 15) == 0, "matcher_cost: bad row strides");
-  matcher_cost_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, boxes, tgt_boxes, tgt_labels, tgt_offsets, Q, C, Tmax, ldl, ldb,
+  launch_k(matcher_cost_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, logits, boxes, tgt_boxes, tgt_labels, tgt_offsets, Q, C, Tmax, ldl, ldb,
                                                            w_class, w_bbox, w_giou, cost);
   return check_launch("matcher_cost_kernel");
 }
@@ -251,6 +253,6 @@ extern "C" int gpvb200_lsap(const float* cost, const int32_t* tgt_offsets, int32
       return GPV_ERR_CUDA;
     }
   }
-  lsap_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(cost, tgt_offsets, Q, Tmax, Kmax, out_q, out_t);
+  launch_k(lsap_kernel, dim3(B), dim3(32), smem, (cudaStream_t)stream, cost, tgt_offsets, Q, Tmax, Kmax, out_q, out_t);
   return check_launch("lsap_kernel");
 }

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float eps, bf16* __restrict__ y, long long ldy,
                                                             float* __restrict__ stats, int M, int D) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = D >> 3;
   for (long long row = (long long)blockIdx.x * 8 + warp; row < M; row += (long long)gridDim.x * 8) {
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
                                                             bf16* __restrict__ dx, long long lddx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int M, int D) {
+  pdl_sync();
   extern __shared__ float red[];  // [2][D] when affine
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = D >> 3;
@@ -176,9 +178,9 @@ extern "C" int gpvb200_layernorm_fwd(const void* x, int64_t ldx, const float* ga
   const int grid = (M + 7) / 8 < 148 * 8 ? (M + 7) / 8 : 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (D <= 768)
-    layernorm_fwd_kernel<3><<<grid, 256, 0, st>>>((const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D);
+    launch_k(layernorm_fwd_kernel<3>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D);
   else
-    layernorm_fwd_kernel<9><<<grid, 256, 0, st>>>((const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D);
+    launch_k(layernorm_fwd_kernel<9>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D);
   return check_launch("layernorm_fwd_kernel");
 }
 
@@ -196,13 +198,13 @@ extern "C" int gpvb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = gamma ? (size_t)2 * D * sizeof(float) : 0;
   if (gamma != nullptr)
-    layernorm_bwd_kernel<3, true><<<grid, 256, smem, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
+    launch_k(layernorm_bwd_kernel<3, true>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
                                                            lddx, dgamma, dbeta, M, D);
   else if (D <= 768)
-    layernorm_bwd_kernel<3, false><<<grid, 256, smem, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
+    launch_k(layernorm_bwd_kernel<3, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
                                                             lddx, dgamma, dbeta, M, D);
   else
-    layernorm_bwd_kernel<9, false><<<grid, 256, smem, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
+    launch_k(layernorm_bwd_kernel<9, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
                                                             lddx, dgamma, dbeta, M, D);
   return check_launch("layernorm_bwd_kernel");
 }

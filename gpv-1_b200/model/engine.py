@@ -48,6 +48,22 @@ def sine_position_table(H, W, device, num_pos_feats=128, temperature=10000.0):
     return torch.cat((py, px), dim=2).reshape(H * W, 2 * num_pos_feats)
 
 
+def sine_position_masked(mask, num_pos_feats=128, temperature=10000.0):
+    """position_encoding.py:28-48 for a padded batch: mask [B,H,W] bool (True = padding) -> [B*H*W, 2*num_pos_feats] fp32.
+    Tiny torch ops (cumsum over a 15x20 map per image); only used when a batch mixes image sizes."""
+    nm = ~mask
+    y = nm.cumsum(1, dtype=F32)
+    x = nm.cumsum(2, dtype=F32)
+    y = y / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
+    x = x / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
+    i = torch.arange(num_pos_feats, dtype=F32, device=mask.device)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / num_pos_feats)
+    px, py = x[..., None] / dim_t, y[..., None] / dim_t
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((py, px), dim=3).reshape(-1, 2 * num_pos_feats)
+
+
 class Engine:
     def __init__(self, tensors, specs, cfg, device):
         """tensors: name -> fp32 CUDA tensor for every state_dict entry (nn.Parameters and buffers of the module that
@@ -402,7 +418,7 @@ class Engine:
                 self._done({4: 4, 3: 5, 2: 6}[li])
 
     # ================================================================================================ attention blocks
-    def _self_attn_fwd(self, p, x, pos, P_rows, B, S, H, *, causal=False, eps=1e-5, norm="norm1", attn="self_attn"):
+    def _self_attn_fwd(self, p, x, pos, P_rows, B, S, H, *, causal=False, eps=1e-5, norm="norm1", attn="self_attn", kmask=None):
         """y = LN(x + out_proj(MHA(q = k = x + pos, v = x))).  x [B*S, D]; pos [P_rows, D] bf16 or None."""
         W, Pm = self.W, self.P
         D = x.shape[1]
@@ -417,12 +433,12 @@ class Engine:
             k.linear(x, wi, bi_, out=qkv)
         dh = D // H
         o, lse = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5,
-                                 causal=causal)
+                                 causal=causal, key_mask=kmask)
         pre = k.linear(o, W[f"{p}.{attn}.out_proj.weight"], Pm[f"{p}.{attn}.out_proj.bias"], residual=x)
         y, st = k.layernorm_fwd(pre, Pm[f"{p}.{norm}.weight"], Pm[f"{p}.{norm}.bias"], eps)
         return y, (x, qk_in, qkv, o, lse, pre, st)
 
-    def _self_attn_bwd(self, p, dy, sv, pos_grad, B, S, H, *, causal=False, norm="norm1", attn="self_attn", has_pos=True):
+    def _self_attn_bwd(self, p, dy, sv, pos_grad, B, S, H, *, causal=False, norm="norm1", attn="self_attn", has_pos=True, kmask=None):
         """Returns dx.  pos_grad: fp32 [S, D] accumulator for a learned position (query_embed) or None."""
         W, Pm, G = self.W, self.P, self.G
         x, qk_in, qkv, o, lse, pre, st = sv
@@ -432,7 +448,7 @@ class Engine:
         do = self._lin_bwd(f"{p}.{attn}.out_proj", o, dpre)
         dqkv = torch.empty_like(qkv)
         k.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
-                        B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5, causal=causal)
+                        B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5, causal=causal, key_mask=kmask)
         wi = W[f"{p}.{attn}.in_proj_weight"]
         gw, gb = G[f"{p}.{attn}.in_proj_weight"], G[f"{p}.{attn}.in_proj_bias"]
         with self._aside(dqkv):
@@ -465,7 +481,7 @@ class Engine:
             k.linear(vmem, wi[2 * D:], bi_[2 * D:], out=kv[:, D:])
         return kv
 
-    def _cross_attn_fwd(self, p, x, qpos, kmem, vmem, B, Sq, Sk, H, *, eps=1e-5, norm="norm2", kv=None):
+    def _cross_attn_fwd(self, p, x, qpos, kmem, vmem, B, Sq, Sk, H, *, eps=1e-5, norm="norm2", kv=None, kmask=None):
         """y = LN(x + out_proj(MHA(q = x + qpos, k = kmem, v = vmem)))  (kmem already carries its position)."""
         W, Pm = self.W, self.P
         D = x.shape[1]
@@ -475,12 +491,12 @@ class Engine:
         if kv is None:
             kv = self._cross_kv(p, kmem, vmem)
         dh = D // H
-        o, lse = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=dh ** -0.5)
+        o, lse = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=dh ** -0.5, key_mask=kmask)
         pre = k.linear(o, W[f"{p}.multihead_attn.out_proj.weight"], Pm[f"{p}.multihead_attn.out_proj.bias"], residual=x)
         y, st = k.layernorm_fwd(pre, Pm[f"{p}.{norm}.weight"], Pm[f"{p}.{norm}.bias"], eps)
         return y, (x, q_in, q, kv, o, lse, pre, st)
 
-    def _cross_attn_bwd(self, p, dy, sv, kmem, vmem, dmem, pos_grad, B, Sq, Sk, H, *, norm="norm2"):
+    def _cross_attn_bwd(self, p, dy, sv, kmem, vmem, dmem, pos_grad, B, Sq, Sk, H, *, norm="norm2", kmask=None):
         """Returns (dx, dmem) with dmem = dmem_in + d(kmem) + d(vmem) (chained through the GEMM residual input)."""
         W, Pm, G = self.W, self.P, self.G
         x, q_in, q, kv, o, lse, pre, st = sv
@@ -492,7 +508,7 @@ class Engine:
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
         k.attention_bwd(q, kv[:, :D], kv[:, D:], o, do, lse, dq, dkv[:, :D], dkv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh,
-                        scale=dh ** -0.5)
+                        scale=dh ** -0.5, key_mask=kmask)
         wi, gw, gb = W[a + ".in_proj_weight"], G[a + ".in_proj_weight"], G[a + ".in_proj_bias"]
         with self._aside(dq, dkv):
             k.colsum(dq, gb[:D])
@@ -612,8 +628,9 @@ class Engine:
 
     # ================================================================================================ trunk forward
     @torch.no_grad()
-    def encode(self, images, qids, save):
-        """gpv.py:137-175: everything up to `memory`.  Returns a dict of the tensors later stages need."""
+    def encode(self, images, qids, save, mask=None):
+        """gpv.py:137-175: everything up to `memory`.  Returns a dict of the tensors later stages need.
+        mask: [B,H,W] bool padding mask of a mixed-size batch (utils/detr_misc.py:282-299) or None."""
         self.refresh()
         W, Pm = self.W, self.P
         B = images.shape[0]
@@ -627,12 +644,21 @@ class Engine:
         S = Hf * Wf
         s.update(acts=acts, c5=c5, S=S, Hf=Hf, Wf=Wf)
         c5f = c5.view(B * S, C5)
-        pos = self._pos(Hf, Wf)
+        kmask = None
+        if mask is None:
+            pos, P_rows = self._pos(Hf, Wf), S
+        else:
+            # backbone.py:76-78 (nearest down-sampling of the mask), position_encoding.py:28-48, key_padding_mask of the
+            # encoder self-attention and of the decoder's cross-attention (transformer.py:50-56)
+            mf = torch.nn.functional.interpolate(mask[None].float(), size=(Hf, Wf)).to(torch.bool)[0]
+            pos, P_rows = k.cast_bf16(sine_position_masked(mf)), B * S
+            kmask = mf.reshape(B, S).to(torch.uint8).contiguous()
+        s["kmask"] = kmask
         x = k.linear(c5f, W["detr.input_proj.weight"], Pm["detr.input_proj.bias"])
         enc = []
         for i in range(self.n_enc):
             p = f"detr.transformer.encoder.layers.{i}"
-            x, sa = self._self_attn_fwd(p, x, pos, S, B, S, self.h_detr)
+            x, sa = self._self_attn_fwd(p, x, pos, P_rows, B, S, self.h_detr, kmask=kmask)
             x, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm2", x, 1e-5)
             enc.append((sa, sf))
         mem = x
@@ -647,7 +673,7 @@ class Engine:
             t, sa = self._self_attn_fwd(p, t, qe, Q, B, Q, self.h_detr)
             if i == 0:
                 self._join(1)
-            t, sc = self._cross_attn_fwd(p, t, qe, mem_pos, mem, B, Q, S, self.h_detr, kv=kvs[i])
+            t, sc = self._cross_attn_fwd(p, t, qe, mem_pos, mem, B, Q, S, self.h_detr, kv=kvs[i], kmask=kmask)
             t, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm3", t, 1e-5)
             dec.append((sa, sc, sf))
         # heads (detr_roi_head.py:81-92).  detr_hs = [LN(roi) | hs] is written in place, no cat.
@@ -776,10 +802,10 @@ class Engine:
 
     # ================================================================================================ training step
     @torch.no_grad()
-    def forward_train(self, images, qids, ans_ids, tgt):
+    def forward_train(self, images, qids, ans_ids, tgt, mask=None):
         """images [B,3,H,W] fp32, qids [B,Tl] int64, ans_ids [B,S] int64 (device).  tgt: HostTargets (see gpv.py).
         Returns (total_loss fp32 [1] on device, outputs dict)."""
-        s = self.encode(images, qids, save=True)
+        s = self.encode(images, qids, save=True, mask=mask)
         B, Q, D = s["B"], self.Q, self.D
         M = B * Q
         S = ans_ids.shape[1]
@@ -876,7 +902,7 @@ class Engine:
             p = f"detr.transformer.decoder.layers.{i}"
             sa, sc, sf = s["dec"][i]
             dt = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm3", dt, sf)
-            dt, dmem = self._cross_attn_bwd(p, dt, sc, s["mem_pos"], s["mem"], dmem, gq, B, Q, S, self.h_detr)
+            dt, dmem = self._cross_attn_bwd(p, dt, sc, s["mem_pos"], s["mem"], dmem, gq, B, Q, S, self.h_detr, kmask=s["kmask"])
             dt = self._self_attn_bwd(p, dt, sa, gq, B, Q, self.h_detr)
             self._join()
         self._done(2)
@@ -885,7 +911,7 @@ class Engine:
             p = f"detr.transformer.encoder.layers.{i}"
             sa, sf = s["enc"][i]
             dx = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm2", dx, sf)
-            dx = self._self_attn_bwd(p, dx, sa, None, B, S, self.h_detr)
+            dx = self._self_attn_bwd(p, dx, sa, None, B, S, self.h_detr, kmask=s["kmask"])
             self._join()
         # ---- input_proj: dC5 = (dx Wip + dC5_roi) * relu'(c5)  -> masked gradient of the last bottleneck
         c5f = s["c5"].view(B * S, C5)

@@ -254,7 +254,9 @@ class GPV(nn.Module):
         """Record the training step for this batch shape into CUDA graphs (model/graph.py).  Later calls of
         forward(images, queries, answer_token_ids, targets) with the same shapes replay them."""
         from .graph import CapturedStep
-        images, qids = self._images(images), self._queries(queries)
+        (images, mask), qids = self._images(images), self._queries(queries)
+        if mask is not None:
+            raise NotImplementedError("capture_step needs an unpadded batch (one image size): the padding mask is per batch")
         ans = answer_token_ids.to(device=images.device, dtype=torch.int64)
         self._captured = CapturedStep(self, images, qids, ans, targets, boxes_per_image_cap)
         return self._captured
@@ -286,22 +288,34 @@ class GPV(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ inputs
     def _images(self, images):
+        """-> (tensor [B,3,H,W] fp32 or [B,H,W,3] uint8 on the device, padding mask [B,H,W] bool or None).
+        Accepts what DETR.forward accepts (detr_roi_head.py:58-61): a NestedTensor, a list of [3,H,W] images (padded to
+        the batch maximum with zeros, mask True on padding: utils/detr_misc.py:282-299) or a batched tensor."""
         dev = self.vision_token.device
+        mask = None
         if hasattr(images, "tensors") and hasattr(images, "mask"):
             if images.mask is not None and bool(images.mask.any()):
-                raise NotImplementedError("padded (mixed-size) image batches are not built yet: resize to one size as the "
-                                          "reference data loader does (coco_generic_dataset.py:61)")
+                mask = images.mask.to(device=dev, dtype=torch.bool, non_blocking=True)
             images = images.tensors
         if isinstance(images, (list, tuple)):
             if len({tuple(i.shape) for i in images}) != 1:
-                raise NotImplementedError("padded (mixed-size) image batches are not built yet")
-            images = torch.stack(list(images))
+                if images[0].dtype == torch.uint8:
+                    raise NotImplementedError("mixed-size uint8 batches: pad on the loader side")
+                H, W = max(i.shape[1] for i in images), max(i.shape[2] for i in images)
+                batch = torch.zeros((len(images), 3, H, W), dtype=torch.float32)
+                m = torch.ones((len(images), H, W), dtype=torch.bool)
+                for b, im in enumerate(images):
+                    batch[b, :, :im.shape[1], :im.shape[2]].copy_(im)
+                    m[b, :im.shape[1], :im.shape[2]] = False
+                images, mask = batch, m.to(dev, non_blocking=True)
+            else:
+                images = torch.stack(list(images))
         if images.dtype == torch.uint8:
             # raw loader format [B,H,W,3]: ToTensor + Normalize (coco_generic_dataset.py:31-32) are folded into the stem's read
             if images.dim() != 4 or images.shape[-1] != 3:
                 raise ValueError("uint8 images must be NHWC [B,H,W,3]")
-            return images.to(device=dev, non_blocking=True).contiguous()
-        return images.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            return images.to(device=dev, non_blocking=True).contiguous(), mask
+        return images.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(), mask
 
     def _queries(self, queries):
         dev = self.vision_token.device
@@ -318,27 +332,27 @@ class GPV(nn.Module):
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, images, queries, answer_token_ids, targets=None, vocab_mask=None):
         eng = self.engine
-        images, qids = self._images(images), self._queries(queries)
+        (images, mask), qids = self._images(images), self._queries(queries)
         B, Q = images.shape[0], self.cfg.detr.num_queries
         if answer_token_ids is not None and targets is not None:
             ans = answer_token_ids.to(device=images.device, dtype=torch.int64, non_blocking=True)
             S = ans.shape[1]
             cap = self._captured
-            if cap is not None and torch.is_grad_enabled() and cap.matches(images, qids, ans):
+            if cap is not None and mask is None and torch.is_grad_enabled() and cap.matches(images, qids, ans):
                 loss = cap.forward(images, qids, ans, targets)
                 return None if loss is None else _Step.apply(self._anchor(), loss, self)
             tgt = HostTargets(targets, B, S, Q, eng.loss_wts, eng.eos_coef, images.device)
             if tgt.n_text == 0 and tgt.n_loc == 0:
                 return None
-            loss, _ = eng.forward_train(images, qids, ans, tgt)
+            loss, _ = eng.forward_train(images, qids, ans, tgt, mask=mask)
             if torch.is_grad_enabled():
                 return _Step.apply(self._anchor(), loss, self)
             eng.saved = None
             return loss.view(())
-        if answer_token_ids is None and targets is None and self.inference_graphs:
+        if answer_token_ids is None and targets is None and self.inference_graphs and mask is None:
             return self._graphed("greedy", images, qids, vocab_mask, None)
         with torch.no_grad():
-            s = eng.encode(images, qids, save=False)
+            s = eng.encode(images, qids, save=False, mask=mask)
             outputs = self._outputs(s)
             if answer_token_ids is None:
                 outputs["answer_logits"] = self._greedy(s, vocab_mask)
@@ -422,13 +436,13 @@ class GPV(nn.Module):
 
     def forward_beam_search(self, images, queries, beam_size=1):
         eng = self.engine
-        images, qids = self._images(images), self._queries(queries)
+        (images, mask), qids = self._images(images), self._queries(queries)
         with torch.no_grad():
-            if self.inference_graphs:
+            if self.inference_graphs and mask is None:
                 outputs = self._graphed("beam", images, qids, None, beam_size)
                 seqs, logp = outputs.pop("beam_token_ids"), outputs.pop("beam_scores")
             else:
-                s = eng.encode(images, qids, save=False)
+                s = eng.encode(images, qids, save=False, mask=mask)
                 outputs = self._outputs(s)
                 seqs, logp = self._beam(s, beam_size)
         seqs_h, p_h = seqs.cpu().tolist(), logp.exp().cpu().tolist()

@@ -71,12 +71,23 @@ def close(a, b, rtol, atol, what):
     return err
 
 
-def train_case(model, P, name, B, H, W, Tl, S, seed, tasks):
+def crop_list(images, sizes):
+    """Mixed-size batch: image b is the top-left sizes[b] = (h, w) crop of the seeded full-size image."""
+    return [images[b, :, :h, :w].clone() for b, (h, w) in enumerate(sizes)]
+
+
+def train_case(model, P, name, B, H, W, Tl, S, seed, tasks, sizes=None):
     images, qids, ans, targets = make_inputs(B, H, W, Tl, S, seed, tasks)
     model.zero_grad()
     t0 = time.time()
     # outputs (teacher forced), then the loss + grads through the reference's own criterion
-    out = model(images, qids, ans, None)
+    mask = None
+    if sizes is not None:                      # the reference pads the list itself (detr_roi_head.py:59-60)
+        ref_in = crop_list(images, sizes)
+        images, mask = TO.nested(ref_in)
+    else:
+        ref_in = images
+    out = model(ref_in, qids, ans, None)
     loss, ld = model.criterion(out, targets)
     loss.backward()
     t_ref = time.time() - t0
@@ -88,7 +99,7 @@ def train_case(model, P, name, B, H, W, Tl, S, seed, tasks):
 
     trainable = {k for k, p in model.named_parameters() if p.requires_grad}
     Pg = {k: (v.clone().requires_grad_(True) if k in trainable else v.clone()) for k, v in P.items()}
-    oout = TO.gpv_forward(Pg, images, qids, ans, None)
+    oout = TO.gpv_forward(Pg, images, qids, ans, None, mask=mask)
     oloss, old = TO.gpv_criterion(oout, targets)
     oloss.backward()
     errs = {"loss": abs(oloss.item() - loss.item())}
@@ -105,7 +116,7 @@ def train_case(model, P, name, B, H, W, Tl, S, seed, tasks):
         if v.requires_grad and v.grad is not None and v.grad.abs().max() > 0:
             assert k in grads, f"oracle has a grad the reference lacks: {k}"
     fix = {
-        "meta": {"B": B, "H": H, "W": W, "Tl": Tl, "S": S, "seed": seed, "tasks": tasks, "V": V, "weights_seed": 0,
+        "meta": {"B": B, "H": H, "W": W, "Tl": Tl, "S": S, "seed": seed, "tasks": tasks, "V": V, "weights_seed": 0, "sizes": sizes,
                  "ref_seconds": t_ref, "oracle_max_err": errs},
         "loss": loss.detach(), "losses": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in ld.items() if v is not None and k != "class_error"},
         "indices": [(q.clone(), t.clone()) for q, t in ind],
@@ -170,7 +181,7 @@ def main():
     P = TO.make_state(specs, seed=0)
     model.load_state_dict(P, strict=True)
     model.eval()
-    which = sys.argv[1:] or ["train_small", "train_mixed", "greedy", "beam", "train_full"]
+    which = sys.argv[1:] or ["train_small", "train_mixed", "greedy", "beam", "train_full", "train_padded"]
     if "train_small" in which:
         train_case(model, P, "train_small", B=2, H=224, W=288, Tl=6, S=7, seed=11, tasks=["CocoCaptioning"])
     if "train_mixed" in which:
@@ -180,6 +191,9 @@ def main():
         greedy_case(model, P, "greedy", B=2, H=224, W=288, Tl=6, seed=13, max_text_len=8)
     if "beam" in which:
         beam_case(model, P, "beam", B=2, H=224, W=288, Tl=6, seed=14, K=3, max_text_len=5)
+    if "train_padded" in which:
+        train_case(model, P, "train_padded", B=3, H=192, W=256, Tl=7, S=5, seed=16, tasks=["CocoCaptioning", "CocoVqa", "CocoDetection"],
+                   sizes=[(192, 224), (160, 256), (128, 200)])
     if "train_full" in which:
         train_case(model, P, "train_full", B=2, H=480, W=640, Tl=20, S=20, seed=15, tasks=["CocoCaptioning"])
 

@@ -90,6 +90,18 @@ def resnet50_c5(P, x, prefix="detr.backbone.0.body"):
     return x
 
 
+def nested(image_list):
+    """utils/detr_misc.py:282-299 nested_tensor_from_tensor_list: zero-pad [3,H,W] images to the batch maximum;
+    mask [B,H,W] is True on padding."""
+    H, W = max(i.shape[1] for i in image_list), max(i.shape[2] for i in image_list)
+    t = torch.zeros((len(image_list), image_list[0].shape[0], H, W), dtype=image_list[0].dtype)
+    m = torch.ones((len(image_list), H, W), dtype=torch.bool)
+    for img, pad, mm in zip(image_list, t, m):
+        pad[:, :img.shape[1], :img.shape[2]].copy_(img)
+        mm[:img.shape[1], :img.shape[2]] = False
+    return t, m
+
+
 def sine_position(mask, num_pos_feats=128, temperature=10000.0):
     """mask [B,H,W] bool (True = padding) -> [B,2*num_pos_feats,H,W]."""
     nm = ~mask

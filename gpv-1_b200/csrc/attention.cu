@@ -25,6 +25,7 @@ struct AttnParams {
   long long bsq, bsk, bsv, bso;   // batch strides (elements) of q, k, v, o in the forward; S*ld unless a KV cache is read in place
   int B, H, Sq, Sk, causal;
   float scale;
+  DropArgs drop;   // dropout on the attention probabilities (train mode); drop.seed == nullptr: none
 };
 
 GPV_DEVINL void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float sl2 = p.scale * 1.4426950408889634f;
+  const uint32_t dkey = p.drop.seed ? drop_key(*p.drop.seed, p.drop.site) : 0u;
   for (int r0 = warp * 16; r0 < Sqp; r0 += NT / 2) {
     uint32_t qa[DH / 16][4];
     load_a_frags<DH>(Qs, LD, r0, g, t, qa);
@@ -140,6 +142,16 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
       }
       l0 = l0 * c0 + rs0;
       l1 = l1 * c1 + rs1;
+      if (p.drop.seed != nullptr) {   // O = dropout(softmax(S)) V: the normaliser keeps every key, the PV product the kept ones
+        const uint32_t hs = (uint32_t)((Sk + 1) >> 1);
+        const uint32_t pr0 = ((uint32_t)bh * (uint32_t)Sq + (uint32_t)row0) * hs, pr1 = pr0 + 8u * hs;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint32_t cp = (uint32_t)((kb + nt * 8) >> 1) + t;
+          drop_pair(s[nt][0], s[nt][1], dkey, pr0 + cp, p.drop.thresh16, p.drop.scale);
+          drop_pair(s[nt][2], s[nt][3], dkey, pr1 + cp, p.drop.thresh16, p.drop.scale);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < DH / 8; ++i) {
         o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1;
@@ -213,6 +225,9 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float sl2 = p.scale * 1.4426950408889634f;
+  const bool drop = p.drop.seed != nullptr;
+  const uint32_t dkey = drop ? drop_key(*p.drop.seed, p.drop.site) : 0u;
+  const uint32_t hs = (uint32_t)((Sk + 1) >> 1);   // mask pairs per (b, h, q) row
 
   // ---------------------------------------------------------------- pass 1: D and dQ
   for (int r0 = warp * 16; r0 < Sqp; r0 += NT / 2) {
@@ -275,8 +290,19 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
           const bool dead = msk[col] != 0;
           const float p0 = (dead || (p.causal && col > row0)) ? 0.f : exp2f(s[nt][e] * sl2 - ls0);
           const float p1 = (dead || (p.causal && col > row1)) ? 0.f : exp2f(s[nt][2 + e] * sl2 - ls1);
-          s[nt][e] = p0 * (dp[nt][e] - d0) * p.scale;
-          s[nt][2 + e] = p1 * (dp[nt][2 + e] - d1) * p.scale;
+          s[nt][e] = p0;
+          s[nt][2 + e] = p1;
+        }
+        if (drop) {   // dP reaches the probabilities through the forward's mask: dP <- dP (*) mask / (1 - p)
+          const uint32_t cp = (uint32_t)((kb + nt * 8) >> 1) + t;
+          const uint32_t pr0 = ((uint32_t)bh * (uint32_t)Sq + (uint32_t)row0) * hs;
+          drop_pair(dp[nt][0], dp[nt][1], dkey, pr0 + cp, p.drop.thresh16, p.drop.scale);
+          drop_pair(dp[nt][2], dp[nt][3], dkey, pr0 + 8u * hs + cp, p.drop.thresh16, p.drop.scale);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          s[nt][e] = s[nt][e] * (dp[nt][e] - d0) * p.scale;
+          s[nt][2 + e] = s[nt][2 + e] * (dp[nt][2 + e] - d1) * p.scale;
         }
       }
 #pragma unroll
@@ -343,10 +369,17 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
           const float ls = lse_s[qc], dd = D_s[qc];
           const float p0 = (dead0 || (p.causal && key0 > qc)) ? 0.f : exp2f(s[nt][e] * sl2 - ls);
           const float p1 = (dead1 || (p.causal && key1 > qc)) ? 0.f : exp2f(s[nt][2 + e] * sl2 - ls);
-          pt[nt][e] = p0;
-          pt[nt][2 + e] = p1;
-          s[nt][e] = p0 * (dp[nt][e] - dd) * p.scale;
-          s[nt][2 + e] = p1 * (dp[nt][2 + e] - dd) * p.scale;
+          float m0 = 1.0f, m1 = 1.0f;
+          if (drop) {   // element (query qc, key): one half of the pair's 32 bits
+            const uint32_t pr = ((uint32_t)bh * (uint32_t)Sq + (uint32_t)qc) * hs;
+            const uint32_t b0 = drop_bits(dkey, pr + (uint32_t)(key0 >> 1)), b1 = drop_bits(dkey, pr + (uint32_t)(key1 >> 1));
+            m0 = (((key0 & 1) ? (b0 >> 16) : (b0 & 0xFFFFu)) >= p.drop.thresh16) ? p.drop.scale : 0.0f;
+            m1 = (((key1 & 1) ? (b1 >> 16) : (b1 & 0xFFFFu)) >= p.drop.thresh16) ? p.drop.scale : 0.0f;
+          }
+          pt[nt][e] = p0 * m0;                                   // dV = dropout(P)^T dO
+          pt[nt][2 + e] = p1 * m1;
+          s[nt][e] = p0 * (dp[nt][e] * m0 - dd) * p.scale;
+          s[nt][2 + e] = p1 * (dp[nt][2 + e] * m1 - dd) * p.scale;
         }
       }
 #pragma unroll
@@ -435,10 +468,19 @@ static int dispatch(const AttnParams& p, int dh, bool bwd, cudaStream_t st) {
 
 using namespace gpv;
 
-extern "C" int gpvb200_attention_fwd_bs(const void* q, const void* k, const void* v, void* o, float* lse,
-                                        const uint8_t* key_mask, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                                        int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, int32_t B, int32_t H, int32_t Sq,
-                                        int32_t Sk, int32_t dh, int32_t causal, float scale, void* stream) {
+static DropArgs attn_drop(const void* seed, uint32_t site, float p) {
+  DropArgs d;
+  d.seed = (p > 0.f) ? (const unsigned long long*)seed : nullptr;
+  d.site = site;
+  d.thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
+  d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, const uint8_t* key_mask, int64_t ldq,
+                         int64_t ldk, int64_t ldv, int64_t ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, int32_t B,
+                         int32_t H, int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale, const DropArgs& drop,
+                         void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(q && k && v && o, "attention_fwd: null pointer");
@@ -454,7 +496,28 @@ extern "C" int gpvb200_attention_fwd_bs(const void* q, const void* k, const void
   p.bsv = bsv > 0 ? bsv : (long long)Sk * ldv;
   p.bso = bso > 0 ? bso : (long long)Sq * ldo;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
+  p.drop = drop;
   return dispatch(p, dh, false, (cudaStream_t)stream);
+}
+
+extern "C" int gpvb200_attention_fwd_bs(const void* q, const void* k, const void* v, void* o, float* lse,
+                                        const uint8_t* key_mask, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                        int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, int32_t B, int32_t H, int32_t Sq,
+                                        int32_t Sk, int32_t dh, int32_t causal, float scale, void* stream) {
+  return attn_fwd_impl(q, k, v, o, lse, key_mask, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, B, H, Sq, Sk, dh, causal, scale,
+                       attn_drop(nullptr, 0, 0.f), stream);
+}
+
+extern "C" int gpvb200_attention_fwd_drop(const void* q, const void* k, const void* v, void* o, float* lse,
+                                          const uint8_t* key_mask, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                          int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale,
+                                          const void* drop_seed, uint32_t drop_site, float drop_p, void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed))) {
+    set_last_error("attention_fwd_drop: bad dropout arguments");
+    return GPV_ERR_ARG;
+  }
+  return attn_fwd_impl(q, k, v, o, lse, key_mask, ldq, ldk, ldv, ldo, 0, 0, 0, 0, B, H, Sq, Sk, dh, causal, scale,
+                       attn_drop(drop_seed, drop_site, drop_p), stream);
 }
 
 extern "C" int gpvb200_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
@@ -464,11 +527,12 @@ extern "C" int gpvb200_attention_fwd(const void* q, const void* k, const void* v
   return gpvb200_attention_fwd_bs(q, k, v, o, lse, key_mask, ldq, ldk, ldv, ldo, 0, 0, 0, 0, B, H, Sq, Sk, dh, causal, scale, stream);
 }
 
-extern "C" int gpvb200_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
-                                     const float* lse, const uint8_t* key_mask, void* dq, void* dk, void* dv,
-                                     int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
-                                     int64_t lddk, int64_t lddv, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh,
-                                     int32_t causal, float scale, void* stream) {
+extern "C" int gpvb200_attention_bwd_drop(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                          const float* lse, const uint8_t* key_mask, void* dq, void* dk, void* dv,
+                                          int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
+                                          int64_t lddk, int64_t lddv, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh,
+                                          int32_t causal, float scale, const void* drop_seed, uint32_t drop_site, float drop_p,
+                                          void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv, "attention_bwd: null pointer");
@@ -480,5 +544,16 @@ extern "C" int gpvb200_attention_bwd(const void* q, const void* k, const void* v
   p.lse = const_cast<float*>(lse); p.kmask = key_mask;
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.lddo = lddo; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
+  GPV_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "attention_bwd: bad dropout arguments");
+  p.drop = attn_drop(drop_seed, drop_site, drop_p);
   return dispatch(p, dh, true, (cudaStream_t)stream);
+}
+
+extern "C" int gpvb200_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                     const float* lse, const uint8_t* key_mask, void* dq, void* dk, void* dv,
+                                     int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
+                                     int64_t lddk, int64_t lddv, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh,
+                                     int32_t causal, float scale, void* stream) {
+  return gpvb200_attention_bwd_drop(q, k, v, o, d_o, lse, key_mask, dq, dk, dv, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, B, H,
+                                    Sq, Sk, dh, causal, scale, nullptr, 0, 0.f, stream);
 }

@@ -140,6 +140,38 @@ GPV_DEVINL void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- dropout masks (train mode)
+// Counter-based, so that backward regenerates the forward's mask instead of storing it.  Element (row, col) of a
+// logical [rows, N] tensor at dropout site `site` of training step `seed`:
+//     pair = row * ceil(N / 2) + (col >> 1);  bits = drop_bits(drop_key(seed, site), pair)
+//     keep = ((col & 1) ? bits >> 16 : bits & 0xFFFF) >= thresh16,   thresh16 = round(p * 65536)
+// (two elements per 32-bit hash; p = 0.1 -> 0.100006).  Kept elements are scaled by 1 / (1 - p) like nn.Dropout.
+// The same formula serves GEMM epilogues (row = output row), LayerNorm (row = token) and attention probabilities
+// (row = (b*H + h)*Sq + q, col = key).  The reference draws its masks from torch's Philox stream; masks cannot be
+// bit-compatible across implementations, so parity runs with dropout off and dropout is tested against autograd with
+// the masks exported by gpvb200_dropout_mask (tests/test_dropout_gpu.py).
+struct DropArgs {
+  const unsigned long long* seed;   // device scalar, bumped once per training step; nullptr = no dropout
+  uint32_t site, thresh16;
+  float scale;                      // 1 / (1 - p)
+};
+GPV_DEVINL uint32_t drop_key(unsigned long long seed, uint32_t site) {
+  uint32_t x = (uint32_t)seed * 0x9E3779B1u ^ (uint32_t)(seed >> 32) ^ (site * 0x85EBCA6Bu + 0x6C62272Eu);
+  x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+  return x;
+}
+GPV_DEVINL uint32_t drop_bits(uint32_t key, uint32_t pair) {
+  uint32_t x = pair * 0x9E3779B1u + key;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+// Applies the mask to the two elements of one pair.
+GPV_DEVINL void drop_pair(float& a, float& b, uint32_t key, uint32_t pair, uint32_t thresh16, float scale) {
+  const uint32_t bits = drop_bits(key, pair);
+  a = ((bits & 0xFFFFu) >= thresh16) ? a * scale : 0.0f;
+  b = ((bits >> 16) >= thresh16) ? b * scale : 0.0f;
+}
+
 // ---------------------------------------------------------------- misc math
 GPV_DEVINL float warp_sum(float v) {
 #pragma unroll

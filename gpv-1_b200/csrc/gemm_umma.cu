@@ -33,6 +33,8 @@ struct KParams {
   int OH, OW, os, ooh, oow;
   int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal, pf_mode;
   uint32_t epi_warp_bytes, epi_aux_off, epi_slot_stride;   // per-warp epilogue slabs (coalesced path)
+  int drop_mode;  // 0 none, 1 before the residual add, 2 after the activation (DropArgs below)
+  DropArgs drop;
   int epi_full;   // 1: every slab of a work item is requested up front (one slot per chunk); 0: two-slot ring, one slab ahead
   float alpha;
   void* D;
@@ -190,9 +192,16 @@ GPV_DEVINL void epi_aux(const KParams& p, float (&v)[kChunk], const float (&a)[k
 // One 32-column slice of an accumulator row, the thread's own row addressed directly:
 // v = alpha*acc*rowscale + bias + residual; D2 = v; v = act(v); v *= mask(aux) / gelu'(aux); store.
 //   vec = false  scalar (ragged N edge, unaligned operands);  vec = true  16-byte vectors (fp32 / atomic outputs)
+// Dropout on the 32-column slice [nb, nb+32) of row `pix` (N even; see common.cuh for the mask definition).
+GPV_DEVINL void epi_dropout(const KParams& p, float (&v)[kChunk], uint32_t dkey, long long pix, int nb) {
+  const uint32_t base = (uint32_t)pix * (uint32_t)((p.N + 1) >> 1) + (uint32_t)(nb >> 1);
+#pragma unroll
+  for (int j = 0; j < kChunk / 2; ++j) drop_pair(v[2 * j], v[2 * j + 1], dkey, base + j, p.drop.thresh16, p.drop.scale);
+}
+
 template <int F>
 GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float rs, long long row_off, long long pix, int nb,
-                          int nvalid, bool vec) {
+                          int nvalid, bool vec, uint32_t dkey) {
   typedef EpiFlags<F> E;
   const long long off_d = row_off + pix * p.ldd + nb, off_r = row_off + pix * p.ldr + nb, off_a = row_off + pix * p.ldaux + nb;
   float v[kChunk];
@@ -211,6 +220,7 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
         if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
     }
   }
+  if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
   if (E::res(p)) {
     if (E::res_fp32(p)) {
       const float* rp = reinterpret_cast<const float*>(p.residual) + off_r;
@@ -239,6 +249,7 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
     }
   }
   epi_activation<F>(p, v);
+  if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
   if (E::aux(p) != GPVB200_AUX_NONE) {
     float a[kChunk];
     if (vec) {
@@ -317,7 +328,8 @@ GPV_DEVINL void store_slab(bf16* const (&dst)[4], uint32_t ok, int col, const fl
 // aux_s (cp.async), outputs leave through out_s (the slab of an input already consumed, or a slab of its own).
 template <int F>
 GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], float rs, const float4 (&b4)[kChunk / 4], int col,
-                               uint32_t res_s, uint32_t aux_s, uint32_t out_s, const CoalRows& cr, const SlabOffs& so) {
+                               uint32_t res_s, uint32_t aux_s, uint32_t out_s, const CoalRows& cr, const SlabOffs& so,
+                               uint32_t dkey, long long pix, int nb) {
   typedef EpiFlags<F> E;
   float v[kChunk];
   if (rs != 1.0f) {  // rs = alpha * rowscale; 1 for most layers
@@ -333,12 +345,14 @@ GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], 
       v[j] += b4[j / 4].x; v[j + 1] += b4[j / 4].y; v[j + 2] += b4[j / 4].z; v[j + 3] += b4[j / 4].w;
     }
   }
+  if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
   if (E::res(p)) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) unpack8(lds128(res_s + so.own[i]), v + 8 * i, true);
   }
   if (E::d2(p)) store_slab(cr.d2, cr.ok, col, v, out_s, so);
   epi_activation<F>(p, v);
+  if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
   if (E::aux(p) != GPVB200_AUX_NONE) {
     float a[kChunk];
 #pragma unroll
@@ -537,6 +551,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 4; ++i) so.own[i] = 16u * slab_slot(lane, i);
     const long long ldd = p.ldd, ldr = p.ldr, lda = p.ldaux;
+    const uint32_t dkey = p.drop_mode ? drop_key(*p.drop.seed, p.drop.site) : 0u;
     int j = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
       const Work wk = decode_work(p, w);
@@ -613,9 +628,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool full = nvalid == kChunk;
           if (coal && full) {                     // whole warp takes part (shared-memory slabs)
             const uint32_t sc = (uint32_t)(full_pf ? c : (c & 1)) * slot_stride;
-            epi_chunk_coal<F>(p, acc, rs, b4, c * kChunk, res_ring + sc, aux_ring + sc, out_ring + sc, cr, so);
+            epi_chunk_coal<F>(p, acc, rs, b4, c * kChunk, res_ring + sc, aux_ring + sc, out_ring + sc, cr, so, dkey, pix, nb);
           } else if (row_ok) {
-            epi_chunk<F>(p, acc, rs, row_off, pix, nb, nvalid, p.vec_ok && full);
+            epi_chunk<F>(p, acc, rs, row_off, pix, nb, nvalid, p.vec_ok && full, dkey);
           }
         }
       }
@@ -869,6 +884,18 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       pf = e ? atoi(e) : 0;
     }
     kp.pf_mode = pf;
+  }
+  kp.drop_mode = 0;
+  if (d->drop_mode != 0 && d->drop_p > 0.f) {
+    GPV_REQUIRE(d->drop_mode == 1 || d->drop_mode == 2, "gemm: bad drop_mode %d", d->drop_mode);
+    GPV_REQUIRE(d->drop_seed != nullptr && d->drop_p < 1.f, "gemm: dropout needs a seed and p < 1");
+    GPV_REQUIRE(d->mode != 2 && (d->mode == 1 || d->batch <= 1) && (d->N % 2 == 0) && splits_in <= 1 && !d->d_atomic,
+                "gemm: dropout needs an unbatched, unsplit problem with even N");
+    kp.drop_mode = d->drop_mode;
+    kp.drop.seed = (const unsigned long long*)d->drop_seed;
+    kp.drop.site = d->drop_site;
+    kp.drop.thresh16 = (uint32_t)(d->drop_p * 65536.0f + 0.5f);
+    kp.drop.scale = 1.0f / (1.0f - d->drop_p);
   }
   kp.coal = kp.vec_ok && !kp.d_fp32 && !kp.res_fp32 && !(d->D2 && d->aux_mode != GPVB200_AUX_NONE);
   kp.stride = d->stride > 0 ? d->stride : 1;

@@ -13,10 +13,11 @@ template <int MAXC>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, long long ldx,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float eps, bf16* __restrict__ y, long long ldy,
-                                                            float* __restrict__ stats, int M, int D) {
+                                                            float* __restrict__ stats, int M, int D, const DropArgs dr) {
   pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = D >> 3;
+  const uint32_t dkey = dr.seed ? drop_key(*dr.seed, dr.site) : 0u;   // y = dropout(LN(x)) (BERT embeddings, vilbert.py:364)
   for (long long row = (long long)blockIdx.x * 8 + warp; row < M; row += (long long)gridDim.x * 8) {
     const bf16* xr = x + row * ldx;
     float v[MAXC][8];
@@ -65,6 +66,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
           if (gamma != nullptr) t = t * __ldg(gamma + ch * 8 + j) + __ldg(beta + ch * 8 + j);
           o[j] = t;
         }
+        if (dr.seed != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            drop_pair(o[2 * j], o[2 * j + 1], dkey, (uint32_t)row * (uint32_t)(D >> 1) + ch * 4 + j, dr.thresh16, dr.scale);
+        }
         uint4 u;
         u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
         u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
@@ -80,8 +86,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
                                                             const bf16* __restrict__ x, long long ldx,
                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
                                                             bf16* __restrict__ dx, long long lddx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int M, int D) {
+                                                            float* __restrict__ dbeta, int M, int D, bf16* __restrict__ dxm,
+                                                            long long lddxm, const DropArgs dr) {
   pdl_sync();
+  // dxm (optional) = dx (*) mask / (1 - p): the gradient of the dropped-out sub-layer output in y = LN(res + dropout(f)),
+  // regenerated from the forward's (seed, site); dx itself is the gradient of the residual branch.
+  const uint32_t dkey = dxm ? drop_key(*dr.seed, dr.site) : 0u;
   extern __shared__ float red[];  // [2][D] when affine
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = D >> 3;
@@ -140,6 +150,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
         u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
         u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
         *reinterpret_cast<uint4*>(dx + row * lddx + ch * 8) = u;
+        if (dxm != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            drop_pair(o[2 * j], o[2 * j + 1], dkey, (uint32_t)row * (uint32_t)(D >> 1) + ch * 4 + j, dr.thresh16, dr.scale);
+          u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+          u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dxm + row * lddxm + ch * 8) = u;
+        }
       }
     }
   }
@@ -167,44 +185,97 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 
 using namespace gpv;
 
-extern "C" int gpvb200_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
-                                     int64_t ldy, float* stats, int32_t M, int32_t D, void* stream) {
+static DropArgs make_drop(const void* seed, uint32_t site, float p) {
+  DropArgs d;
+  d.seed = (p > 0.f) ? (const unsigned long long*)seed : nullptr;
+  d.site = site;
+  d.thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
+  d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+
+extern "C" int gpvb200_layernorm_fwd_drop(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
+                                          int64_t ldy, float* stats, int32_t M, int32_t D, const void* drop_seed,
+                                          uint32_t drop_site, float drop_p, void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(x && y && M >= 0 && D > 0, "layernorm_fwd: bad arguments");
   GPV_REQUIRE(D % 8 == 0 && D <= 2304 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm_fwd: D must be a multiple of 8, <= 2304");
   GPV_REQUIRE((gamma == nullptr) == (beta == nullptr), "layernorm_fwd: gamma and beta go together");
+  GPV_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "layernorm_fwd: bad dropout arguments");
   if (M == 0) return GPV_OK;
+  const DropArgs dr = make_drop(drop_seed, drop_site, drop_p);
   const int grid = (M + 7) / 8 < 148 * 8 ? (M + 7) / 8 : 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (D <= 768)
-    launch_k(layernorm_fwd_kernel<3>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D);
+    launch_k(layernorm_fwd_kernel<3>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
   else
-    launch_k(layernorm_fwd_kernel<9>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D);
+    launch_k(layernorm_fwd_kernel<9>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
   return check_launch("layernorm_fwd_kernel");
 }
 
-extern "C" int gpvb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* stats,
-                                     const float* gamma, void* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M,
-                                     int32_t D, void* stream) {
+extern "C" int gpvb200_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
+                                     int64_t ldy, float* stats, int32_t M, int32_t D, void* stream) {
+  return gpvb200_layernorm_fwd_drop(x, ldx, gamma, beta, eps, y, ldy, stats, M, D, nullptr, 0, 0.f, stream);
+}
+
+extern "C" int gpvb200_layernorm_bwd_drop(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* stats,
+                                          const float* gamma, void* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M,
+                                          int32_t D, void* dx_masked, int64_t lddxm, const void* drop_seed, uint32_t drop_site,
+                                          float drop_p, void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(dy && x && stats && dx && M >= 0 && D > 0, "layernorm_bwd: bad arguments");
   GPV_REQUIRE(D % 8 == 0 && D <= 2304 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "layernorm_bwd: bad D / strides");
   GPV_REQUIRE(gamma == nullptr || (dgamma && dbeta), "layernorm_bwd: affine needs dgamma/dbeta");
   GPV_REQUIRE(gamma == nullptr || D <= 768, "layernorm_bwd: affine path supports D <= 768");
+  GPV_REQUIRE(dx_masked == nullptr || (drop_seed && drop_p > 0.f && drop_p < 1.f && lddxm % 8 == 0), "layernorm_bwd: bad dropout arguments");
   if (M == 0) return GPV_OK;
+  const DropArgs dr = make_drop(drop_seed, drop_site, dx_masked ? drop_p : 0.f);
+  bf16* dxm = (bf16*)dx_masked;
   const int grid = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = gamma ? (size_t)2 * D * sizeof(float) : 0;
   if (gamma != nullptr)
-    launch_k(layernorm_bwd_kernel<3, true>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
-                                                           lddx, dgamma, dbeta, M, D);
+    launch_k(layernorm_bwd_kernel<3, true>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma,
+             (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr);
   else if (D <= 768)
-    launch_k(layernorm_bwd_kernel<3, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
-                                                            lddx, dgamma, dbeta, M, D);
+    launch_k(layernorm_bwd_kernel<3, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma,
+             (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr);
   else
-    launch_k(layernorm_bwd_kernel<9, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, (bf16*)dx,
-                                                            lddx, dgamma, dbeta, M, D);
+    launch_k(layernorm_bwd_kernel<9, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma,
+             (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr);
   return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int gpvb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* stats,
+                                     const float* gamma, void* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M,
+                                     int32_t D, void* stream) {
+  return gpvb200_layernorm_bwd_drop(dy, lddy, x, ldx, stats, gamma, dx, lddx, dgamma, dbeta, M, D, nullptr, 0, nullptr, 0, 0.f, stream);
+}
+
+// Test / debug export of the dropout mask of a logical [rows, N] tensor: out[row*N + col] = 1 (kept) or 0.
+namespace gpv {
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, long long rows, int N, const DropArgs dr) {
+  const uint32_t key = drop_key(*dr.seed, dr.site);
+  const long long total = rows * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / N;
+    const int col = (int)(i % N);
+    const uint32_t bits = drop_bits(key, (uint32_t)row * (uint32_t)((N + 1) >> 1) + (uint32_t)(col >> 1));
+    out[i] = (((col & 1) ? (bits >> 16) : (bits & 0xFFFFu)) >= dr.thresh16) ? 1 : 0;
+  }
+}
+}  // namespace gpv
+
+extern "C" int gpvb200_dropout_mask(uint8_t* out, int64_t rows, int32_t N, const void* drop_seed, uint32_t drop_site, float drop_p,
+                                    void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(out && drop_seed && rows >= 0 && N > 0 && drop_p > 0.f && drop_p < 1.f, "dropout_mask: bad arguments");
+  if (rows == 0) return GPV_OK;
+  long long blocks = (rows * N + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dropout_mask_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, rows, N, make_drop(drop_seed, drop_site, drop_p));
+  return check_launch("dropout_mask_kernel");
 }

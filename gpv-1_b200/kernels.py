@@ -14,6 +14,30 @@ AUX_NONE, AUX_RELU_MASK, AUX_GELU_GRAD = 0, 1, 2
 BF16 = torch.bfloat16
 
 
+class Drop:
+    """One dropout site of a training step: (device uint64 step counter, site id, probability).  The mask is a
+    counter-based function of these and of the element's (row, col) -- csrc/common.cuh -- so backward regenerates it."""
+    __slots__ = ("seed", "site", "p")
+
+    def __init__(self, seed, site, p):
+        self.seed, self.site, self.p = seed, int(site) & 0xFFFFFFFF, float(p)
+
+    @property
+    def scale(self):
+        return 1.0 / (1.0 - self.p)
+
+
+DROP_PRE_RESIDUAL, DROP_POST_ACT = 1, 2
+
+
+def dropout_mask(rows, N, drop):
+    """uint8 [rows, N]: 1 = kept (test / debug export of the mask every kernel regenerates)."""
+    out = torch.empty((rows, N), device=drop.seed.device, dtype=torch.uint8)
+    _C.check(_C.lib().gpvb200_dropout_mask(_C.ptr(out), ctypes.c_int64(rows), N, _C.ptr(drop.seed), ctypes.c_uint32(drop.site),
+                                           ctypes.c_float(drop.p), _C.stream_ptr()), "dropout_mask")
+    return out
+
+
 def _req(t, dtype=None):
     if t is None:
         return None
@@ -30,7 +54,7 @@ def _launch_gemm(d: _C.GemmDesc):
 
 def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, batch=1, a_bs=0, b_bs=0, d_bs=0,
          bias=None, rowscale=None, residual=None, ldr=0, aux=None, ldaux=0, aux_mode=AUX_NONE, act=ACT_NONE,
-         alpha=1.0, atomic=False, splits=1, D2=None):
+         alpha=1.0, atomic=False, splits=1, D2=None, drop=None, drop_mode=0):
     """mode-0 contraction (see include/gpvb200.h). D dtype decides bf16 / fp32 output."""
     d = _C.GemmDesc()
     d.mode = 0
@@ -47,21 +71,24 @@ def gemm(A, B, D, *, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, batch=1, a_
     d.res_fp32 = int(residual is not None and residual.dtype == torch.float32)
     d.lda, d.ldb, d.ldd, d.ldr, d.ldaux = lda, ldb, ldd, ldr, ldaux
     d.a_batch_stride, d.b_batch_stride, d.d_batch_stride = a_bs, b_bs, d_bs
+    if drop is not None and drop_mode:
+        d.drop_seed, d.drop_mode, d.drop_site, d.drop_p = _C.ptr(drop.seed), drop_mode, drop.site, drop.p
     _launch_gemm(d)
     return D
 
 
-def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, out_dtype=BF16, out=None, out2=None, alpha=1.0):
+def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, out_dtype=BF16, out=None, out2=None, alpha=1.0, drop=None, drop_mode=0):
     """y[M,N] = act(alpha * x[M,K] @ w[N,K]^T + bias + residual).  x, w bf16 row-major (last dim contiguous)."""
     _req(x, BF16), _req(w, BF16)
     M, K = x.shape
     N = w.shape[0]
     y = out if out is not None else torch.empty((M, N), device=x.device, dtype=out_dtype)
     return gemm(x, w, y, M=M, N=N, K=K, lda=x.stride(0), ldb=w.stride(0), ldd=y.stride(0), bias=bias,
-                residual=residual, ldr=residual.stride(0) if residual is not None else 0, act=act, D2=out2, alpha=alpha)
+                residual=residual, ldr=residual.stride(0) if residual is not None else 0, act=act, D2=out2, alpha=alpha,
+                drop=drop, drop_mode=drop_mode)
 
 
-def linear_dgrad(dy, w, *, aux=None, aux_mode=AUX_NONE, residual=None, out=None, out_dtype=BF16):
+def linear_dgrad(dy, w, *, aux=None, aux_mode=AUX_NONE, residual=None, out=None, out_dtype=BF16, alpha=1.0):
     """dx[M,K] = (dy[M,N] @ w[N,K] + residual) (* mask(aux)).  w is read in its forward layout (MN-major B)."""
     _req(dy, BF16), _req(w, BF16)
     M, N = dy.shape
@@ -69,7 +96,7 @@ def linear_dgrad(dy, w, *, aux=None, aux_mode=AUX_NONE, residual=None, out=None,
     dx = out if out is not None else torch.empty((M, K), device=dy.device, dtype=out_dtype)
     return gemm(dy, w, dx, M=M, N=K, K=N, lda=dy.stride(0), ldb=w.stride(0), ldd=dx.stride(0), b_mn=True,
                 residual=residual, ldr=residual.stride(0) if residual is not None else 0,
-                aux=aux, ldaux=aux.stride(0) if aux is not None else 0, aux_mode=aux_mode)
+                aux=aux, ldaux=aux.stride(0) if aux is not None else 0, aux_mode=aux_mode, alpha=alpha)
 
 
 def linear_wgrad(dy, x, dw, *, rowscale=None, splits=0):
@@ -194,13 +221,22 @@ def lsap(cost, tgt_offsets):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def attention_fwd(q, k, v, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None, need_lse=True, out=None, bs_k=0, bs_v=0):
+def attention_fwd(q, k, v, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None, need_lse=True, out=None, bs_k=0, bs_v=0,
+                  drop=None):
     """q/k/v: bf16 2-D views [B*S, >=H*dh] (row stride = tokens' leading dimension; may be slices of a packed QKV).
     bs_k / bs_v: batch strides in elements when K / V are read in place from a cache [B][S_max][...] with Sk <= S_max.
     Returns (o [B*Sq, H*dh] bf16, lse [B,H,Sq] fp32 log2-domain or None)."""
     o = out if out is not None else torch.empty((B * Sq, H * dh), device=q.device, dtype=BF16)
     lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32) if need_lse else None
     i64 = ctypes.c_int64
+    if drop is not None:
+        assert not bs_k and not bs_v
+        _C.check(_C.lib().gpvb200_attention_fwd_drop(
+            _C.ptr(_req(q, BF16)), _C.ptr(_req(k, BF16)), _C.ptr(_req(v, BF16)), _C.ptr(o), _C.ptr(lse),
+            _C.ptr(_req(key_mask, torch.uint8)), i64(q.stride(0)), i64(k.stride(0)), i64(v.stride(0)), i64(o.stride(0)),
+            B, H, Sq, Sk, dh, int(causal), ctypes.c_float(scale), _C.ptr(drop.seed), ctypes.c_uint32(drop.site),
+            ctypes.c_float(drop.p), _C.stream_ptr()), "attention_fwd_drop")
+        return o, lse
     _C.check(_C.lib().gpvb200_attention_fwd_bs(
         _C.ptr(_req(q, BF16)), _C.ptr(_req(k, BF16)), _C.ptr(_req(v, BF16)), _C.ptr(o), _C.ptr(lse),
         _C.ptr(_req(key_mask, torch.uint8)), i64(q.stride(0)), i64(k.stride(0)), i64(v.stride(0)), i64(o.stride(0)),
@@ -208,9 +244,17 @@ def attention_fwd(q, k, v, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=No
     return o, lse
 
 
-def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None):
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, dh, scale, causal=False, key_mask=None, drop=None):
     """Writes dq/dk/dv (bf16 2-D views, may be slices of one packed gradient buffer)."""
     i64 = ctypes.c_int64
+    if drop is not None:
+        _C.check(_C.lib().gpvb200_attention_bwd_drop(
+            _C.ptr(_req(q, BF16)), _C.ptr(_req(k, BF16)), _C.ptr(_req(v, BF16)), _C.ptr(_req(o, BF16)), _C.ptr(_req(d_o, BF16)),
+            _C.ptr(_req(lse, torch.float32)), _C.ptr(_req(key_mask, torch.uint8)), _C.ptr(dq), _C.ptr(dk), _C.ptr(dv),
+            i64(q.stride(0)), i64(k.stride(0)), i64(v.stride(0)), i64(o.stride(0)), i64(d_o.stride(0)), i64(dq.stride(0)),
+            i64(dk.stride(0)), i64(dv.stride(0)), B, H, Sq, Sk, dh, int(causal), ctypes.c_float(scale), _C.ptr(drop.seed),
+            ctypes.c_uint32(drop.site), ctypes.c_float(drop.p), _C.stream_ptr()), "attention_bwd_drop")
+        return
     _C.check(_C.lib().gpvb200_attention_bwd(
         _C.ptr(_req(q, BF16)), _C.ptr(_req(k, BF16)), _C.ptr(_req(v, BF16)), _C.ptr(_req(o, BF16)), _C.ptr(_req(d_o, BF16)),
         _C.ptr(_req(lse, torch.float32)), _C.ptr(_req(key_mask, torch.uint8)), _C.ptr(dq), _C.ptr(dk), _C.ptr(dv),
@@ -220,19 +264,36 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, dh, scale, 
 
 
 # ------------------------------------------------------------------------------------------------ layernorm
-def layernorm_fwd(x, gamma, beta, eps, *, out=None, need_stats=True):
+def layernorm_fwd(x, gamma, beta, eps, *, out=None, need_stats=True, drop=None):
+    """drop: y = dropout(LN(x)) (BERT embeddings)."""
     M, D = x.shape
     y = out if out is not None else torch.empty((M, D), device=x.device, dtype=BF16)
     stats = torch.empty((M, 2), device=x.device, dtype=torch.float32) if need_stats else None
+    if drop is not None:
+        _C.check(_C.lib().gpvb200_layernorm_fwd_drop(
+            _C.ptr(_req(x, BF16)), ctypes.c_int64(x.stride(0)), _C.ptr(gamma), _C.ptr(beta), ctypes.c_float(eps), _C.ptr(y),
+            ctypes.c_int64(y.stride(0)), _C.ptr(stats), M, D, _C.ptr(drop.seed), ctypes.c_uint32(drop.site), ctypes.c_float(drop.p),
+            _C.stream_ptr()), "layernorm_fwd_drop")
+        return y, stats
     _C.check(_C.lib().gpvb200_layernorm_fwd(_C.ptr(_req(x, BF16)), ctypes.c_int64(x.stride(0)), _C.ptr(gamma), _C.ptr(beta),
                                             ctypes.c_float(eps), _C.ptr(y), ctypes.c_int64(y.stride(0)), _C.ptr(stats), M, D,
                                             _C.stream_ptr()), "layernorm_fwd")
     return y, stats
 
 
-def layernorm_bwd(dy, x, stats, gamma, dgamma, dbeta, *, out=None):
+def layernorm_bwd(dy, x, stats, gamma, dgamma, dbeta, *, out=None, drop=None):
+    """drop: also returns dx (*) mask / (1 - p) -- the gradient of the dropped-out sub-layer output in
+    y = LN(res + dropout(f)) -- as a second tensor: (dx, dx_masked)."""
     M, D = x.shape
     dx = out if out is not None else torch.empty((M, D), device=x.device, dtype=BF16)
+    if drop is not None:
+        dxm = torch.empty((M, D), device=x.device, dtype=BF16)
+        _C.check(_C.lib().gpvb200_layernorm_bwd_drop(
+            _C.ptr(_req(dy, BF16)), ctypes.c_int64(dy.stride(0)), _C.ptr(_req(x, BF16)), ctypes.c_int64(x.stride(0)), _C.ptr(stats),
+            _C.ptr(gamma), _C.ptr(dx), ctypes.c_int64(dx.stride(0)), _C.ptr(dgamma), _C.ptr(dbeta), M, D, _C.ptr(dxm),
+            ctypes.c_int64(dxm.stride(0)), _C.ptr(drop.seed), ctypes.c_uint32(drop.site), ctypes.c_float(drop.p), _C.stream_ptr()),
+            "layernorm_bwd_drop")
+        return dx, dxm
     _C.check(_C.lib().gpvb200_layernorm_bwd(_C.ptr(_req(dy, BF16)), ctypes.c_int64(dy.stride(0)), _C.ptr(_req(x, BF16)),
                                             ctypes.c_int64(x.stride(0)), _C.ptr(stats), _C.ptr(gamma), _C.ptr(dx),
                                             ctypes.c_int64(dx.stride(0)), _C.ptr(dgamma), _C.ptr(dbeta), M, D, _C.stream_ptr()),

@@ -86,6 +86,15 @@ typedef struct gpvb200_gemm_desc {
   const void* aux;        /* bf16, indexed like D with leading dimension ldaux, or NULL */
   int64_t lda, ldb, ldd, ldr, ldaux;
   int64_t a_batch_stride, b_batch_stride, d_batch_stride; /* elements; mode 0 batches / mode 2 taps */
+  /* train-mode dropout fused into the epilogue (nn.Dropout sites of transformer.py:155,158-160, vilbert.py:848-851,
+   * 471,514 and nn.TransformerDecoderLayer): drop_mode 1 = on alpha*acc*rowscale + bias, before the residual is added
+   * (y = res + dropout(xW + b)); 2 = on the activation output (h = dropout(relu(xW + b))).  The mask of element
+   * (row, col) is a counter-based function of (*drop_seed, drop_site, row, col), see gpvb200_dropout_mask. */
+  const void* drop_seed;  /* device uint64 scalar (training-step counter) or NULL */
+  int32_t drop_mode;      /* 0 none */
+  uint32_t drop_site;
+  float drop_p;
+  int32_t pad_;
 } gpvb200_gemm_desc;
 
 size_t gpvb200_gemm_desc_size(void);
@@ -124,6 +133,17 @@ int gpvb200_attention_fwd_bs(const void* q, const void* k, const void* v, void* 
                              int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t bsq, int64_t bsk, int64_t bsv,
                              int64_t bso, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale,
                              void* stream);
+/* train-mode variants: dropout with probability drop_p on the attention probabilities (nn.MultiheadAttention dropout,
+ * vilbert.py:443,782,805); mask row = (b*H + h)*Sq + q, col = key, site drop_site, seed *drop_seed */
+int gpvb200_attention_fwd_drop(const void* q, const void* k, const void* v, void* o, float* lse, const uint8_t* key_mask,
+                               int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int32_t B, int32_t H, int32_t Sq, int32_t Sk,
+                               int32_t dh, int32_t causal, float scale, const void* drop_seed, uint32_t drop_site, float drop_p,
+                               void* stream);
+int gpvb200_attention_bwd_drop(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                               const uint8_t* key_mask, void* dq, void* dk, void* dv, int64_t ldq, int64_t ldk, int64_t ldv,
+                               int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, int32_t B, int32_t H,
+                               int32_t Sq, int32_t Sk, int32_t dh, int32_t causal, float scale, const void* drop_seed,
+                               uint32_t drop_site, float drop_p, void* stream);
 int gpvb200_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                           const uint8_t* key_mask, void* dq, void* dk, void* dv, int64_t ldq, int64_t ldk, int64_t ldv,
                           int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, int32_t B, int32_t H,
@@ -201,6 +221,19 @@ int gpvb200_set_criterion(const float* logits, int64_t ldl, const float* boxes, 
                           const uint8_t* loc_valid, int32_t B, int32_t Q, float eos_coef, float weight_sum, float num_boxes,
                           float wt_ce, float wt_bbox, float wt_giou, float* out3, float* dlogits, void* dbox_pre, int64_t lddb,
                           void* stream);
+
+/* ---- train-mode dropout helpers.  layernorm_fwd_drop: y = dropout(LN(x)) (BERT embeddings, vilbert.py:364 / HF
+ * BertEmbeddings).  layernorm_bwd_drop: additionally writes dx_masked = dx (*) mask / (1 - p), the gradient of the
+ * dropped-out sub-layer output in y = LN(res + dropout(f)).  dropout_mask: out[row*N + col] = 1 kept / 0 dropped for
+ * the logical [rows, N] tensor of (seed, site) -- what the tests feed to autograd to check forward and backward. */
+int gpvb200_layernorm_fwd_drop(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y, int64_t ldy,
+                               float* stats, int32_t M, int32_t D, const void* drop_seed, uint32_t drop_site, float drop_p,
+                               void* stream);
+int gpvb200_layernorm_bwd_drop(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* stats, const float* gamma,
+                               void* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t D, void* dx_masked,
+                               int64_t lddxm, const void* drop_seed, uint32_t drop_site, float drop_p, void* stream);
+int gpvb200_dropout_mask(uint8_t* out, int64_t rows, int32_t N, const void* drop_seed, uint32_t drop_site, float drop_p,
+                         void* stream);
 
 /* ---- optimizer: clip_grad_norm_ + AdamW over the flat gradient arena (exp/gpv/train_distr.py:414-428, 228-253).
  * items: device array of {float* p; int64 goff; int32 n, group, clip, pad} (gpvb200_optim_item_size() bytes each);

@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the captured CUDA graphs")
     ap.add_argument("--profiling", action="store_true", help="under ncu only: allow fewer than 3 warm-up steps, skip the e2e loop")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown of one extra step to this file")
+    ap.add_argument("--eval-mode", action="store_true", help="time the dropout-free (model.eval()) arithmetic instead of the training mode")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -231,6 +232,7 @@ def main():
     cfg = load_config()
     B = args.batch
     model = GPV(cfg.model, vocab=vocab_list(V_BENCH), seed=0).to(dev)
+    model.train(not args.eval_mode)       # training mode: every nn.Dropout site of the reference is active (p = 0.1), as in train_distr.py:407
     sync = GradSync(model) if world > 1 else None
     broadcast_parameters(model)
 
@@ -389,7 +391,9 @@ def main():
             "dtype": "bf16", "data": "synthetic (random-init weights, randn images, random token ids)",
             "config": {"workload": workload_name(B), "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graph_launches is not None,
                        "l2": "per-step working set (4 GB of saved activations) exceeds the 126 MB L2; no explicit flush",
-                       "dropout": "off (eval-mode-with-grad parity contract; Philox dropout not fused yet)", "loss": loss_val},
+                       "dropout": ("off (model.eval(): the parity arithmetic)" if args.eval_mode else
+                                   "on: p=0.1 at every nn.Dropout site (counter-based masks fused into the GEMM epilogues, LayerNorm "
+                                   "and attention kernels, regenerated in backward)"), "loss": loss_val},
             "clocks": clocks,
             "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "e2e_uint8": None if ms_e2e_u8 is None else {

@@ -67,7 +67,7 @@ GPV_DEVINL void load_a_frags(const bf16* s, int LD, int r0, int g, int t, uint32
 }
 
 // ======================================================================================== forward
-template <int DH, int NT>
+template <int DH, int NT, bool DROP>
 __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
   pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float sl2 = p.scale * 1.4426950408889634f;
-  const uint32_t dkey = p.drop.seed ? drop_key(*p.drop.seed, p.drop.site) : 0u;
+  const uint32_t dkey = DROP ? drop_key(*p.drop.seed, p.drop.site) : 0u;
   for (int r0 = warp * 16; r0 < Sqp; r0 += NT / 2) {
     uint32_t qa[DH / 16][4];
     load_a_frags<DH>(Qs, LD, r0, g, t, qa);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
       }
       l0 = l0 * c0 + rs0;
       l1 = l1 * c1 + rs1;
-      if (p.drop.seed != nullptr) {   // O = dropout(softmax(S)) V: the normaliser keeps every key, the PV product the kept ones
+      if (DROP) {   // O = dropout(softmax(S)) V: the normaliser keeps every key, the PV product the kept ones
         const uint32_t hs = (uint32_t)((Sk + 1) >> 1);
         const uint32_t pr0 = ((uint32_t)bh * (uint32_t)Sq + (uint32_t)row0) * hs, pr1 = pr0 + 8u * hs;
 #pragma unroll
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
 // ======================================================================================== backward
 // Pass 1 (warp owns 16 queries): D = rowsum(dO*O), dQ = scale * [P o (dO V^T - D)] K
 // Pass 2 (warp owns 16 keys):    dV = P^T dO,      dK = scale * [P o (dO V^T - D)]^T Q
-template <int DH, int NT>
+template <int DH, int NT, bool DROP>
 __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
   pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float sl2 = p.scale * 1.4426950408889634f;
-  const bool drop = p.drop.seed != nullptr;
+  constexpr bool drop = DROP;
   const uint32_t dkey = drop ? drop_key(*p.drop.seed, p.drop.site) : 0u;
   const uint32_t hs = (uint32_t)((Sk + 1) >> 1);   // mask pairs per (b, h, q) row
 
@@ -442,7 +442,9 @@ static int launch_attn(const AttnParams& p, bool bwd, cudaStream_t st) {
   // 16 query (or key) rows per warp and pass: 12 warps cover the 300-token encoder maps in two rounds; the wide heads
   // (d_h >= 48) keep 8 warps so that the backward's accumulators stay in registers.
   constexpr int NTF = 256, NTB = (DH <= 32) ? 384 : 256;
-  auto kern = bwd ? attn_bwd_kernel<DH, NTB> : attn_fwd_kernel<DH, NTF>;
+  const bool drop = p.drop.seed != nullptr;
+  auto kern = bwd ? (drop ? attn_bwd_kernel<DH, NTB, true> : attn_bwd_kernel<DH, NTB, false>)
+                  : (drop ? attn_fwd_kernel<DH, NTF, true> : attn_fwd_kernel<DH, NTF, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_last_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));

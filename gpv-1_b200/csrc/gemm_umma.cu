@@ -220,7 +220,9 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
         if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
     }
   }
-  if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
+  if constexpr (F < 0) {
+    if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
+  }
   if (E::res(p)) {
     if (E::res_fp32(p)) {
       const float* rp = reinterpret_cast<const float*>(p.residual) + off_r;
@@ -249,7 +251,9 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
     }
   }
   epi_activation<F>(p, v);
-  if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
+  if constexpr (F < 0) {
+    if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
+  }
   if (E::aux(p) != GPVB200_AUX_NONE) {
     float a[kChunk];
     if (vec) {
@@ -345,14 +349,18 @@ GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], 
       v[j] += b4[j / 4].x; v[j + 1] += b4[j / 4].y; v[j + 2] += b4[j / 4].z; v[j + 3] += b4[j / 4].w;
     }
   }
-  if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
+  if constexpr (F < 0) {   // train-mode dropout runs on the run-time-flag kernel only: the hot variants carry none of it
+    if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
+  }
   if (E::res(p)) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) unpack8(lds128(res_s + so.own[i]), v + 8 * i, true);
   }
   if (E::d2(p)) store_slab(cr.d2, cr.ok, col, v, out_s, so);
   epi_activation<F>(p, v);
-  if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
+  if constexpr (F < 0) {
+    if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
+  }
   if (E::aux(p) != GPVB200_AUX_NONE) {
     float a[kChunk];
 #pragma unroll
@@ -551,7 +559,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 4; ++i) so.own[i] = 16u * slab_slot(lane, i);
     const long long ldd = p.ldd, ldr = p.ldr, lda = p.ldaux;
-    const uint32_t dkey = p.drop_mode ? drop_key(*p.drop.seed, p.drop.site) : 0u;
+    const uint32_t dkey = (F < 0 && p.drop_mode) ? drop_key(*p.drop.seed, p.drop.site) : 0u;
     int j = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
       const Work wk = decode_work(p, w);
@@ -1120,7 +1128,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
 
   cudaStream_t st = (cudaStream_t)stream;
   int f = -1;
-  if (kp.coal)
+  if (kp.coal && !kp.drop_mode)
     f = (d->bias ? 1 : 0) | (d->residual ? 2 : 0) | ((d->act & 3) << 2) | ((d->aux_mode & 3) << 4) | (d->D2 ? 64 : 0);
   if (BN == 256) return launch_bn<256>(f, ma, mb, kp, smem, st);
   if (BN == 128) return launch_bn<128>(f, ma, mb, kp, smem, st);

@@ -9,7 +9,7 @@
 
 namespace gpv {
 
-template <int MAXC>
+template <int MAXC, bool DROP>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, long long ldx,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float eps, bf16* __restrict__ y, long long ldy,
@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
   pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = D >> 3;
-  const uint32_t dkey = dr.seed ? drop_key(*dr.seed, dr.site) : 0u;   // y = dropout(LN(x)) (BERT embeddings, vilbert.py:364)
+  const uint32_t dkey = DROP ? drop_key(*dr.seed, dr.site) : 0u;   // y = dropout(LN(x)) (BERT embeddings, vilbert.py:364)
   for (long long row = (long long)blockIdx.x * 8 + warp; row < M; row += (long long)gridDim.x * 8) {
     const bf16* xr = x + row * ldx;
     float v[MAXC][8];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
           if (gamma != nullptr) t = t * __ldg(gamma + ch * 8 + j) + __ldg(beta + ch * 8 + j);
           o[j] = t;
         }
-        if (dr.seed != nullptr) {
+        if (DROP) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             drop_pair(o[2 * j], o[2 * j + 1], dkey, (uint32_t)row * (uint32_t)(D >> 1) + ch * 4 + j, dr.thresh16, dr.scale);
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += dy * xhat;  dbeta += dy
-template <int MAXC, bool AFFINE>
+template <int MAXC, bool AFFINE, bool DXM>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, long long lddy,
                                                             const bf16* __restrict__ x, long long ldx,
                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
   pdl_sync();
   // dxm (optional) = dx (*) mask / (1 - p): the gradient of the dropped-out sub-layer output in y = LN(res + dropout(f)),
   // regenerated from the forward's (seed, site); dx itself is the gradient of the residual branch.
-  const uint32_t dkey = dxm ? drop_key(*dr.seed, dr.site) : 0u;
+  const uint32_t dkey = DXM ? drop_key(*dr.seed, dr.site) : 0u;
   extern __shared__ float red[];  // [2][D] when affine
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = D >> 3;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
         u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
         u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
         *reinterpret_cast<uint4*>(dx + row * lddx + ch * 8) = u;
-        if (dxm != nullptr) {
+        if (DXM) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             drop_pair(o[2 * j], o[2 * j + 1], dkey, (uint32_t)row * (uint32_t)(D >> 1) + ch * 4 + j, dr.thresh16, dr.scale);
@@ -207,10 +207,14 @@ extern "C" int gpvb200_layernorm_fwd_drop(const void* x, int64_t ldx, const floa
   const DropArgs dr = make_drop(drop_seed, drop_site, drop_p);
   const int grid = (M + 7) / 8 < 148 * 8 ? (M + 7) / 8 : 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  if (D <= 768)
-    launch_k(layernorm_fwd_kernel<3>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
+  if (D <= 768 && dr.seed != nullptr)
+    launch_k(layernorm_fwd_kernel<3, true>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
+  else if (D <= 768)
+    launch_k(layernorm_fwd_kernel<3, false>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
+  else if (dr.seed != nullptr)
+    launch_k(layernorm_fwd_kernel<9, true>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
   else
-    launch_k(layernorm_fwd_kernel<9>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
+    launch_k(layernorm_fwd_kernel<9, false>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, gamma, beta, eps, (bf16*)y, ldy, stats, M, D, dr);
   return check_launch("layernorm_fwd_kernel");
 }
 
@@ -236,15 +240,17 @@ extern "C" int gpvb200_layernorm_bwd_drop(const void* dy, int64_t lddy, const vo
   const int grid = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = gamma ? (size_t)2 * D * sizeof(float) : 0;
-  if (gamma != nullptr)
-    launch_k(layernorm_bwd_kernel<3, true>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma,
-             (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr);
-  else if (D <= 768)
-    launch_k(layernorm_bwd_kernel<3, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma,
-             (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr);
-  else
-    launch_k(layernorm_bwd_kernel<9, false>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma,
-             (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr);
+#define GPV_LN_BWD(MAXC, AFF, DXM)                                                                                          \
+  launch_k(layernorm_bwd_kernel<MAXC, AFF, DXM>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, \
+           gamma, (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr)
+  if (gamma != nullptr) {
+    if (dxm) GPV_LN_BWD(3, true, true); else GPV_LN_BWD(3, true, false);
+  } else if (D <= 768) {
+    if (dxm) GPV_LN_BWD(3, false, true); else GPV_LN_BWD(3, false, false);
+  } else {
+    if (dxm) GPV_LN_BWD(9, false, true); else GPV_LN_BWD(9, false, false);
+  }
+#undef GPV_LN_BWD
   return check_launch("layernorm_bwd_kernel");
 }
 

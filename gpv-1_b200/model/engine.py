@@ -19,6 +19,7 @@ HungarianMatcher matcher.py:32-77, and autograd's backward of all of it.
 """
 import contextlib
 import math
+import zlib
 
 import torch
 
@@ -96,6 +97,14 @@ class Engine:
         self._versions = None
         self._pos_cache = {}
         self.saved = None
+        # train-mode dropout (every nn.Dropout site of the reference uses cfg.detr.dropout = 0.1: gpv.yaml:50,64,75-82;
+        # HF BERT 0.1).  train_mode is set by the owning module from nn.Module.training before each call.
+        self.train_mode = False
+        co = cfg.co_att
+        self.p_drop = {"detr": float(cfg.detr.dropout), "txt": float(cfg.text_decoder.dropout), "bert": 0.1,
+                       "co_att_l": float(co.v_attention_probs_dropout_prob), "co_att_v": float(co.attention_probs_dropout_prob),
+                       "co_hid_l": float(co.v_hidden_dropout_prob), "co_hid_v": float(co.hidden_dropout_prob)}
+        self.drop_seed = torch.zeros(1, dtype=torch.int64, device=device)     # training-step counter read by the kernels
         self.concurrent = True                                # run independent branches on side streams (lanes)
         self._lanes, self._dirty, self._keep = {}, set(), []
 
@@ -284,6 +293,33 @@ class Engine:
         if self.on_stage_done is not None:
             self.on_stage_done(stage)
 
+    # ---- dropout sites
+    def _pfam(self, name):
+        if name.startswith("detr."):
+            return self.p_drop["detr"]
+        if name.startswith("text_decoder."):
+            return self.p_drop["txt"]
+        if name.startswith("bert."):
+            return self.p_drop["bert"]
+        return 0.0
+
+    def _drop(self, site, p=None):
+        """k.Drop for the dropout site named `site` (None in eval mode or when p = 0).  Forward and backward of a site
+        call this with the same name, so both regenerate the same mask from (step counter, crc32(name))."""
+        if not self.train_mode:
+            return None
+        p = self._pfam(site) if p is None else p
+        if p <= 0.0:
+            return None
+        return k.Drop(self.drop_seed, zlib.crc32(site.encode()), p)
+
+    def _ln_bwd(self, dy, x, st, gamma, dgamma, dbeta, drop):
+        """(dx, dx_masked): LayerNorm backward of y = LN(res + dropout(f)); dx_masked is the gradient of f's output."""
+        if drop is None:
+            dx = k.layernorm_bwd(dy, x, st, gamma, dgamma, dbeta)
+            return dx, dx
+        return k.layernorm_bwd(dy, x, st, gamma, dgamma, dbeta, drop=drop)
+
     # ---- concurrent branches.  Most GEMMs of the transformer stacks cover 15-75 of the 148 SMs, so independent
     # branches (weight/bias gradients beside the data-gradient chain, BERT beside the backbone, K/V projections of a
     # fixed memory beside the decoder's self-attention) are enqueued on side streams ("lanes"); inside a captured
@@ -316,7 +352,7 @@ class Engine:
         return self._pos_cache[key]
 
     def _lin_bwd(self, name, x, dy, *, need_dx=True, aux=None, aux_mode=k.AUX_NONE, residual=None, wkey=None, gkey=None,
-                 bias=True):
+                 bias=True, alpha=1.0):
         """dW += dy^T x, db += colsum(dy), returns dx = (dy W + residual) (*) mask."""
         g = gkey or name
         with self._aside(dy, x):
@@ -324,7 +360,7 @@ class Engine:
             if bias:
                 k.colsum(dy, self.G[g + ".bias"])
         if need_dx:
-            return k.linear_dgrad(dy, self.W[wkey or (name + ".weight")], aux=aux, aux_mode=aux_mode, residual=residual)
+            return k.linear_dgrad(dy, self.W[wkey or (name + ".weight")], aux=aux, aux_mode=aux_mode, residual=residual, alpha=alpha)
         return None
 
     # ================================================================================================ backbone
@@ -433,8 +469,9 @@ class Engine:
             k.linear(x, wi, bi_, out=qkv)
         dh = D // H
         o, lse = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5,
-                                 causal=causal, key_mask=kmask)
-        pre = k.linear(o, W[f"{p}.{attn}.out_proj.weight"], Pm[f"{p}.{attn}.out_proj.bias"], residual=x)
+                                 causal=causal, key_mask=kmask, drop=self._drop(f"{p}.{attn}.probs"))
+        pre = k.linear(o, W[f"{p}.{attn}.out_proj.weight"], Pm[f"{p}.{attn}.out_proj.bias"], residual=x,
+                       drop=self._drop(f"{p}.{norm}.in"), drop_mode=k.DROP_PRE_RESIDUAL)
         y, st = k.layernorm_fwd(pre, Pm[f"{p}.{norm}.weight"], Pm[f"{p}.{norm}.bias"], eps)
         return y, (x, qk_in, qkv, o, lse, pre, st)
 
@@ -444,11 +481,13 @@ class Engine:
         x, qk_in, qkv, o, lse, pre, st = sv
         D = x.shape[1]
         dh = D // H
-        dpre = k.layernorm_bwd(dy, pre, st, Pm[f"{p}.{norm}.weight"], G[f"{p}.{norm}.weight"], G[f"{p}.{norm}.bias"])
-        do = self._lin_bwd(f"{p}.{attn}.out_proj", o, dpre)
+        dpre, dpre_m = self._ln_bwd(dy, pre, st, Pm[f"{p}.{norm}.weight"], G[f"{p}.{norm}.weight"], G[f"{p}.{norm}.bias"],
+                                    self._drop(f"{p}.{norm}.in"))
+        do = self._lin_bwd(f"{p}.{attn}.out_proj", o, dpre_m)
         dqkv = torch.empty_like(qkv)
         k.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
-                        B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5, causal=causal, key_mask=kmask)
+                        B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5, causal=causal, key_mask=kmask,
+                        drop=self._drop(f"{p}.{attn}.probs"))
         wi = W[f"{p}.{attn}.in_proj_weight"]
         gw, gb = G[f"{p}.{attn}.in_proj_weight"], G[f"{p}.{attn}.in_proj_bias"]
         with self._aside(dqkv):
@@ -491,8 +530,10 @@ class Engine:
         if kv is None:
             kv = self._cross_kv(p, kmem, vmem)
         dh = D // H
-        o, lse = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=dh ** -0.5, key_mask=kmask)
-        pre = k.linear(o, W[f"{p}.multihead_attn.out_proj.weight"], Pm[f"{p}.multihead_attn.out_proj.bias"], residual=x)
+        o, lse = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh, scale=dh ** -0.5, key_mask=kmask,
+                                 drop=self._drop(f"{p}.multihead_attn.probs"))
+        pre = k.linear(o, W[f"{p}.multihead_attn.out_proj.weight"], Pm[f"{p}.multihead_attn.out_proj.bias"], residual=x,
+                       drop=self._drop(f"{p}.{norm}.in"), drop_mode=k.DROP_PRE_RESIDUAL)
         y, st = k.layernorm_fwd(pre, Pm[f"{p}.{norm}.weight"], Pm[f"{p}.{norm}.bias"], eps)
         return y, (x, q_in, q, kv, o, lse, pre, st)
 
@@ -503,12 +544,13 @@ class Engine:
         D = x.shape[1]
         dh = D // H
         a = f"{p}.multihead_attn"
-        dpre = k.layernorm_bwd(dy, pre, st, Pm[f"{p}.{norm}.weight"], G[f"{p}.{norm}.weight"], G[f"{p}.{norm}.bias"])
-        do = self._lin_bwd(a + ".out_proj", o, dpre)
+        dpre, dpre_m = self._ln_bwd(dy, pre, st, Pm[f"{p}.{norm}.weight"], G[f"{p}.{norm}.weight"], G[f"{p}.{norm}.bias"],
+                                    self._drop(f"{p}.{norm}.in"))
+        do = self._lin_bwd(a + ".out_proj", o, dpre_m)
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
         k.attention_bwd(q, kv[:, :D], kv[:, D:], o, do, lse, dq, dkv[:, :D], dkv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh,
-                        scale=dh ** -0.5, key_mask=kmask)
+                        scale=dh ** -0.5, key_mask=kmask, drop=self._drop(f"{p}.multihead_attn.probs"))
         wi, gw, gb = W[a + ".in_proj_weight"], G[a + ".in_proj_weight"], G[a + ".in_proj_bias"]
         with self._aside(dq, dkv):
             k.colsum(dq, gb[:D])
@@ -532,24 +574,29 @@ class Engine:
             dx = k.add(dpre, dq_in, out=dq_in)
         return dx, dmem
 
-    def _ffn_fwd(self, w1, w2, ln, x, eps, act=RELU):
-        """y = LN(x + W2 act(W1 x + b1) + b2)."""
+    def _ffn_fwd(self, w1, w2, ln, x, eps, act=RELU, p_out=None):
+        """y = LN(x + drop(W2 drop_h(act(W1 x + b1)) + b2)).  Train mode: the ReLU networks (DETR, text decoder) drop
+        the hidden activation too (transformer.py:158); the GELU ones (ViLBERT / BERT intermediate) only the output."""
         W, Pm = self.W, self.P
         if act == GELU:
             hpre = torch.empty((x.shape[0], W[w1 + ".weight"].shape[0]), device=self.dev, dtype=BF16)
             h = k.linear(x, W[w1 + ".weight"], Pm[w1 + ".bias"], act=GELU, out2=hpre)
         else:
-            h = k.linear(x, W[w1 + ".weight"], Pm[w1 + ".bias"], act=RELU)
+            h = k.linear(x, W[w1 + ".weight"], Pm[w1 + ".bias"], act=RELU, drop=self._drop(w1 + ".hidden"), drop_mode=k.DROP_POST_ACT)
             hpre = h
-        pre = k.linear(h, W[w2 + ".weight"], Pm[w2 + ".bias"], residual=x)
+        pre = k.linear(h, W[w2 + ".weight"], Pm[w2 + ".bias"], residual=x, drop=self._drop(ln + ".in", p_out),
+                       drop_mode=k.DROP_PRE_RESIDUAL)
         y, st = k.layernorm_fwd(pre, Pm[ln + ".weight"], Pm[ln + ".bias"], eps)
         return y, (x, h, hpre, pre, st)
 
-    def _ffn_bwd(self, w1, w2, ln, dy, sv, act=RELU):
+    def _ffn_bwd(self, w1, w2, ln, dy, sv, act=RELU, p_out=None):
         Pm, G = self.P, self.G
         x, h, hpre, pre, st = sv
-        dpre = k.layernorm_bwd(dy, pre, st, Pm[ln + ".weight"], G[ln + ".weight"], G[ln + ".bias"])
-        dh = self._lin_bwd(w2, h, dpre, aux=hpre, aux_mode=GRAD_GELU if act == GELU else MASK_RELU)
+        dpre, dpre_m = self._ln_bwd(dy, pre, st, Pm[ln + ".weight"], G[ln + ".weight"], G[ln + ".bias"], self._drop(ln + ".in", p_out))
+        dh_drop = self._drop(w1 + ".hidden") if act != GELU else None
+        # hidden dropout: the saved h is already masked, so relu'(h) (*) mask = [h > 0]; only the 1/(1-p) scale remains
+        dh = self._lin_bwd(w2, h, dpre_m, aux=hpre, aux_mode=GRAD_GELU if act == GELU else MASK_RELU,
+                           alpha=dh_drop.scale if dh_drop is not None else 1.0)
         return self._lin_bwd(w1, x, dh, residual=dpre)
 
     # ================================================================================================ BERT (no grad)
@@ -560,17 +607,23 @@ class Engine:
         B, T = ids.shape
         e = k.gather_rows(P[f"{b}.embeddings.word_embeddings.weight"], ids.reshape(-1), pos=P[f"{b}.embeddings.position_embeddings.weight"],
                           cst=P[f"{b}.embeddings.token_type_embeddings.weight"], T=T)
-        x, _ = k.layernorm_fwd(e, P[f"{b}.embeddings.LayerNorm.weight"], P[f"{b}.embeddings.LayerNorm.bias"], 1e-12, need_stats=False)
+        # bert.py:11-22 runs under no_grad but in the module's train/eval mode: HF's dropouts (embeddings, attention
+        # probabilities, both dense outputs) are active while training
+        x, _ = k.layernorm_fwd(e, P[f"{b}.embeddings.LayerNorm.weight"], P[f"{b}.embeddings.LayerNorm.bias"], 1e-12, need_stats=False,
+                               drop=self._drop(f"{b}.embeddings.out"))
         D = x.shape[1]
         for i in range(12):
             p = f"{b}.encoder.layer.{i}"
             qkv = k.linear(x, W[p + ".qkv"], self.Bcat[p + ".qkv"])
-            o, _ = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=12, Sq=T, Sk=T, dh=64, scale=0.125, need_lse=False)
-            pre = k.linear(o, W[p + ".attention.output.dense.weight"], P[p + ".attention.output.dense.bias"], residual=x)
+            o, _ = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=12, Sq=T, Sk=T, dh=64, scale=0.125, need_lse=False,
+                                   drop=self._drop(p + ".attention.probs"))
+            pre = k.linear(o, W[p + ".attention.output.dense.weight"], P[p + ".attention.output.dense.bias"], residual=x,
+                           drop=self._drop(p + ".attention.output.in"), drop_mode=k.DROP_PRE_RESIDUAL)
             x1, _ = k.layernorm_fwd(pre, P[p + ".attention.output.LayerNorm.weight"], P[p + ".attention.output.LayerNorm.bias"], 1e-12,
                                     need_stats=False)
             h = k.linear(x1, W[p + ".intermediate.dense.weight"], P[p + ".intermediate.dense.bias"], act=GELU)
-            pre = k.linear(h, W[p + ".output.dense.weight"], P[p + ".output.dense.bias"], residual=x1)
+            pre = k.linear(h, W[p + ".output.dense.weight"], P[p + ".output.dense.bias"], residual=x1,
+                           drop=self._drop(p + ".output.in"), drop_mode=k.DROP_PRE_RESIDUAL)
             x, _ = k.layernorm_fwd(pre, P[p + ".output.LayerNorm.weight"], P[p + ".output.LayerNorm.bias"], 1e-12, need_stats=False)
         return x
 
@@ -581,19 +634,26 @@ class Engine:
         D, H = self.D, self.h_co
         dh = D // H
         sc = 1.0 / math.sqrt(dh)
+        pd = self.p_drop          # vilbert.py:720-727, 833-851: "1" modules (language stream here) use the v_* probabilities
         with self._aside(lang, lane=1):
             qkv1 = k.linear(lang, W[p + ".qkv1"], self.Bcat[p + ".qkv1"])
         qkv2 = k.linear(vis, W[p + ".qkv2"], self.Bcat[p + ".qkv2"])
         self._join(1)
         with self._aside(lang, qkv2, lane=1):                 # language stream (attends to vision) beside the vision stream
-            ctx2, lse2 = k.attention_fwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
-            pa1 = k.linear(ctx2, W[p + ".biOutput.dense1.weight"], Pm[p + ".biOutput.dense1.bias"], residual=lang)
+            ctx2, lse2 = k.attention_fwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc,
+                                         drop=self._drop(p + ".probs2", pd["co_att_v"]))
+            pa1 = k.linear(ctx2, W[p + ".biOutput.dense1.weight"], Pm[p + ".biOutput.dense1.bias"], residual=lang,
+                           drop=self._drop(p + ".biOutput.LayerNorm1.in", pd["co_hid_l"]), drop_mode=k.DROP_PRE_RESIDUAL)
             att1, sa1 = k.layernorm_fwd(pa1, Pm[p + ".biOutput.LayerNorm1.weight"], Pm[p + ".biOutput.LayerNorm1.bias"], 1e-12)
-            o1, f1 = self._ffn_fwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", att1, 1e-12, GELU)
-        ctx1, lse1 = k.attention_fwd(qkv2[:, :D], qkv1[:, D:2 * D], qkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc)
-        pa2 = k.linear(ctx1, W[p + ".biOutput.dense2.weight"], Pm[p + ".biOutput.dense2.bias"], residual=vis)
+            o1, f1 = self._ffn_fwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", att1, 1e-12, GELU,
+                                   p_out=pd["co_hid_l"])
+        ctx1, lse1 = k.attention_fwd(qkv2[:, :D], qkv1[:, D:2 * D], qkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc,
+                                     drop=self._drop(p + ".probs1", pd["co_att_l"]))
+        pa2 = k.linear(ctx1, W[p + ".biOutput.dense2.weight"], Pm[p + ".biOutput.dense2.bias"], residual=vis,
+                       drop=self._drop(p + ".biOutput.LayerNorm2.in", pd["co_hid_v"]), drop_mode=k.DROP_PRE_RESIDUAL)
         att2, sa2 = k.layernorm_fwd(pa2, Pm[p + ".biOutput.LayerNorm2.weight"], Pm[p + ".biOutput.LayerNorm2.bias"], 1e-12)
-        o2, f2 = self._ffn_fwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", att2, 1e-12, GELU)
+        o2, f2 = self._ffn_fwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", att2, 1e-12, GELU,
+                               p_out=pd["co_hid_v"])
         self._join(1)
         return o1, o2, (lang, vis, qkv1, qkv2, ctx1, lse1, ctx2, lse2, pa1, sa1, pa2, sa2, f1, f2)
 
@@ -603,22 +663,25 @@ class Engine:
         dh = D // H
         sc = 1.0 / math.sqrt(dh)
         lang, vis, qkv1, qkv2, ctx1, lse1, ctx2, lse2, pa1, sa1, pa2, sa2, f1, f2 = sv
+        pd = self.p_drop
         with self._aside(do1, lane=1):                        # language stream beside the vision stream
-            datt1 = self._ffn_bwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", do1, f1, GELU)
-            dpa1 = k.layernorm_bwd(datt1, pa1, sa1, Pm[p + ".biOutput.LayerNorm1.weight"], G[p + ".biOutput.LayerNorm1.weight"],
-                                   G[p + ".biOutput.LayerNorm1.bias"])
-            dctx2 = self._lin_bwd(p + ".biOutput.dense1", ctx2, dpa1)
-        datt2 = self._ffn_bwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", do2, f2, GELU)
-        dpa2 = k.layernorm_bwd(datt2, pa2, sa2, Pm[p + ".biOutput.LayerNorm2.weight"], G[p + ".biOutput.LayerNorm2.weight"],
-                               G[p + ".biOutput.LayerNorm2.bias"])
-        dctx1 = self._lin_bwd(p + ".biOutput.dense2", ctx1, dpa2)
+            datt1 = self._ffn_bwd(p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm", do1, f1, GELU,
+                                  p_out=pd["co_hid_l"])
+            dpa1, dpa1_m = self._ln_bwd(datt1, pa1, sa1, Pm[p + ".biOutput.LayerNorm1.weight"], G[p + ".biOutput.LayerNorm1.weight"],
+                                        G[p + ".biOutput.LayerNorm1.bias"], self._drop(p + ".biOutput.LayerNorm1.in", pd["co_hid_l"]))
+            dctx2 = self._lin_bwd(p + ".biOutput.dense1", ctx2, dpa1_m)
+        datt2 = self._ffn_bwd(p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", do2, f2, GELU,
+                              p_out=pd["co_hid_v"])
+        dpa2, dpa2_m = self._ln_bwd(datt2, pa2, sa2, Pm[p + ".biOutput.LayerNorm2.weight"], G[p + ".biOutput.LayerNorm2.weight"],
+                                    G[p + ".biOutput.LayerNorm2.bias"], self._drop(p + ".biOutput.LayerNorm2.in", pd["co_hid_v"]))
+        dctx1 = self._lin_bwd(p + ".biOutput.dense2", ctx1, dpa2_m)
         dqkv1, dqkv2 = torch.empty_like(qkv1), torch.empty_like(qkv2)
         self._join(1)
         with self._aside(dqkv1, dqkv2, lane=1):
             k.attention_bwd(qkv1[:, :D], qkv2[:, D:2 * D], qkv2[:, 2 * D:], ctx2, dctx2, lse2, dqkv1[:, :D], dqkv2[:, D:2 * D],
-                            dqkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc)
+                            dqkv2[:, 2 * D:], B=B, H=H, Sq=Tl, Sk=Q, dh=dh, scale=sc, drop=self._drop(p + ".probs2", pd["co_att_v"]))
         k.attention_bwd(qkv2[:, :D], qkv1[:, D:2 * D], qkv1[:, 2 * D:], ctx1, dctx1, lse1, dqkv2[:, :D], dqkv1[:, D:2 * D],
-                        dqkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc)
+                        dqkv1[:, 2 * D:], B=B, H=H, Sq=Q, Sk=Tl, dh=dh, scale=sc, drop=self._drop(p + ".probs1", pd["co_att_l"]))
         self._join(1)
         with self._aside(dqkv1, lane=1):
             dlang = self._lin_bwd(p + ".qkv1", lang, dqkv1, residual=dpa1, wkey=p + ".qkv1", need_dx=need_dlang)
@@ -805,6 +868,8 @@ class Engine:
     def forward_train(self, images, qids, ans_ids, tgt, mask=None):
         """images [B,3,H,W] fp32, qids [B,Tl] int64, ans_ids [B,S] int64 (device).  tgt: HostTargets (see gpv.py).
         Returns (total_loss fp32 [1] on device, outputs dict)."""
+        if self.train_mode:
+            self.drop_seed.add_(1)                            # new masks every step; backward re-reads the same value
         s = self.encode(images, qids, save=True, mask=mask)
         B, Q, D = s["B"], self.Q, self.D
         M = B * Q

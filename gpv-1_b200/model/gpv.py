@@ -258,6 +258,7 @@ class GPV(nn.Module):
         if mask is not None:
             raise NotImplementedError("capture_step needs an unpadded batch (one image size): the padding mask is per batch")
         ans = answer_token_ids.to(device=images.device, dtype=torch.int64)
+        self.engine.train_mode = bool(self.training)
         self._captured = CapturedStep(self, images, qids, ans, targets, boxes_per_image_cap)
         return self._captured
 
@@ -332,6 +333,9 @@ class GPV(nn.Module):
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, images, queries, answer_token_ids, targets=None, vocab_mask=None):
         eng = self.engine
+        # nn.Dropout semantics: masks in train(), identity in eval().  Generation (no answer_token_ids) always runs the
+        # eval arithmetic: the reference only generates under model.eval() (inference.py:63, metrics.py)
+        eng.train_mode = bool(self.training) and answer_token_ids is not None
         (images, mask), qids = self._images(images), self._queries(queries)
         B, Q = images.shape[0], self.cfg.detr.num_queries
         if answer_token_ids is not None and targets is not None:
@@ -437,6 +441,7 @@ class GPV(nn.Module):
     def forward_beam_search(self, images, queries, beam_size=1):
         eng = self.engine
         (images, mask), qids = self._images(images), self._queries(queries)
+        eng.train_mode = False
         with torch.no_grad():
             if self.inference_graphs and mask is None:
                 outputs = self._graphed("beam", images, qids, None, beam_size)

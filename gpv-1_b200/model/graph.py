@@ -21,6 +21,7 @@ class CapturedStep:
         B, S = ans.shape
         self.B, self.S, self.Q = B, S, eng.Q
         self.img_shape, self.Tl = tuple(images.shape), qids.shape[1]
+        self.train_mode = eng.train_mode                   # the dropout kernels are part of the captured graphs
         cap = boxes_per_image_cap or eng.Q
         self.static_t = HostTargets.alloc_static(B, S, cap, dev)
         self.images = torch.empty(self.img_shape, dtype=images.dtype, device=dev)      # fp32 NCHW or uint8 NHWC
@@ -82,7 +83,8 @@ class CapturedStep:
         self.pending = False
 
     def matches(self, images, qids, ans):
-        return (tuple(images.shape) == self.img_shape and images.dtype == self.images.dtype and qids.shape[1] == self.Tl
+        return (self.eng.train_mode == self.train_mode and tuple(images.shape) == self.img_shape
+                and images.dtype == self.images.dtype and qids.shape[1] == self.Tl
                 and tuple(ans.shape) == (self.B, self.S))
 
     def _load(self, images, qids, ans, targets):

@@ -35,6 +35,7 @@ def ctx(cuda):
     model = GPV(load_config().model, vocab=vocab, vocab_embed=P["answer_head.vocab_embed"].numpy())
     model.load_state_dict(P, strict=True)
     model.to(cuda)
+    model.eval()
     eng = model.engine
     eng.refresh()
     # oracle weights = the bf16-rounded weights the kernels actually use (isolates activation rounding only)

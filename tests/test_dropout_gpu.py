@@ -109,3 +109,118 @@ def test_attention_dropout_forward_backward(cuda, H, Sq, Sk, dh, causal):
     for got, leaf, S in ((dq, qf, Sq), (dk, kf, Sk), (dv, vf, Sk)):
         want = leaf.grad.transpose(1, 2).reshape(B * S, D)
         assert _rel(got, want) < 2.5e-2, (_rel(got, want))
+
+
+# ---------------------------------------------------------------------------------------------------- engine blocks
+@pytest.fixture(scope="module")
+def ctx(cuda):
+    import json
+    import os
+    from gpv1_b200.config import load_config
+    from gpv1_b200.model import GPV
+    from oracle import torch_oracle as TO
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gpv_specs.json")))
+    P = TO.make_state([tuple(s) for s in g["specs"]], seed=0)
+    vocab = ["__pad__", "__cls__", "__stop__", "__unk__"] + [f"w{i}" for i in range(g["V"] - 4)]
+    model = GPV(load_config().model, vocab=vocab, vocab_embed=P["answer_head.vocab_embed"].numpy())
+    model.load_state_dict(P, strict=True)
+    model.to(cuda)
+    eng = model.engine
+    eng.refresh()
+    Pd = {n: (t.to(cuda).to(BF).float() if t.dtype.is_floating_point and t.dim() >= 2 else t.to(cuda)) for n, t in P.items()}
+    return model, eng, Pd
+
+
+def test_encoder_layer_with_dropout_matches_autograd(ctx, cuda):
+    """One DETR encoder layer (transformer.py:148-161) in train mode: attention-probability dropout, dropout1, the FFN's
+    hidden dropout and dropout2, forward and backward, against autograd fed with the masks of the engine's sites."""
+    import torch.nn.functional as F
+    from gpv1_b200 import kernels as k
+    model, eng, Pd = ctx
+    torch.manual_seed(0)
+    B, S, D, H = 2, 64, 256, 8
+    p = "detr.transformer.encoder.layers.1"
+    x = (torch.randn(B * S, D, device=cuda)).to(BF)
+    pos = torch.randn(S, D, device=cuda).to(BF)
+    dy = (0.1 * torch.randn(B * S, D, device=cuda)).to(BF)
+    eng.train_mode = True
+    eng.drop_seed.fill_(123)
+    try:
+        eng.grad_arena.zero_()
+        y1, sa = eng._self_attn_fwd(p, x, pos, S, B, S, H)
+        y2, sf = eng._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm2", y1, 1e-5)
+        d1 = eng._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm2", dy, sf)
+        dx = eng._self_attn_bwd(p, d1, sa, None, B, S, H)
+        eng._join()
+        m = lambda site, rows, N: k.dropout_mask(rows, N, eng._drop(site)).float()
+        mp = m(f"{p}.self_attn.probs", B * H * S, S).view(B, H, S, S)
+        m1 = m(f"{p}.norm1.in", B * S, D).view(B, S, D)
+        mh = m(f"{p}.linear1.hidden", B * S, 2048).view(B, S, 2048)
+        m2 = m(f"{p}.norm2.in", B * S, D).view(B, S, D)
+    finally:
+        eng.train_mode = False
+    sc = 1.0 / 0.9
+    Pl = {n: t.clone().requires_grad_(True) for n, t in Pd.items() if n.startswith(p) and t.dtype.is_floating_point}
+    # each sub-block gets the engine's own bf16 input (as tests/test_blocks_gpu.py does: ReLU gates flip under input noise)
+    xf = x.float().view(B, S, D).requires_grad_(True)
+    qk = xf + pos.float()[None]
+    Wi, bi = Pl[f"{p}.self_attn.in_proj_weight"], Pl[f"{p}.self_attn.in_proj_bias"]
+    q = F.linear(qk, Wi[:D], bi[:D]).view(B, S, H, D // H).transpose(1, 2) * (D // H) ** -0.5
+    kk = F.linear(qk, Wi[D:2 * D], bi[D:2 * D]).view(B, S, H, D // H).transpose(1, 2)
+    v = F.linear(xf, Wi[2 * D:], bi[2 * D:]).view(B, S, H, D // H).transpose(1, 2)
+    a = ((torch.softmax(q @ kk.transpose(-1, -2), -1) * mp * sc) @ v).transpose(1, 2).reshape(B, S, D)
+    a = F.linear(a, Pl[f"{p}.self_attn.out_proj.weight"], Pl[f"{p}.self_attn.out_proj.bias"])
+    h1 = F.layer_norm(xf + a * m1 * sc, (D,), Pl[f"{p}.norm1.weight"], Pl[f"{p}.norm1.bias"], 1e-5)
+    h1.backward(d1.float().view(B, S, D))                      # upstream gradient = the engine's own FFN-block output
+    y1f = y1.float().view(B, S, D).requires_grad_(True)
+    f = F.relu(F.linear(y1f, Pl[f"{p}.linear1.weight"], Pl[f"{p}.linear1.bias"])) * mh * sc
+    f = F.linear(f, Pl[f"{p}.linear2.weight"], Pl[f"{p}.linear2.bias"])
+    out = F.layer_norm(y1f + f * m2 * sc, (D,), Pl[f"{p}.norm2.weight"], Pl[f"{p}.norm2.bias"], 1e-5)
+    out.backward(dy.float().view(B, S, D))
+    TOL = 1.5e-2
+    assert _rel(y1.view(B, S, D), h1) < TOL
+    assert _rel(y2.view(B, S, D), out) < TOL
+    assert _rel(d1.view(B, S, D), y1f.grad) < TOL
+    assert _rel(dx.view(B, S, D), xf.grad) < TOL
+    bad = []
+    for n, t in Pl.items():
+        if t.grad is not None and n in eng.G and t.grad.norm() > 1e-6:
+            r = _rel(eng.G[n], t.grad)
+            if r > TOL:
+                bad.append((n, r))
+    assert not bad, bad
+
+
+def test_train_mode_step_runs_and_eval_is_unchanged(ctx, cuda):
+    """model.train(): a full step with every dropout site active gives a finite loss that changes from step to step
+    (new masks) and finite gradients; model.eval() afterwards reproduces the dropout-free loss bit for bit."""
+    from oracle.make_golden import make_inputs
+    model, eng, Pd = ctx
+    images, qids, ans, targets = make_inputs(3, 192, 256, 8, 5, 55, ["CocoCaptioning", "CocoVqa", "CocoDetection"])
+    dt = [{kk: (v.to(cuda) if torch.is_tensor(v) else v) for kk, v in t.items()} for t in targets]
+    b = (images.to(cuda), qids.to(cuda), ans.to(cuda), dt)
+
+    def step():
+        for p_ in model.parameters():
+            p_.grad = None
+        loss = model(*b)
+        loss.backward()
+        torch.cuda.synchronize()
+        gn = sum(p_.grad.float().norm().item() ** 2 for p_ in model.parameters() if p_.grad is not None) ** 0.5
+        return loss.item(), gn
+
+    model.eval()
+    l_eval, g_eval = step()
+    model.train()
+    try:
+        l1, g1 = step()
+        l2, g2 = step()
+    finally:
+        model.eval()
+    l_eval2, _ = step()
+    for v_ in (l1, l2, g1, g2):
+        assert v_ == v_ and abs(v_) < 1e6
+    assert l1 != l2 and l1 != l_eval
+    assert abs(l1 - l_eval) < 0.5 * abs(l_eval) and abs(l2 - l_eval) < 0.5 * abs(l_eval)
+    assert 0.2 * g_eval < g1 < 5 * g_eval
+    assert abs(l_eval2 - l_eval) <= 1e-6 * abs(l_eval)

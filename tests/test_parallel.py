@@ -85,6 +85,7 @@ def _nccl_worker(rank, world, port, out):
     model = GPV(load_config().model, vocab=vocab, vocab_embed=P["answer_head.vocab_embed"].numpy())
     model.load_state_dict(P, strict=True)
     model.to(dev)
+    model.eval()
     broadcast_parameters(model)
     images, qids, ans, targets = make_inputs(2, 192, 256, 6, 5, 100 + rank, ["CocoCaptioning", "CocoVqa"])
     dt = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]

@@ -19,6 +19,7 @@ HungarianMatcher matcher.py:32-77, and autograd's backward of all of it.
 """
 import contextlib
 import math
+import re
 import zlib
 
 import torch
@@ -33,6 +34,7 @@ RELU, GELU, SIGMOID = k.ACT_RELU, k.ACT_GELU, k.ACT_SIGMOID
 MASK_RELU, GRAD_GELU = k.AUX_RELU_MASK, k.AUX_GELU_GRAD
 TASK_LOSS = {"CocoCaptioning": "loss_caption", "CocoVqa": "loss_vqa", "CocoClassification": "loss_cls"}
 BB = "detr.backbone.0.body"
+_QKV_GROUP = re.compile(r"(co_att_transformer\.\d+)\.qkv([12])\.weight")
 
 
 def sine_position_table(H, W, device, num_pos_feats=128, temperature=10000.0):
@@ -105,6 +107,7 @@ class Engine:
                        "co_att_l": float(co.v_attention_probs_dropout_prob), "co_att_v": float(co.attention_probs_dropout_prob),
                        "co_hid_l": float(co.v_hidden_dropout_prob), "co_hid_v": float(co.hidden_dropout_prob)}
         self.drop_seed = torch.zeros(1, dtype=torch.int64, device=device)     # training-step counter read by the kernels
+        self.frozen = set()                                   # names with requires_grad = False: no weight / bias gradient kernels
         self.concurrent = True                                # run independent branches on side streams (lanes)
         self._lanes, self._dirty, self._keep = {}, set(), []
 
@@ -313,6 +316,17 @@ class Engine:
             return None
         return k.Drop(self.drop_seed, zlib.crc32(site.encode()), p)
 
+    def _trains(self, name):
+        """False when the parameter (or, for the packed co-attention q/k/v groups, its first member) is frozen."""
+        if not self.frozen:
+            return True
+        if name in self.frozen:
+            return False
+        m = _QKV_GROUP.match(name)
+        if m:
+            return f"{m.group(1)}.biattention.query{m.group(2)}.weight" not in self.frozen
+        return True
+
     def _ln_bwd(self, dy, x, st, gamma, dgamma, dbeta, drop):
         """(dx, dx_masked): LayerNorm backward of y = LN(res + dropout(f)); dx_masked is the gradient of f's output."""
         if drop is None:
@@ -355,10 +369,11 @@ class Engine:
                  bias=True, alpha=1.0):
         """dW += dy^T x, db += colsum(dy), returns dx = (dy W + residual) (*) mask."""
         g = gkey or name
-        with self._aside(dy, x):
-            k.linear_wgrad(dy, x, self.G[g + ".weight"].view(dy.shape[1], -1))
-            if bias:
-                k.colsum(dy, self.G[g + ".bias"])
+        if self._trains(g + ".weight"):
+            with self._aside(dy, x):
+                k.linear_wgrad(dy, x, self.G[g + ".weight"].view(dy.shape[1], -1))
+                if bias:
+                    k.colsum(dy, self.G[g + ".bias"])
         if need_dx:
             return k.linear_dgrad(dy, self.W[wkey or (name + ".weight")], aux=aux, aux_mode=aux_mode, residual=residual, alpha=alpha)
         return None
@@ -412,8 +427,9 @@ class Engine:
         # conv3 (1x1)
         dh2 = k.linear_dgrad(dpre2, W[p + ".conv3.weight"][0], aux=h2f, aux_mode=MASK_RELU)
         with self._aside(dpre):
-            k.linear_wgrad(dpre2, h2f, G[p + ".conv3.weight"].view(planes * 4, planes), rowscale=sc[p + ".bn3"])
-            if ds:
+            if self._trains(p + ".conv3.weight"):
+                k.linear_wgrad(dpre2, h2f, G[p + ".conv3.weight"].view(planes * 4, planes), rowscale=sc[p + ".bn3"])
+            if ds and self._trains(p + ".downsample.0.weight"):
                 gds = G[p + ".downsample.0.weight"].view(1, planes * 4, inp)
                 if s == 1:
                     k.linear_wgrad(dpre2, xf, gds[0], rowscale=sc[p + ".downsample.1"])
@@ -422,16 +438,18 @@ class Engine:
         # conv2 (3x3, stride s)
         dh2 = dh2.view(h2.shape)
         dh1 = conv_dgrad(dh2, W[p + ".conv2.weight"], ksize=3, stride=s, in_hw=(H, Wd), aux=h1, aux_mode=MASK_RELU)
-        with self._aside(dh2):
-            k.conv_wgrad(dh2, h1, self.Gp[p + ".conv2.weight"], ksize=3, stride=s, rowscale=sc[p + ".bn2"])
+        if self._trains(p + ".conv2.weight"):
+            with self._aside(dh2):
+                k.conv_wgrad(dh2, h1, self.Gp[p + ".conv2.weight"], ksize=3, stride=s, rowscale=sc[p + ".bn2"])
         # identity / downsample branch
         if ds:
             didn = conv_dgrad(dpre, W[p + ".downsample.0.weight"], ksize=1, stride=s, in_hw=(H, Wd)) if need_dx else None
         else:
             didn = dpre
         # conv1 (1x1): dx = (dh1 W1 + didn) * relu'(x)  -> already the masked gradient of the previous block
-        with self._aside(dh1):
-            k.linear_wgrad(dh1.view(-1, planes), xf, G[p + ".conv1.weight"].view(planes, inp), rowscale=sc[p + ".bn1"])
+        if self._trains(p + ".conv1.weight"):
+            with self._aside(dh1):
+                k.linear_wgrad(dh1.view(-1, planes), xf, G[p + ".conv1.weight"].view(planes, inp), rowscale=sc[p + ".bn1"])
         dx = None
         if need_dx:
             dx = k.linear_dgrad(dh1.view(-1, planes), W[p + ".conv1.weight"][0], residual=didn.view(-1, inp), aux=xf,
@@ -490,13 +508,14 @@ class Engine:
                         drop=self._drop(f"{p}.{attn}.probs"))
         wi = W[f"{p}.{attn}.in_proj_weight"]
         gw, gb = G[f"{p}.{attn}.in_proj_weight"], G[f"{p}.{attn}.in_proj_bias"]
-        with self._aside(dqkv):
-            k.colsum(dqkv, gb)
-            if not has_pos:
-                k.linear_wgrad(dqkv, x, gw)
-            else:
-                k.linear_wgrad(dqkv[:, :2 * D], qk_in, gw[:2 * D])
-                k.linear_wgrad(dqkv[:, 2 * D:], x, gw[2 * D:])
+        if self._trains(f"{p}.{attn}.in_proj_weight"):
+            with self._aside(dqkv):
+                k.colsum(dqkv, gb)
+                if not has_pos:
+                    k.linear_wgrad(dqkv, x, gw)
+                else:
+                    k.linear_wgrad(dqkv[:, :2 * D], qk_in, gw[:2 * D])
+                    k.linear_wgrad(dqkv[:, 2 * D:], x, gw[2 * D:])
         if not has_pos:
             return k.linear_dgrad(dqkv, wi, residual=dpre)
         dx = k.linear_dgrad(dqkv[:, 2 * D:], wi[2 * D:], residual=dpre)
@@ -552,15 +571,16 @@ class Engine:
         k.attention_bwd(q, kv[:, :D], kv[:, D:], o, do, lse, dq, dkv[:, :D], dkv[:, D:], B=B, H=H, Sq=Sq, Sk=Sk, dh=dh,
                         scale=dh ** -0.5, key_mask=kmask, drop=self._drop(f"{p}.multihead_attn.probs"))
         wi, gw, gb = W[a + ".in_proj_weight"], G[a + ".in_proj_weight"], G[a + ".in_proj_bias"]
-        with self._aside(dq, dkv):
-            k.colsum(dq, gb[:D])
-            k.colsum(dkv, gb[D:])
-            k.linear_wgrad(dq, q_in, gw[:D])
-            if kmem is vmem:
-                k.linear_wgrad(dkv, kmem, gw[D:])
-            else:
-                k.linear_wgrad(dkv[:, :D], kmem, gw[D:2 * D])
-                k.linear_wgrad(dkv[:, D:], vmem, gw[2 * D:])
+        if self._trains(a + ".in_proj_weight"):
+            with self._aside(dq, dkv):
+                k.colsum(dq, gb[:D])
+                k.colsum(dkv, gb[D:])
+                k.linear_wgrad(dq, q_in, gw[:D])
+                if kmem is vmem:
+                    k.linear_wgrad(dkv, kmem, gw[D:])
+                else:
+                    k.linear_wgrad(dkv[:, :D], kmem, gw[D:2 * D])
+                    k.linear_wgrad(dkv[:, D:], vmem, gw[2 * D:])
         if kmem is vmem:
             dmem = k.linear_dgrad(dkv, wi[D:], residual=dmem)
         else:

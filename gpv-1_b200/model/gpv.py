@@ -272,9 +272,24 @@ class GPV(nn.Module):
         if not eng.unit_upstream_grad:
             eng.grad_arena.mul_(g)
         for n, p in self._live:
+            if not p.requires_grad:                   # frozen (train_distr.py:136-140 freeze_detr_params): autograd gives no grad
+                p.grad = None
+                continue
             gv = eng.G[n]
             if p.grad is None or p.grad.data_ptr() != gv.data_ptr():
                 p.grad = gv
+
+    def sync_trainable(self):
+        """Tell the engine which parameters are frozen (`requires_grad = False`, e.g. after the reference's
+        freeze_detr_params for the first training phase, train_distr.py:136-140,160-161): their weight- and bias-gradient
+        kernels are skipped.  Called from forward; cheap (a tuple compare) when nothing changed."""
+        eng = self.engine
+        key = tuple(p.requires_grad for _, p in self._live)
+        if key != getattr(self, "_trainable_key", None):
+            eng.frozen = {n for n, p in self._live if not p.requires_grad}
+            self._trainable_key = key
+            if self._captured is not None:
+                self._captured = None                 # the captured backward contains the old set of gradient kernels
 
     def load_pretr_detr(self):
         """gpv.py:122-135: copy same-shaped tensors of a DETR checkpoint under the `detr.` prefix."""
@@ -333,6 +348,7 @@ class GPV(nn.Module):
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, images, queries, answer_token_ids, targets=None, vocab_mask=None):
         eng = self.engine
+        self.sync_trainable()
         # nn.Dropout semantics: masks in train(), identity in eval().  Generation (no answer_token_ids) always runs the
         # eval arithmetic: the reference only generates under model.eval() (inference.py:63, metrics.py)
         eng.train_mode = bool(self.training) and answer_token_ids is not None

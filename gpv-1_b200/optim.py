@@ -82,7 +82,7 @@ class ClipAdamW:
         hyper-parameters (configs/exp/gpv.yaml:130-144) unless overridden."""
         eng = model.engine
         params = dict(model.named_parameters())
-        named = [(n, params[n].data, eng.G[n]) for n in eng.live_names]
+        named = [(n, params[n].data, eng.G[n]) for n in eng.live_names if params[n].requires_grad]   # torch skips params without grad
         if training_cfg is not None:
             for key in ("lr", "lr_backbone", "weight_decay", "clip_max_norm"):
                 if key not in kw and hasattr(training_cfg, key):

@@ -37,6 +37,14 @@ GPV_DEVINL void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uin
 
 GPV_DEVINL uint32_t lds32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
+// B fragment (k16 x n8) of mma.m16n8k16 from a ROW-major [k][n] shared-memory matrix X (row stride LD elements, rows
+// 16-byte aligned): ldmatrix.trans hands lane (g, t) the pair X[k0 + 2t .. 2t+1][n0 + g] (b0) and the same for k + 8 (b1),
+// which is exactly the "col" operand layout -- no transposed copy of K / V / Q / dO in shared memory.
+GPV_DEVINL void ldsm_bt(const bf16* X, int LD, int k0, int n0, int lane, uint32_t& b0, uint32_t& b1) {
+  const uint32_t a = smem_u32(X + (k0 + (lane & 15)) * LD + n0);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(a));
+}
+
 // Stage rows [0,S) x DH of a token-major global matrix into smem row-major (stride LD) and optionally transposed
 // (dst_t[d][s], stride LDT).  Rows >= S are zero-filled up to Sp.
 template <int DH>
@@ -75,15 +83,14 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
   const int Sq = p.Sq, Sk = p.Sk;
   const int Sqp = (Sq + 15) & ~15, Skp = (Sk + 63) & ~63;
   constexpr int LD = DH + 8;
-  const int LDT = Skp + 8;
   bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
   bf16* Ks = Qs + Sqp * LD;
-  bf16* Vt = Ks + Skp * LD;
-  uint8_t* msk = reinterpret_cast<uint8_t*>(Vt + DH * LDT);
+  bf16* Vs = Ks + Skp * LD;
+  uint8_t* msk = reinterpret_cast<uint8_t*>(Vs + Skp * LD);
 
   stage<DH>(p.q + b * p.bsq + h * DH, p.ldq, Sq, Sqp, Qs, LD, nullptr, 0);
   stage<DH>(p.k + b * p.bsk + h * DH, p.ldk, Sk, Skp, Ks, LD, nullptr, 0);
-  stage<DH>(p.v + b * p.bsv + h * DH, p.ldv, Sk, Skp, nullptr, 0, Vt, LDT);
+  stage<DH>(p.v + b * p.bsv + h * DH, p.ldv, Sk, Skp, Vs, LD, nullptr, 0);
   for (int j = threadIdx.x; j < Skp; j += blockDim.x)
     msk[j] = (j >= Sk) ? 1 : (p.kmask ? p.kmask[(long long)b * Sk + j] : 0);
   __syncthreads();
@@ -165,8 +172,9 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
         pa[3] = pack_bf16x2(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
 #pragma unroll
         for (int nd = 0; nd < DH / 8; ++nd) {
-          const bf16* vr = Vt + (nd * 8 + g) * LDT + kb + k2 * 16 + 2 * t;
-          mma16816(o[nd], pa, lds32(vr), lds32(vr + 8));
+          uint32_t b0, b1;
+          ldsm_bt(Vs, LD, kb + k2 * 16, nd * 8, lane, b0, b1);
+          mma16816(o[nd], pa, b0, b1);
         }
       }
     }
@@ -194,28 +202,25 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
 // Pass 1 (warp owns 16 queries): D = rowsum(dO*O), dQ = scale * [P o (dO V^T - D)] K
 // Pass 2 (warp owns 16 keys):    dV = P^T dO,      dK = scale * [P o (dO V^T - D)]^T Q
 template <int DH, int NT, bool DROP>
-__global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(NT, (DH <= 32) ? 2 : 1) attn_bwd_kernel(const AttnParams p) {
   pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int Sq = p.Sq, Sk = p.Sk;
   const int Sqp = (Sq + 63) & ~63, Skp = (Sk + 63) & ~63;
   constexpr int LD = DH + 8;
-  const int LDTq = Sqp + 8, LDTk = Skp + 8;
+
   bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
   bf16* dOs = Qs + Sqp * LD;
   bf16* Ks = dOs + Sqp * LD;
   bf16* Vs = Ks + Skp * LD;
-  bf16* Kt = Vs + Skp * LD;
-  bf16* Qt = Kt + DH * LDTk;
-  bf16* dOt = Qt + DH * LDTq;
-  float* lse_s = reinterpret_cast<float*>(dOt + DH * LDTq);
+  float* lse_s = reinterpret_cast<float*>(Vs + Skp * LD);
   float* D_s = lse_s + Sqp;
   uint8_t* msk = reinterpret_cast<uint8_t*>(D_s + Sqp);
 
-  stage<DH>(p.q + ((long long)b * Sq) * p.ldq + h * DH, p.ldq, Sq, Sqp, Qs, LD, Qt, LDTq);
-  stage<DH>(p.d_o + ((long long)b * Sq) * p.lddo + h * DH, p.lddo, Sq, Sqp, dOs, LD, dOt, LDTq);
-  stage<DH>(p.k + ((long long)b * Sk) * p.ldk + h * DH, p.ldk, Sk, Skp, Ks, LD, Kt, LDTk);
+  stage<DH>(p.q + ((long long)b * Sq) * p.ldq + h * DH, p.ldq, Sq, Sqp, Qs, LD, nullptr, 0);
+  stage<DH>(p.d_o + ((long long)b * Sq) * p.lddo + h * DH, p.lddo, Sq, Sqp, dOs, LD, nullptr, 0);
+  stage<DH>(p.k + ((long long)b * Sk) * p.ldk + h * DH, p.ldk, Sk, Skp, Ks, LD, nullptr, 0);
   stage<DH>(p.v + ((long long)b * Sk) * p.ldv + h * DH, p.ldv, Sk, Skp, Vs, LD, nullptr, 0);
   for (int j = threadIdx.x; j < Skp; j += blockDim.x)
     msk[j] = (j >= Sk) ? 1 : (p.kmask ? p.kmask[(long long)b * Sk + j] : 0);
@@ -314,8 +319,9 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
         pa[3] = pack_bf16x2(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
 #pragma unroll
         for (int nd = 0; nd < DH / 8; ++nd) {
-          const bf16* kr = Kt + (nd * 8 + g) * LDTk + kb + k2 * 16 + 2 * t;
-          mma16816(dq[nd], pa, lds32(kr), lds32(kr + 8));
+          uint32_t b0, b1;
+          ldsm_bt(Ks, LD, kb + k2 * 16, nd * 8, lane, b0, b1);
+          mma16816(dq[nd], pa, b0, b1);
         }
       }
     }
@@ -395,10 +401,11 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
         sa[3] = pack_bf16x2(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
 #pragma unroll
         for (int nd = 0; nd < DH / 8; ++nd) {
-          const bf16* dr = dOt + (nd * 8 + g) * LDTq + qb + k2 * 16 + 2 * t;
-          const bf16* qr = Qt + (nd * 8 + g) * LDTq + qb + k2 * 16 + 2 * t;
-          mma16816(dv[nd], pa, lds32(dr), lds32(dr + 8));
-          mma16816(dk[nd], sa, lds32(qr), lds32(qr + 8));
+          uint32_t b0, b1, c0, c1;
+          ldsm_bt(dOs, LD, qb + k2 * 16, nd * 8, lane, b0, b1);
+          ldsm_bt(Qs, LD, qb + k2 * 16, nd * 8, lane, c0, c1);
+          mma16816(dv[nd], pa, b0, b1);
+          mma16816(dk[nd], sa, c0, c1);
         }
       }
     }
@@ -424,12 +431,12 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const AttnParams p) {
 }
 
 static size_t fwd_smem(int DH, int Sq, int Sk) {
-  const int Sqp = (Sq + 15) & ~15, Skp = (Sk + 63) & ~63, LD = DH + 8, LDT = Skp + 8;
-  return (size_t)(Sqp * LD + Skp * LD + DH * LDT) * 2 + Skp + 16;
+  const int Sqp = (Sq + 15) & ~15, Skp = (Sk + 63) & ~63, LD = DH + 8;
+  return (size_t)(Sqp * LD + 2 * Skp * LD) * 2 + Skp + 16;
 }
 static size_t bwd_smem(int DH, int Sq, int Sk) {
   const int Sqp = (Sq + 63) & ~63, Skp = (Sk + 63) & ~63, LD = DH + 8;
-  return (size_t)(2 * Sqp * LD + 2 * Skp * LD + DH * (Skp + 8) + 2 * DH * (Sqp + 8)) * 2 + (size_t)Sqp * 8 + Skp + 16;
+  return (size_t)(2 * Sqp * LD + 2 * Skp * LD) * 2 + (size_t)Sqp * 8 + Skp + 16;
 }
 
 template <int DH>
@@ -439,9 +446,10 @@ static int launch_attn(const AttnParams& p, bool bwd, cudaStream_t st) {
     set_last_error("attention: Sq=%d Sk=%d dh=%d needs %zu bytes of shared memory (> 227 KB)", p.Sq, p.Sk, DH, smem);
     return GPV_ERR_ARG;
   }
-  // 16 query (or key) rows per warp and pass: 12 warps cover the 300-token encoder maps in two rounds; the wide heads
-  // (d_h >= 48) keep 8 warps so that the backward's accumulators stay in registers.
-  constexpr int NTF = 256, NTB = (DH <= 32) ? 384 : 256;
+  // 16 query (or key) rows per warp and pass, 8 warps per CTA.  With K / V / Q / dO kept row-major only (ldmatrix.trans
+  // builds the transposed operand fragments) the encoder's S = 300, d_h = 32 backward needs 105 KB of shared memory and
+  // <= 128 registers, so two CTAs share an SM and the 256 (batch, head) CTAs of a B = 32 step run in one wave.
+  constexpr int NTF = 256, NTB = 256;
   const bool drop = p.drop.seed != nullptr;
   auto kern = bwd ? (drop ? attn_bwd_kernel<DH, NTB, true> : attn_bwd_kernel<DH, NTB, false>)
                   : (drop ? attn_fwd_kernel<DH, NTF, true> : attn_fwd_kernel<DH, NTF, false>);

@@ -152,7 +152,7 @@ GPV_DEVINL bool tile_row(const KParams& p, const Work& wk, int r, long long* pix
 
 // Epilogue variant F: -1 = every flag read from KParams at run time (any combination, any output type);
 // F >= 0 = compile-time flags of the bf16 coalesced path (bit 0 bias, bit 1 bf16 residual, bits 2-3 activation,
-// bits 4-5 aux mode, bit 6 second output D2), so the hot variants carry no flag tests.
+// bits 4-5 aux mode, bit 6 second output D2, bits 7-8 dropout mode), so the hot variants carry no flag tests.
 template <int F>
 struct EpiFlags {
   GPV_DEVINL static bool bias(const KParams& p) { if constexpr (F < 0) return p.bias != nullptr; else return (F & 1) != 0; }
@@ -162,6 +162,7 @@ struct EpiFlags {
   GPV_DEVINL static bool d2(const KParams& p) { if constexpr (F < 0) return p.D2 != nullptr; else return (F & 64) != 0; }
   GPV_DEVINL static bool res_fp32(const KParams& p) { if constexpr (F < 0) return p.res_fp32 != 0; else return false; }
   GPV_DEVINL static bool d_fp32(const KParams& p) { if constexpr (F < 0) return p.d_fp32 != 0; else return false; }
+  GPV_DEVINL static int drop(const KParams& p) { if constexpr (F < 0) return p.drop_mode; else return (F >> 7) & 3; }
 };
 
 template <int F>
@@ -220,9 +221,7 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
         if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
     }
   }
-  if constexpr (F < 0) {
-    if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
-  }
+  if (E::drop(p) == 1) epi_dropout(p, v, dkey, pix, nb);
   if (E::res(p)) {
     if (E::res_fp32(p)) {
       const float* rp = reinterpret_cast<const float*>(p.residual) + off_r;
@@ -251,9 +250,7 @@ GPV_DEVINL void epi_chunk(const KParams& p, const uint32_t (&acc)[kChunk], float
     }
   }
   epi_activation<F>(p, v);
-  if constexpr (F < 0) {
-    if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
-  }
+  if (E::drop(p) == 2) epi_dropout(p, v, dkey, pix, nb);
   if (E::aux(p) != GPVB200_AUX_NONE) {
     float a[kChunk];
     if (vec) {
@@ -349,18 +346,14 @@ GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], 
       v[j] += b4[j / 4].x; v[j + 1] += b4[j / 4].y; v[j + 2] += b4[j / 4].z; v[j + 3] += b4[j / 4].w;
     }
   }
-  if constexpr (F < 0) {   // train-mode dropout runs on the run-time-flag kernel only: the hot variants carry none of it
-    if (p.drop_mode == 1) epi_dropout(p, v, dkey, pix, nb);
-  }
+  if (E::drop(p) == 1) epi_dropout(p, v, dkey, pix, nb);   // compile-time in the F >= 0 variants: only the two dropout variants carry it
   if (E::res(p)) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) unpack8(lds128(res_s + so.own[i]), v + 8 * i, true);
   }
   if (E::d2(p)) store_slab(cr.d2, cr.ok, col, v, out_s, so);
   epi_activation<F>(p, v);
-  if constexpr (F < 0) {
-    if (p.drop_mode == 2) epi_dropout(p, v, dkey, pix, nb);
-  }
+  if (E::drop(p) == 2) epi_dropout(p, v, dkey, pix, nb);
   if (E::aux(p) != GPVB200_AUX_NONE) {
     float a[kChunk];
 #pragma unroll
@@ -559,7 +552,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 4; ++i) so.own[i] = 16u * slab_slot(lane, i);
     const long long ldd = p.ldd, ldr = p.ldr, lda = p.ldaux;
-    const uint32_t dkey = (F < 0 && p.drop_mode) ? drop_key(*p.drop.seed, p.drop.site) : 0u;
+    const uint32_t dkey = E::drop(p) ? drop_key(*p.drop.seed, p.drop.site) : 0u;
     int j = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
       const Work wk = decode_work(p, w);
@@ -824,7 +817,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
 
 // Epilogue variants compiled with their flags fixed (the bf16 coalesced path of the hot layers); anything else runs
 // the run-time-flag kernel (F = -1).  bit 0 bias, bit 1 residual, bits 2-3 act, bits 4-5 aux, bit 6 D2.
-#define GPV_EPI_VARIANTS(X) X(0) X(1) X(2) X(3) X(5) X(7) X(16) X(18) X(32) X(73)
+#define GPV_EPI_VARIANTS(X) X(0) X(1) X(2) X(3) X(5) X(7) X(16) X(18) X(32) X(73) X(131) X(261)   // 131 / 261: + dropout before the residual / after ReLU
 
 template <int BN>
 static int launch_bn(int f, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, size_t smem, cudaStream_t st) {
@@ -1128,8 +1121,8 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
 
   cudaStream_t st = (cudaStream_t)stream;
   int f = -1;
-  if (kp.coal && !kp.drop_mode)
-    f = (d->bias ? 1 : 0) | (d->residual ? 2 : 0) | ((d->act & 3) << 2) | ((d->aux_mode & 3) << 4) | (d->D2 ? 64 : 0);
+  if (kp.coal)
+    f = (d->bias ? 1 : 0) | (d->residual ? 2 : 0) | ((d->act & 3) << 2) | ((d->aux_mode & 3) << 4) | (d->D2 ? 64 : 0) | (kp.drop_mode << 7);
   if (BN == 256) return launch_bn<256>(f, ma, mb, kp, smem, st);
   if (BN == 128) return launch_bn<128>(f, ma, mb, kp, smem, st);
   return launch_bn<64>(f, ma, mb, kp, smem, st);

@@ -254,6 +254,7 @@ class GPV(nn.Module):
         """Record the training step for this batch shape into CUDA graphs (model/graph.py).  Later calls of
         forward(images, queries, answer_token_ids, targets) with the same shapes replay them."""
         from .graph import CapturedStep
+        self.sync_trainable()
         (images, mask), qids = self._images(images), self._queries(queries)
         if mask is not None:
             raise NotImplementedError("capture_step needs an unpadded batch (one image size): the padding mask is per batch")

@@ -439,6 +439,20 @@ static size_t bwd_smem(int DH, int Sq, int Sk) {
   return (size_t)(2 * Sqp * LD + 2 * Skp * LD) * 2 + (size_t)Sqp * 8 + Skp + 16;
 }
 
+template <int DH, int NT>
+static int launch_attn_nt(const AttnParams& p, bool bwd, size_t smem, cudaStream_t st) {
+  const bool drop = p.drop.seed != nullptr;
+  auto kern = bwd ? (drop ? attn_bwd_kernel<DH, NT, true> : attn_bwd_kernel<DH, NT, false>)
+                  : (drop ? attn_fwd_kernel<DH, NT, true> : attn_fwd_kernel<DH, NT, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_last_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return GPV_ERR_CUDA;
+  }
+  launch_k(kern, dim3(p.B * p.H), dim3(NT), smem, st, p);
+  return check_launch(bwd ? "attn_bwd_kernel" : "attn_fwd_kernel");
+}
+
 template <int DH>
 static int launch_attn(const AttnParams& p, bool bwd, cudaStream_t st) {
   const size_t smem = bwd ? bwd_smem(DH, p.Sq, p.Sk) : fwd_smem(DH, p.Sq, p.Sk);
@@ -446,20 +460,14 @@ static int launch_attn(const AttnParams& p, bool bwd, cudaStream_t st) {
     set_last_error("attention: Sq=%d Sk=%d dh=%d needs %zu bytes of shared memory (> 227 KB)", p.Sq, p.Sk, DH, smem);
     return GPV_ERR_ARG;
   }
-  // 16 query (or key) rows per warp and pass, 8 warps per CTA.  With K / V / Q / dO kept row-major only (ldmatrix.trans
-  // builds the transposed operand fragments) the encoder's S = 300, d_h = 32 backward needs 105 KB of shared memory and
-  // <= 128 registers, so two CTAs share an SM and the 256 (batch, head) CTAs of a B = 32 step run in one wave.
-  constexpr int NTF = 256, NTB = 256;
-  const bool drop = p.drop.seed != nullptr;
-  auto kern = bwd ? (drop ? attn_bwd_kernel<DH, NTB, true> : attn_bwd_kernel<DH, NTB, false>)
-                  : (drop ? attn_fwd_kernel<DH, NTF, true> : attn_fwd_kernel<DH, NTF, false>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_last_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    return GPV_ERR_CUDA;
-  }
-  launch_k(kern, dim3(p.B * p.H), dim3(bwd ? NTB : NTF), smem, st, p);
-  return check_launch(bwd ? "attn_bwd_kernel" : "attn_fwd_kernel");
+  // 16 query (or key) rows per warp and pass.  Long sequences: 8 warps per CTA; with K / V / Q / dO kept row-major only
+  // (ldmatrix.trans builds the transposed operand fragments) the encoder's S = 300, d_h = 32 backward needs 105 KB of
+  // shared memory and <= 128 registers, so two CTAs share an SM and the 256 (batch, head) CTAs of a B = 32 step run in
+  // one wave.  Short sequences (co-attention 100 x 20, text decoder 20 x 120): 4 warps already cover every row block,
+  // and the smaller CTAs fit 2-3 per SM by registers (the d_h >= 48 backward uses 160-240 registers per thread).
+  const int rows = (p.Sq > p.Sk ? p.Sq : p.Sk);
+  if (rows <= 64 || (DH >= 48 && rows <= 128)) return launch_attn_nt<DH, 128>(p, bwd, smem, st);
+  return launch_attn_nt<DH, 256>(p, bwd, smem, st);
 }
 
 static int dispatch(const AttnParams& p, int dh, bool bwd, cudaStream_t st) {

@@ -188,28 +188,26 @@ __global__ void maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
     pth /= Wo;
     const int ho = (int)(pth % Ho);
     const int b = (int)(pth / Ho);
-    float m[8];
+    // max of bf16 values is exact in bf16: packed __hmax2, no unpacking
+    __nv_bfloat162 m[4];
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < 4; ++j) m[j] = ninf;
     for (int r = 0; r < 3; ++r) {
       const int h = 2 * ho - 1 + r;
       if (h < 0 || h >= H) continue;
       for (int s = 0; s < 3; ++s) {
         const int w = 2 * wo - 1 + s;
         if (w < 0 || w >= W) continue;
-        const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * C + c * 8);
-        const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * C + c * 8));
+        const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(ww[j]);
-          m[2 * j] = fmaxf(m[2 * j], f.x);
-          m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
-        }
+        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], e[j]);
       }
     }
     uint4 o;
-    o.x = pack_bf16x2(m[0], m[1]); o.y = pack_bf16x2(m[2], m[3]);
-    o.z = pack_bf16x2(m[4], m[5]); o.w = pack_bf16x2(m[6], m[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&m[0]); o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&m[2]); o.w = *reinterpret_cast<uint32_t*>(&m[3]);
     *reinterpret_cast<uint4*>(y + (((long long)b * Ho + ho) * Wo + wo) * C + c * 8) = o;
   }
 }

@@ -103,3 +103,25 @@ def test_train_loop_two_phases_and_resume(tmp_path):
     assert loss1 is not None and loss2 is not None and np.isfinite(loss1) and np.isfinite(loss2)
     assert any("Loading checkpoint at the end of epoch 0" in l for l in logs)
     assert sum("total_loss" in l for l in logs) == 6
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_yields_the_same_batches():
+    """data.DevicePrefetcher (double-buffered H2D on a copy stream) hands GPV.forward device tensors equal to the host
+    batches, in order, across buffer reuse."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gpv1_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    host = []
+    for i in range(5):
+        imgs = torch.randn(2, 3, 32, 48, generator=g)
+        host.append((imgs, torch.randint(0, 100, (2, 6), generator=g), [{"task": "CocoVqa", "boxes": torch.rand(3, 4, generator=g)} for _ in range(2)]))
+    got = []
+    for imgs, q, tg in DevicePrefetcher(host, "cuda:0"):
+        assert imgs.is_cuda and q.is_cuda and tg[0]["boxes"].is_cuda and tg[0]["task"] == "CocoVqa"
+        got.append((imgs.clone(), q.clone(), tg[1]["boxes"].clone()))       # consumed on the compute stream, like a step would
+    torch.cuda.synchronize()
+    assert len(got) == 5
+    for (hi, hq, ht), (di, dq, db) in zip(host, got):
+        assert torch.equal(hi, di.cpu()) and torch.equal(hq, dq.cpu()) and torch.equal(ht[1]["boxes"], db.cpu())

@@ -223,6 +223,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: keep rank 0's stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from gpv1_b200 import _C
@@ -403,6 +405,11 @@ def main():
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = gf_all * B / ms_step              # TFLOP/s per GPU: GFLOP/sample * samples / ms
+    traffic = None
+    try:                                     # DRAM bytes of one step from the committed ncu pass (profiles/step_traffic.json)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "step_traffic.json")))["dram_bytes_per_step"]
+    except (OSError, KeyError, ValueError):
+        pass
     cpu = None
     if not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_steps(steps=2, warmup=1)
@@ -427,8 +434,10 @@ def main():
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
                           "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                         "what": f"whole step: {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd ({gf_fwd:.1f} fwd) x {B} samples / step time; peak = "
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "what": f"whole step (1006 launches, 75 % of it the tcgen05 GEMM kernel): {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd "
+                                 f"({gf_fwd:.1f} fwd) x {B} samples / step time; traffic = DRAM bytes of one step summed over its launches "
+                                 "by ncu (profiles/step_traffic.json; writes still in L2 at kernel end are not counted); peak = "
                                  + ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)")},
             "cpu_baseline": cpu}
     if sync is not None:

@@ -14,6 +14,6 @@ cat $out/${tag}_bench.json
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --breakdown $out/${tag}_breakdown.json > $out/${tag}_bench_eager.json 2>> $out/${tag}_bench.err
 echo "breakdown exit $?"
 timeout 300 python tools/prof_gemm.py > $out/${tag}_gemm_shapes.txt 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/${tag}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4000 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 1 --profiling --no-graph > $out/${tag}_ncu_bench.log 2>&1
 echo "ncu exit $?"

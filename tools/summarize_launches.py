@@ -1,31 +1,52 @@
-"""Developer tool: aggregate an ncu `--metrics gpu__time_duration.sum --csv` launch list over the LAST training step
-(one stem-to-stem period at the end of the list) into a per-kernel table (markdown)."""
+"""Developer tool: aggregate an ncu `--metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv`
+launch list over the LAST training step (one stem-to-stem period at the end of the list) into a per-kernel markdown
+table; with `--json` also prints the step totals (kernel time, DRAM bytes) as one JSON line."""
 import collections
 import csv
+import json
 import re
 import sys
 
+UNIT = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
-def main(path):
+
+def main(path, as_json=False):
     with open(path) as f:
         rows = list(csv.DictReader([l for l in f if l.startswith('"')]))
-    idx = [i for i, x in enumerate(rows) if "stem_im2col" in x["Kernel Name"]]
+    # one record per launch ID, metrics merged
+    launches = collections.OrderedDict()
+    for x in rows:
+        rec = launches.setdefault(x["ID"], {"name": x["Kernel Name"], "us": 0.0, "rd": 0.0, "wr": 0.0})
+        v = float(x["Metric Value"].replace(",", "")) * UNIT.get(x["Metric Unit"], 1.0)
+        if x["Metric Name"].startswith("gpu__time_duration"):
+            rec["us"] = v
+        elif "bytes_read" in x["Metric Name"]:
+            rec["rd"] = v
+        elif "bytes_write" in x["Metric Name"]:
+            rec["wr"] = v
+    recs = list(launches.values())
+    idx = [i for i, r in enumerate(recs) if "stem_s2d" in r["name"] or "stem_im2col" in r["name"]]
     # one step = the launches between two consecutive stem kernels (BERT is enqueued ahead of the stem on its own lane)
-    step = rows[-(idx[-1] - idx[-2]):] if len(idx) >= 2 else rows
-    tot = sum(float(x["Metric Value"]) for x in step) / 1e3
+    step = recs[-(idx[-1] - idx[-2]):] if len(idx) >= 2 else recs
+    tot = sum(r["us"] for r in step)
     agg = collections.OrderedDict()
-    for x in step:
-        n = re.sub(r"\(.*", "", x["Kernel Name"].replace("(int)", ""))[:70]
-        a = agg.setdefault(n, [0, 0.0])
+    for r in step:
+        n = re.sub(r"\(.*", "", r["name"].replace("(int)", "").replace("(bool)", ""))[:70]
+        a = agg.setdefault(n, [0, 0.0, 0.0])
         a[0] += 1
-        a[1] += float(x["Metric Value"]) / 1e3
-    print(f"one step: {len(step)} launches, {tot / 1e3:.2f} ms of kernel time (cold-cache, serialised)\n")
-    print("| kernel | launches | us | us/launch | share |\n|---|---|---|---|---|")
-    for k, (c, us) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        a[1] += r["us"]
+        a[2] += r["rd"] + r["wr"]
+    dram = sum(r["rd"] + r["wr"] for r in step)
+    print(f"one step: {len(step)} launches, {tot / 1e3:.2f} ms of kernel time (cold-cache, serialised), {dram / 1e9:.2f} GB of DRAM traffic\n")
+    print("| kernel | launches | us | us/launch | share | DRAM GB |\n|---|---|---|---|---|---|")
+    for k, (c, us, by) in sorted(agg.items(), key=lambda x: -x[1][1]):
         if us / tot < 0.001:
             continue
-        print(f"| `{k}` | {c} | {us:.0f} | {us / c:.1f} | {100 * us / tot:.1f}% |")
+        print(f"| `{k}` | {c} | {us:.0f} | {us / c:.1f} | {100 * us / tot:.1f}% | {by / 1e9:.3f} |")
+    if as_json:
+        print(json.dumps({"launches": len(step), "kernel_ms": tot / 1e3, "dram_read_bytes": sum(r["rd"] for r in step),
+                          "dram_write_bytes": sum(r["wr"] for r in step)}))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], "--json" in sys.argv)

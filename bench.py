@@ -411,7 +411,7 @@ def main():
     except (OSError, KeyError, ValueError):
         pass
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N = 1 only (torchrun pins OMP threads to 1)
         v, cores, sample, _ = cpu_reference_steps(steps=2, warmup=1)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
     h2d = h_images.numel() * 4 + h_qids.numel() * 8 + h_ans.numel() * 8 + sum(t["boxes"].numel() * 4 + t["labels"].numel() * 8 + t["answer_token_ids"].numel() * 8 for t in targets)

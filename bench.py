@@ -97,6 +97,24 @@ def make_batch(B, seed, V=V_BENCH):
     return images, qids, ans, targets
 
 
+def make_multitask_batches(n, B, seed, V=V_BENCH):
+    """BASELINE.json configs[2] (SURVEY 8d "Config 3"): `n` batches of the multitask stream (gpv1_b200.data.SyntheticMultitask:
+    captioning / VQA / detection / classification drawn 0.35 / 0.35 / 0.15 / 0.15), answers encoded as GPV.encode_answers
+    does for the synthetic vocabulary (`__cls__ w.. __stop__`, padded with `__pad__` to the batch maximum: gpv.py:401-430)."""
+    from gpv1_b200.data import SyntheticMultitask
+    vocab = vocab_list(V)
+    w2i = {w: i for i, w in enumerate(vocab)}
+    out = []
+    for images, qids, targets in SyntheticMultitask(n, B, H_IMG, W_IMG, vocab, seed=seed, Tl=T_L):
+        rows = [[w2i["__cls__"]] + [w2i[w] for w in t.get("answer", "").split()] + [w2i["__stop__"]] for t in targets]
+        S = max(len(r) for r in rows)
+        ans = torch.tensor([r + [w2i["__pad__"]] * (S - len(r)) for r in rows], dtype=torch.long)
+        for b, t in enumerate(targets):
+            t["answer_token_ids"] = ans[b, 1:]
+        out.append((images, qids, ans, targets))
+    return out
+
+
 def vocab_list(V):
     return ["__pad__", "__cls__", "__stop__", "__unk__"] + [f"w{i}" for i in range(V - 4)]
 
@@ -147,7 +165,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_steps(steps, warmup, B_cpu=2, seed=1):
+def cpu_reference_steps(steps, warmup, B_cpu=2, seed=1, workload="configs[1]"):
     """The reference's arithmetic (fp32 oracle port of GPV.forward + criterion + autograd backward) on the host cores.
     Each step is a bounded sample of the workload: B_cpu images of the same shape instead of 32."""
     from oracle import torch_oracle as TO
@@ -161,7 +179,7 @@ def cpu_reference_steps(steps, warmup, B_cpu=2, seed=1):
     specs = gpv_specs(cfg.model, V_BENCH)
     P = TO.make_state([(s.name, s.shape, s.kind) for s in specs], seed=0)
     Pg = {n: (t.requires_grad_(True) if s.kind == "param" and not n.startswith("bert.") else t) for (n, t), s in zip(P.items(), specs)}
-    images, qids, ans, targets = make_batch(B_cpu, seed)
+    images, qids, ans, targets = make_batch(B_cpu, seed) if workload == "configs[1]" else make_multitask_batches(1, B_cpu, seed)[0]
     times = []
     for i in range(warmup + steps):
         for t in Pg.values():
@@ -182,16 +200,64 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 6))
     warmup = max(1, min(args.warmup, 1))
-    sps, cores, sample, ms = cpu_reference_steps(steps, warmup)
+    sps, cores, sample, ms = cpu_reference_steps(steps, warmup, workload=args.workload)
     line = {"impl": "reference", "metric": "samples/sec (img+query fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(32)},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(32, args.workload)},
             "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_name(B):
+def gemm_algorithmic_flop(d):
+    """Algorithmic FLOPs (2 per MAC) of one gpvb200_gemm call from its descriptor (include/gpvb200.h): mode 0 plain /
+    batched GEMM, mode 1 implicit-GEMM convolution (K channels per tap), mode 2 convolution weight gradient (contraction
+    over the pixels).  The stem runs its 7x7x3 = 147-deep contraction as 4 taps x 64 padded channels: counted as 147."""
+    if d.mode == 0:
+        return 2.0 * d.M * d.N * d.K * max(d.batch, 1)
+    pix = float(d.n_img) * d.Ho * d.Wo
+    if d.mode == 1:
+        depth = 147.0 if (d.ntaps == 4 and d.K == 64 and d.N == 64) else float(d.K) * d.ntaps
+        return 2.0 * pix * d.N * depth
+    return 2.0 * pix * d.M * d.N * d.ntaps
+
+
+def trace_gemm_kernel(model, lib, step_fn):
+    """Live, in this run: one extra EAGER step (no graph replay, no concurrent lanes) with every C-ABI call bracketed by
+    CUDA events on its launching stream (_C._Counting.trace).  Returns the tcgen05 GEMM kernel's launch count, summed
+    algorithmic FLOPs and summed launch durations, and the summed duration of every traced launch of the step."""
+    eng = model.engine
+    cap, model._captured = model._captured, None
+    conc, eng.concurrent = eng.concurrent, False
+    hooks, eng.on_stage_done, eng.on_backward_end = (eng.on_stage_done, eng.on_backward_end), None, None   # rank-local: no all-reduce
+    try:
+        step_fn()                                       # eager warm-up (allocator, tensor-map cache)
+        torch.cuda.synchronize()
+        lib.trace = []
+        step_fn()
+        torch.cuda.synchronize()
+        tr, lib.trace = lib.trace, None
+    finally:
+        lib.trace = None
+        model._captured, eng.concurrent = cap, conc
+        eng.on_stage_done, eng.on_backward_end = hooks
+    n = 0
+    flop = ms_gemm = ms_all = 0.0
+    for name, a, e0, e1 in tr:
+        t = e0.elapsed_time(e1)
+        ms_all += t
+        if name == "gpvb200_gemm":
+            n += 1
+            flop += gemm_algorithmic_flop(a[0]._obj)
+            ms_gemm += t
+    return n, flop, ms_gemm, ms_all, len(tr)
+
+
+def workload_name(B, workload="configs[1]"):
+    if workload == "multitask":
+        return (f"configs[2]: batch={B}/GPU CocoCaptioning-shaped synthetic multitask stream (captioning/VQA/detection/classification "
+                f"0.35/0.35/0.15/0.15), 3x{H_IMG}x{W_IMG} + {T_L}-tok prompts, answers padded to the batch maximum (S varies per step), "
+                f"full fwd+bwd with the task-filtered criterion, V={V_BENCH}")
     return f"configs[1]: batch={B}/GPU synthetic 3x{H_IMG}x{W_IMG} + {T_L}-tok prompts + {S_ANS}-tok answers, full fwd+bwd with SetCriterion, V={V_BENCH}"
 
 
@@ -203,6 +269,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--workload", default="configs[1]", choices=["configs[1]", "multitask"],
+                    help="configs[1] (default, the headline): fixed-shape captioning batch; multitask: BASELINE configs[2], the all.yaml task mix")
+    ap.add_argument("--multitask-batches", type=int, default=8, help="distinct batches the multitask workload cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the captured CUDA graphs")
     ap.add_argument("--profiling", action="store_true", help="under ncu only: allow fewer than 3 warm-up steps, skip the e2e loop")
@@ -238,12 +307,20 @@ def main():
     sync = GradSync(model) if world > 1 else None
     broadcast_parameters(model)
 
-    images, qids, ans, targets = make_batch(B, seed=1000 + rank)
+    multitask = args.workload == "multitask"
+    if multitask:
+        batches = make_multitask_batches(args.multitask_batches, B, seed=1000 + rank)
+    else:
+        batches = [make_batch(B, seed=1000 + rank)]
     # resident copies (for `value`) and pinned host copies (for `e2e`)
-    d_images, d_qids, d_ans = images.to(dev), qids.to(dev), ans.to(dev)
-    d_targets = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
-    h_images, h_qids, h_ans = images.pin_memory(), qids.pin_memory(), ans.pin_memory()
-    h_targets = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
+    dev_b = [(i.to(dev), q.to(dev), a.to(dev), [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in t.items()} for t in tg])
+             for i, q, a, tg in batches]
+    host_b = [(i.pin_memory(), q.pin_memory(), a.pin_memory(), [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in t.items()} for t in tg])
+              for i, q, a, tg in batches]
+    images, qids, ans, targets = batches[0]
+    d_images, d_qids, d_ans, d_targets = dev_b[0]
+    h_images, h_qids, h_ans, h_targets = host_b[0]
+    turn = [0]                                         # the multitask workload cycles through its batches; configs[1] has one
 
     def note(msg):
         if os.environ.get("GPV_BENCH_VERBOSE"):
@@ -252,16 +329,22 @@ def main():
     note("model built, parameters broadcast")
     graph_launches = None
     if not args.no_graph and not args.breakdown:
-        cap = model.capture_step(d_images, d_qids, d_ans, d_targets)
+        seen = set()
+        for b in dev_b:                                # one captured step per distinct answer length S
+            if b[2].shape[1] not in seen:
+                seen.add(b[2].shape[1])
+                cap = model.capture_step(*b, add=True)
         graph_launches = cap.launches_per_step
 
     def step_resident():
-        loss = model(d_images, d_qids, d_ans, d_targets)
+        turn[0] += 1
+        loss = model(*dev_b[turn[0] % len(dev_b)])
         loss.backward()
         return loss
 
     def step_e2e():
-        loss = model(h_images, h_qids, h_ans, h_targets)
+        turn[0] += 1
+        loss = model(*host_b[turn[0] % len(host_b)])
         loss.backward()
         return loss.item()
 
@@ -315,7 +398,8 @@ def main():
     opt = ClipAdamW.for_model(model, cfg.training if hasattr(cfg, "training") else None)
 
     def step_full():
-        loss = model(d_images, d_qids, d_ans, d_targets)
+        turn[0] += 1
+        loss = model(*dev_b[turn[0] % len(dev_b)])
         loss.backward()
         opt.step()
         return loss
@@ -327,7 +411,7 @@ def main():
     # e2e with the input staged one step ahead (gpv1_b200.data.DevicePrefetcher): every step still moves one
     # batch of pinned host pixels to the device inside the timed region, but on a copy stream, under the previous step
     ms_e2e_pf = None
-    if not args.no_graph and not args.breakdown:
+    if not args.no_graph and not args.breakdown and not multitask:
         from gpv1_b200.data import DevicePrefetcher
 
         def host_batches():
@@ -349,7 +433,7 @@ def main():
     # third number: the same end-to-end step fed with the loader's raw format, uint8 NHWC pixels, whose
     # ToTensor + Normalize (coco_generic_dataset.py:31-32) are folded into the stem's read: a quarter of the H2D bytes
     ms_e2e_u8 = None
-    if not args.no_graph and not args.breakdown:
+    if not args.no_graph and not args.breakdown and not multitask:
         g8 = torch.Generator().manual_seed(2000 + rank)
         h_u8 = torch.randint(0, 256, (B, H_IMG, W_IMG, 3), generator=g8, dtype=torch.uint8).pin_memory()
         model.capture_step(h_u8.to(dev), d_qids, d_ans, d_targets)
@@ -390,6 +474,10 @@ def main():
             json.dump({"note": "CUDA-event time per C-ABI entry point over one extra step (serialised by the events; shares, not absolutes)",
                        "ms_per_step_untraced": ms / args.steps, "entries": breakdown}, f, indent=1)
 
+    gemm_trace = None
+    if not args.breakdown:                              # every rank (keeps the ranks in step); rank 0's numbers are reported
+        gemm_trace = trace_gemm_kernel(model, lib, step_resident)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -397,7 +485,8 @@ def main():
     ms_step = ms / args.steps
     sps = world * B * args.steps / (ms / 1e3)
     sps_e2e = world * B * args.steps / (ms_e2e / 1e3)
-    gf_fwd, gf_all = algorithmic_gflop(B)
+    gfs = [algorithmic_gflop(B, S=b[2].shape[1]) for b in batches]
+    gf_fwd, gf_all = sum(g[0] for g in gfs) / len(gfs), sum(g[1] for g in gfs) / len(gfs)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -405,20 +494,43 @@ def main():
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = gf_all * B / ms_step              # TFLOP/s per GPU: GFLOP/sample * samples / ms
-    traffic = None
-    try:                                     # DRAM bytes of one step from the committed ncu pass (profiles/step_traffic.json)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "step_traffic.json")))["dram_bytes_per_step"]
+    traffic = gemm_traffic = None
+    try:                                     # DRAM bytes from the committed ncu pass (profiles/step_traffic.json): whole step, and per GEMM launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "step_traffic.json")))
+        traffic, gemm_traffic = tj["dram_bytes_per_step"], tj["gemm_kernel"]["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)"
+    step_roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "what": f"whole step as one unit: {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd ({gf_fwd:.1f} fwd) x {B} samples / step "
+                             "time (graph replay); traffic = DRAM bytes of one step summed over its launches by ncu "
+                             f"(profiles/step_traffic.json); peak = {peak_src}"}
+    roofline = step_roofline
+    if gemm_trace is not None and gemm_trace[0] > 0 and gemm_trace[2] > 0:
+        n_g, flop_g, ms_g, ms_all, n_all = gemm_trace
+        ach_g = flop_g / (ms_g * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gpv::umma_gemm_kernel<BN,F> (tcgen05 contraction: every nn.Linear / nn.Conv2d forward, data "
+                                                  "gradient and weight gradient of the step)",
+                    "achieved": ach_g, "peak": peak, "unit": "TFLOP/s", "frac": ach_g / peak, "traffic": gemm_traffic,
+                    "launches_per_step": n_g, "flop_per_launch": flop_g / n_g, "avg_launch_us": 1e3 * ms_g / n_g,
+                    "share_of_step_kernel_time": ms_g / ms_all,
+                    "what": f"dominant kernel: algorithmic FLOPs per launch (from each call's descriptor, 2 per MAC) / average launch "
+                            f"duration over the {n_g} GEMM launches of one eager step of this run, CUDA events on the launching stream "
+                            f"({n_all} traced launches in the step); traffic = ncu DRAM bytes per GEMM launch "
+                            f"(profiles/step_traffic.json); peak = {peak_src}"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N = 1 only (torchrun pins OMP threads to 1)
-        v, cores, sample, _ = cpu_reference_steps(steps=2, warmup=1)
+        v, cores, sample, _ = cpu_reference_steps(steps=2, warmup=1, workload=args.workload)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
-    h2d = h_images.numel() * 4 + h_qids.numel() * 8 + h_ans.numel() * 8 + sum(t["boxes"].numel() * 4 + t["labels"].numel() * 8 + t["answer_token_ids"].numel() * 8 for t in targets)
+    def batch_bytes(b):
+        i, q, a, tg = b
+        return i.numel() * 4 + q.numel() * 8 + a.numel() * 8 + sum(v.numel() * v.element_size() for t in tg for v in t.values() if torch.is_tensor(v))
+
+    h2d = sum(batch_bytes(b) for b in batches) // len(batches)
     line = {"metric": "samples/sec (img+query fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random-init weights, randn images, random token ids)",
-            "config": {"workload": workload_name(B), "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graph_launches is not None,
+            "config": {"workload": workload_name(B, args.workload), "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graph_launches is not None,
                        "l2": "per-step working set (4 GB of saved activations) exceeds the 126 MB L2; no explicit flush",
                        "dropout": ("off (model.eval(): the parity arithmetic)" if args.eval_mode else
                                    "on: p=0.1 at every nn.Dropout site (counter-based masks fused into the GEMM epilogues, LayerNorm "
@@ -434,11 +546,7 @@ def main():
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
                           "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                         "what": f"whole step (1006 launches, 75 % of it the tcgen05 GEMM kernel): {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd "
-                                 f"({gf_fwd:.1f} fwd) x {B} samples / step time; traffic = DRAM bytes of one step summed over its launches "
-                                 "by ncu (profiles/step_traffic.json; writes still in L2 at kernel end are not counted); peak = "
-                                 + ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)")},
+            "roofline": roofline, "roofline_step": step_roofline,
             "cpu_baseline": cpu}
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_per_step

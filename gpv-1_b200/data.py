@@ -59,3 +59,48 @@ class DevicePrefetcher:
         torch.cuda.current_stream(self.dev).wait_event(ev)
         self._stage()                  # batch i+1 starts crossing PCIe while batch i computes
         return images, queries, targets
+
+
+# Task mix of the multitask loader (configs/learning_datasets/all.yaml concatenated and shuffled,
+# datasets/coco_multitask_dataset.py:15-42), as SURVEY 8d "Config 3" fixes it for synthetic data:
+# (task, probability, answer words lo..hi or None, boxes lo..hi or None).  Only detection samples carry boxes
+# (datasets/coco_datasets.py:23-70,191); samples without an answer are encoded as `__cls__ __stop__` (gpv.py:404-406).
+TASK_MIX = (("CocoCaptioning", 0.35, (8, 18), None), ("CocoVqa", 0.35, (1, 3), None),
+            ("CocoDetection", 0.15, None, (1, 10)), ("CocoClassification", 0.15, (1, 1), None))
+
+
+class SyntheticMultitask:
+    """`n` synthetic batches shaped like the reference's multitask stream: normalised images [B,3,H,W], `Tl` query token
+    ids per sample, and per-sample target dicts whose task is drawn from TASK_MIX.  The answer length -- hence the
+    teacher-forced sequence length S = batch maximum + 2 -- varies from batch to batch, as in the reference."""
+
+    def __init__(self, n, batch_size, H, W, vocab, seed=0, Tl=20):
+        self.n, self.B, self.H, self.W, self.seed, self.Tl = n, batch_size, H, W, seed, Tl
+        self.words = [w for w in vocab if not w.startswith("__")]
+
+    def __len__(self):
+        return self.n
+
+    def targets(self, g):
+        cum = torch.tensor([p for _, p, _, _ in TASK_MIX]).cumsum(0)
+        out = []
+        for _ in range(self.B):
+            ti = min(int(torch.searchsorted(cum, torch.rand(1, generator=g))), len(TASK_MIX) - 1)
+            task, _, words, boxes = TASK_MIX[ti]
+            t = {"task": task}
+            if words is not None:
+                nw = int(torch.randint(words[0], words[1] + 1, (1,), generator=g))
+                t["answer"] = " ".join(self.words[int(i)] for i in torch.randint(0, len(self.words), (nw,), generator=g))
+            if boxes is not None:
+                nb = int(torch.randint(boxes[0], boxes[1] + 1, (1,), generator=g))
+                t["boxes"] = torch.cat((0.25 + 0.5 * torch.rand(nb, 2, generator=g), 0.05 + 0.3 * torch.rand(nb, 2, generator=g)), -1)
+                t["labels"] = torch.zeros(nb, dtype=torch.long)
+            out.append(t)
+        return out
+
+    def __iter__(self):
+        g = torch.Generator().manual_seed(self.seed)
+        for _ in range(self.n):
+            imgs = torch.randn(self.B, 3, self.H, self.W, generator=g)
+            qids = torch.randint(1000, 30000, (self.B, self.Tl), generator=g)
+            yield imgs, qids, self.targets(g)

@@ -108,6 +108,7 @@ class Engine:
                        "co_hid_l": float(co.v_hidden_dropout_prob), "co_hid_v": float(co.hidden_dropout_prob)}
         self.drop_seed = torch.zeros(1, dtype=torch.int64, device=device)     # training-step counter read by the kernels
         self.frozen = set()                                   # names with requires_grad = False: no weight / bias gradient kernels
+        self.last_stage = N_STAGES - 1                        # last gradient stage backward() reaches (lower when the tail is frozen)
         self.concurrent = True                                # run independent branches on side streams (lanes)
         self._lanes, self._dirty, self._keep = {}, set(), []
 
@@ -326,6 +327,32 @@ class Engine:
         if m:
             return f"{m.group(1)}.biattention.query{m.group(2)}.weight" not in self.frozen
         return True
+
+    def _backward_depth(self):
+        """How far down the DETR sub-graph backward() has to go, from which parameters still train (freeze_detr_params,
+        train_distr.py:136-140, freezes whatever was initialised from the DETR checkpoint): 4 = backbone, 3 = encoder /
+        input_proj, 2 = decoder layers / query_embed, 1 = box / class heads and the decoder's final norm, 0 = nothing
+        under `detr.` trains, so no data gradient enters it at all (only detr_joiner's weight gradient is left)."""
+        if not self.frozen:
+            return 4
+        depth = 0
+        for n in self.G:
+            if n in self.frozen or not n.startswith("detr."):
+                continue
+            if n.startswith("detr.backbone."):
+                return 4
+            if n.startswith(("detr.transformer.encoder.", "detr.input_proj.")):
+                depth = max(depth, 3)
+            elif n.startswith("detr.transformer.decoder.layers.") or n == "detr.query_embed.weight":
+                depth = max(depth, 2)
+            else:
+                depth = max(depth, 1)
+        return depth
+
+    def _backward_end(self):
+        if self.on_backward_end is not None:
+            self.on_backward_end()
+        return self.G
 
     def _ln_bwd(self, dy, x, st, gamma, dgamma, dbeta, drop):
         """(dx, dx_masked): LayerNorm backward of y = LN(res + dropout(f)); dx_masked is the gradient of f's output."""
@@ -930,6 +957,8 @@ class Engine:
         self.grad_pack.zero_()
         B, Q, D, d = s["B"], self.Q, self.D, self.d
         M, S, Tl, Tm, Sx = B * Q, s["S"], s["Tl"], s["Tm"], s["S_ans"]
+        depth = self._backward_depth()
+        self.last_stage = {4: N_STAGES - 1, 3: 3}.get(depth, 2)   # gradient stages past it hold frozen parameters only: never touched
         # ---- answer head + text decoder
         emb, layers, xf, wc = s["sv_txt"]
         dlv = s["dlogits_v"]
@@ -968,6 +997,10 @@ class Engine:
         # ---- detr_joiner, ROI head, box / class heads
         detr_hs = s["detr_hs"]
         C5 = detr_hs.shape[1] - d
+        if depth == 0:                                      # all of DETR frozen: the data gradient stops at its output
+            self._lin_bwd("detr_joiner", detr_hs, dvis, need_dx=False)
+            self._done(2)
+            return self._backward_end()
         d_hs_all = self._lin_bwd("detr_joiner", detr_hs, dvis)                 # [M, C5 + d]
         hs = detr_hs[:, C5:]
         dy2 = self._lin_bwd("detr.bbox_embed.layers.2", s["y2"], s["dbox"][:, :4], aux=s["y2"], aux_mode=MASK_RELU)
@@ -980,6 +1013,9 @@ class Engine:
                a_bs=Q * s["ldw"], b_bs=Q * C5, d_bs=S * C5)
         dt = k.layernorm_bwd(dhs, s["t_final"], s["st_dn"], Pm["detr.transformer.decoder.norm.weight"],
                              G["detr.transformer.decoder.norm.weight"], G["detr.transformer.decoder.norm.bias"])
+        if depth == 1:
+            self._done(2)
+            return self._backward_end()
         # ---- DETR decoder / encoder
         gq = G["detr.query_embed.weight"]
         dmem = None
@@ -991,6 +1027,8 @@ class Engine:
             dt = self._self_attn_bwd(p, dt, sa, gq, B, Q, self.h_detr)
             self._join()
         self._done(2)
+        if depth == 2:
+            return self._backward_end()
         dx = dmem
         for i in range(self.n_enc - 1, -1, -1):
             p = f"detr.transformer.encoder.layers.{i}"
@@ -1002,7 +1040,7 @@ class Engine:
         c5f = s["c5"].view(B * S, C5)
         dpre = self._lin_bwd("detr.input_proj", c5f, dx, residual=dc5, aux=c5f, aux_mode=MASK_RELU)
         self._done(3)
+        if depth == 3:
+            return self._backward_end()
         self._backbone_bwd(dpre.view(s["c5"].shape), s["acts"])
-        if self.on_backward_end is not None:
-            self.on_backward_end()
-        return self.G
+        return self._backward_end()

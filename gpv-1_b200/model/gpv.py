@@ -223,7 +223,8 @@ class GPV(nn.Module):
         self._anchor_t = None
         self._tokenizer = None
         self.grad_sync = None          # parallel.GradSync installs itself here
-        self._captured = None          # model/graph.py:CapturedStep once capture_step() ran
+        self._captured = None          # model/graph.py:CapturedStep once capture_step() ran (the one forward() tries first)
+        self._captures = []            # every CapturedStep kept by capture_step(..., add=True): one per batch shape
         self.inference_graphs = False  # True: greedy / beam inference of a repeated input shape replays one CUDA graph
         self._inf_graphs = {}
 
@@ -250,9 +251,11 @@ class GPV(nn.Module):
             self._anchor_t = torch.zeros(1, device=dev, requires_grad=True)
         return self._anchor_t
 
-    def capture_step(self, images, queries, answer_token_ids, targets, boxes_per_image_cap=None):
+    def capture_step(self, images, queries, answer_token_ids, targets, boxes_per_image_cap=None, add=False):
         """Record the training step for this batch shape into CUDA graphs (model/graph.py).  Later calls of
-        forward(images, queries, answer_token_ids, targets) with the same shapes replay them."""
+        forward(images, queries, answer_token_ids, targets) with the same shapes replay them.  `add=True` keeps the
+        shapes captured before (each owns its graphs and memory pool): a multitask stream pads answers to the batch
+        maximum (gpv.py:401-430), so the answer length S changes from step to step -- capture one step per S."""
         from .graph import CapturedStep
         self.sync_trainable()
         (images, mask), qids = self._images(images), self._queries(queries)
@@ -261,6 +264,7 @@ class GPV(nn.Module):
         ans = answer_token_ids.to(device=images.device, dtype=torch.int64)
         self.engine.train_mode = bool(self.training)
         self._captured = CapturedStep(self, images, qids, ans, targets, boxes_per_image_cap)
+        self._captures = (self._captures if add else []) + [self._captured]
         return self._captured
 
     def _run_backward(self, g):
@@ -290,7 +294,7 @@ class GPV(nn.Module):
             eng.frozen = {n for n, p in self._live if not p.requires_grad}
             self._trainable_key = key
             if self._captured is not None:
-                self._captured = None                 # the captured backward contains the old set of gradient kernels
+                self._captured, self._captures = None, []   # the captured backward contains the old set of gradient kernels
 
     def load_pretr_detr(self):
         """gpv.py:122-135: copy same-shaped tensors of a DETR checkpoint under the `detr.` prefix."""
@@ -359,6 +363,10 @@ class GPV(nn.Module):
             ans = answer_token_ids.to(device=images.device, dtype=torch.int64, non_blocking=True)
             S = ans.shape[1]
             cap = self._captured
+            if cap is not None and mask is None and torch.is_grad_enabled() and not cap.matches(images, qids, ans):
+                cap = next((c for c in self._captures if c.matches(images, qids, ans)), None)
+                if cap is not None:
+                    self._captured = cap              # _run_backward replays the backward graphs of the step that ran forward
             if cap is not None and mask is None and torch.is_grad_enabled() and cap.matches(images, qids, ans):
                 loss = cap.forward(images, qids, ans, targets)
                 return None if loss is None else _Step.apply(self._anchor(), loss, self)

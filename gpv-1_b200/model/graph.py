@@ -64,7 +64,7 @@ class CapturedStep:
                     if self.sync is None:
                         return
                     self.g_bwd[-1].capture_end()
-                    if stage == N_STAGES - 1:             # nothing is launched after the last stage: no empty trailing graph
+                    if stage == eng.last_stage:           # nothing is launched after the last stage backward reaches: no empty trailing graph
                         open_capture[0] = False
                         return
                     g2 = torch.cuda.CUDAGraph()

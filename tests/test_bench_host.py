@@ -1,0 +1,83 @@
+"""Host-side logic of bench.py and the synthetic multitask stream (BASELINE.json configs[2]; SURVEY.md 8d "Config 3"):
+task mix, answer encoding as GPV.encode_answers does it, algorithmic FLOP accounting.  No GPU, no kernels."""
+import collections
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_multitask_stream_follows_the_task_mix():
+    from gpv1_b200.data import TASK_MIX, SyntheticMultitask
+    vocab = ["__pad__", "__cls__", "__stop__", "__unk__"] + [f"w{i}" for i in range(50)]
+    assert abs(sum(p for _, p, _, _ in TASK_MIX) - 1.0) < 1e-12
+    counts = collections.Counter()
+    n = 0
+    for imgs, qids, targets in SyntheticMultitask(40, 16, 8, 12, vocab, seed=3, Tl=5):
+        assert imgs.shape == (16, 3, 8, 12) and qids.shape == (16, 5) and len(targets) == 16
+        for t in targets:
+            counts[t["task"]] += 1
+            n += 1
+            spec = {name: (words, boxes) for name, _, words, boxes in TASK_MIX}[t["task"]]
+            if spec[0] is None:
+                assert "answer" not in t                                  # detection: encoded as `__cls__ __stop__`
+            else:
+                assert spec[0][0] <= len(t["answer"].split()) <= spec[0][1]
+            if spec[1] is None:
+                assert "boxes" not in t                                   # only detection samples carry boxes
+            else:
+                nb = t["boxes"].shape[0]
+                assert spec[1][0] <= nb <= spec[1][1] and t["labels"].shape == (nb,) and t["labels"].dtype == torch.long
+                assert (t["boxes"] > 0).all() and (t["boxes"] < 1).all()
+    for name, p, _, _ in TASK_MIX:
+        assert abs(counts[name] / n - p) < 0.06, (name, counts[name] / n)
+    # same seed -> same stream; another seed (another rank) -> another stream
+    a = [t["task"] for _, _, tg in SyntheticMultitask(2, 8, 4, 4, vocab, seed=7) for t in tg]
+    b = [t["task"] for _, _, tg in SyntheticMultitask(2, 8, 4, 4, vocab, seed=7) for t in tg]
+    c = [t["task"] for _, _, tg in SyntheticMultitask(2, 8, 4, 4, vocab, seed=8) for t in tg]
+    assert a == b and a != c
+
+
+def test_multitask_answers_are_encoded_like_encode_answers():
+    """bench.make_multitask_batches must produce exactly what GPV.encode_answers (gpv.py:377-430 of the reference) gives
+    for the same targets: `__cls__ words __stop__`, `__pad__` up to the batch maximum, targets = ids[:, 1:]."""
+    import bench
+    from gpv1_b200.model.gpv import GPV
+    batches = bench.make_multitask_batches(3, 6, seed=5, V=64)
+    vocab = bench.vocab_list(64)
+    stub = types.SimpleNamespace(word_to_idx={w: i for i, w in enumerate(vocab)}, vision_token=torch.zeros(1),
+                                 cfg=types.SimpleNamespace(answering_type="generation", max_text_len=20))
+    for images, qids, ans, targets in batches:
+        _, ids = GPV.encode_answers(stub, targets)
+        assert torch.equal(ids, ans)
+        S = ans.shape[1]
+        assert S == max(len(t.get("answer", "").split()) for t in targets) + 2
+        for b, t in enumerate(targets):
+            assert torch.equal(t["answer_token_ids"], ans[b, 1:])
+            if "answer" not in t:
+                assert ans[b, 0] == 1 and ans[b, 1] == 2 and (ans[b, 2:] == 0).all()
+
+
+def test_algorithmic_flop_accounting():
+    import bench
+    from gpv1_b200._C import GemmDesc
+    d = GemmDesc()
+    d.mode, d.M, d.N, d.K, d.batch = 0, 128, 256, 512, 3
+    assert bench.gemm_algorithmic_flop(d) == 2.0 * 128 * 256 * 512 * 3
+    d = GemmDesc()
+    d.mode, d.n_img, d.Ho, d.Wo, d.N, d.K, d.ntaps = 1, 2, 30, 40, 128, 128, 9           # 3x3 convolution, 128 -> 128 channels
+    assert bench.gemm_algorithmic_flop(d) == 2.0 * 2 * 30 * 40 * 128 * 128 * 9
+    d = GemmDesc()
+    d.mode, d.n_img, d.Ho, d.Wo, d.N, d.K, d.ntaps = 1, 2, 240, 320, 64, 64, 4            # the stem: 4 taps x 64 padded channels = 7x7x3
+    assert bench.gemm_algorithmic_flop(d) == 2.0 * 2 * 240 * 320 * 64 * 147
+    d = GemmDesc()
+    d.mode, d.n_img, d.Ho, d.Wo, d.M, d.N, d.ntaps = 2, 2, 30, 40, 256, 128, 1            # 1x1 weight gradient
+    assert bench.gemm_algorithmic_flop(d) == 2.0 * 2 * 30 * 40 * 256 * 128
+    # the closed-form step total the bench's whole-step roofline uses (70.0 fwd / 180.1 fwd+bwd measured with FlopCounterMode)
+    fwd, both = bench.algorithmic_gflop(32)
+    assert abs(fwd - 69.4) < 0.5 and abs(both - 179.6) < 1.0
+    assert bench.algorithmic_gflop(32, S=12)[1] < both

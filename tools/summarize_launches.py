@@ -1,6 +1,7 @@
 """Developer tool: aggregate an ncu `--metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv`
 launch list over the LAST training step (one stem-to-stem period at the end of the list) into a per-kernel markdown
-table; with `--json` also prints the step totals (kernel time, DRAM bytes) as one JSON line."""
+table; with `--json` also prints the step totals (kernel time, DRAM bytes) as one JSON line; with `--traffic OUT.json`
+writes the step totals plus those of the tcgen05 GEMM kernel (what bench.py reads as `roofline.traffic`)."""
 import collections
 import csv
 import json
@@ -10,7 +11,7 @@ import sys
 UNIT = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def main(path, as_json=False):
+def main(path, as_json=False, traffic_out=None):
     with open(path) as f:
         rows = list(csv.DictReader([l for l in f if l.startswith('"')]))
     # one record per launch ID, metrics merged
@@ -43,10 +44,19 @@ def main(path, as_json=False):
         if us / tot < 0.001:
             continue
         print(f"| `{k}` | {c} | {us:.0f} | {us / c:.1f} | {100 * us / tot:.1f}% | {by / 1e9:.3f} |")
+    if traffic_out:
+        g = [r for r in step if "umma_gemm_kernel" in r["name"]]
+        gus, gby = sum(r["us"] for r in g), sum(r["rd"] + r["wr"] for r in g)
+        with open(traffic_out, "w") as f:
+            json.dump({"source": f"{path}: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+                                 "python bench.py --steps 1 --warmup 1 --profiling --no-graph; last step of the list",
+                       "launches_per_step": len(step), "kernel_us_per_step": tot, "dram_bytes_per_step": dram,
+                       "gemm_kernel": {"name": "gpv::umma_gemm_kernel<BN,F>", "launches": len(g), "us": gus, "dram_bytes": gby,
+                                       "share_of_kernel_time": gus / tot, "dram_bytes_per_launch": gby / max(len(g), 1)}}, f, indent=1)
     if as_json:
         print(json.dumps({"launches": len(step), "kernel_ms": tot / 1e3, "dram_read_bytes": sum(r["rd"] for r in step),
                           "dram_write_bytes": sum(r["wr"] for r in step)}))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], "--json" in sys.argv)
+    main(sys.argv[1], "--json" in sys.argv, sys.argv[sys.argv.index("--traffic") + 1] if "--traffic" in sys.argv else None)

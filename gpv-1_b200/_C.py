@@ -44,6 +44,7 @@ def lib():
             raise RuntimeError("gpvb200_gemm_desc layout mismatch between _C.py and libgpvb200.so")
         L.gpvb200_last_error.argtypes = [ctypes.c_char_p, c_size_t]
         L.gpvb200_pack_item_size.restype = c_size_t
+        L.gpvb200_gemm_pair_launches.restype = c_int64
         L.gpvb200_optim_item_size.restype = c_size_t
         _lib = _Counting(L)
     return _lib
@@ -63,7 +64,8 @@ class _Counting:
         fn = self._cache.get(name)
         if fn is None:
             raw = getattr(self._L, name)
-            if name in ("gpvb200_version", "gpvb200_last_error", "gpvb200_gemm_desc_size", "gpvb200_pack_item_size", "gpvb200_pack_chunk",
+            if name in ("gpvb200_version", "gpvb200_last_error", "gpvb200_gemm_desc_size", "gpvb200_gemm_pair_launches", "gpvb200_pack_item_size",
+                        "gpvb200_pack_chunk",
                         "gpvb200_optim_item_size", "gpvb200_optim_chunk"):
                 fn = raw
             else:

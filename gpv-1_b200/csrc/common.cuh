@@ -58,6 +58,57 @@ GPV_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pair (cta_group::2: the two SMs of a TPC, cluster of 2)
+GPV_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+GPV_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in the pair's leader (CTA rank 0)
+GPV_DEVINL uint32_t leader_smem_addr(uint32_t cta_addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(cta_addr));
+  return r;
+}
+// This CTA's part of a pair operand into its OWN shared memory; the bytes are counted on `bar_cluster`, a
+// shared::cluster address (the leader's full barrier).
+GPV_DEVINL void tma_load_4d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+GPV_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+GPV_DEVINL void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {   // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+GPV_DEVINL void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+GPV_DEVINL void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 MMA over the pair, issued by ONE thread of the leader: each CTA's tensor core reads its own 128 rows of A and
+// both halves of B (its own and, through the pair's shared memory, the peer's) and accumulates into its own TMEM.
+GPV_DEVINL void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far have completed.
+GPV_DEVINL void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 GPV_DEVINL void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)

@@ -8,6 +8,13 @@
 // of one tile (HBM-bound for the K = 64..256 1x1 convolutions) overlaps the TMA/MMA main loop of the next; epilogue
 // warps prefetch the residual / mask rows of the next 32-column slice while they process the current one.
 //
+// Pair variant (umma_gemm_kernel<BN, F, true>, `cta_group::2`): the two SMs of a TPC form a cluster of two CTAs that own
+// TWO 128-row tiles with the same columns.  Each CTA stages its own A tile but only ITS half of the B tile (32 KB per
+// 64-deep k-block instead of 48 KB: the main loop of the single-CTA kernel is bound by the chip's L2 -> SM throughput);
+// the leader issues one M = 256 MMA per k-step that reads both halves of B through the pair's shared memory and writes
+// each CTA's 128 accumulator rows into that CTA's TMEM; stages are 128 deep.  Measured on the prototype
+// (tools/proto/gemm_2cta.cu, profiles/r1H_proto_2cta.md): 1.12-1.33x on the deep-K shapes of the trunk.
+//
 // Replaces the cuDNN / cuBLAS calls behind every nn.Conv2d / nn.Linear of the reference hot path
 // (backbone.py:72, detr_roi_head.py:79-84, transformer.py:153-160,218-231, vilbert.py:748-761,847-898,
 //  gpv.py:140,145,162, answer_head.py:31-33) and their autograd backward.
@@ -26,6 +33,8 @@ namespace gpv {
 struct KParams {
   int mode, M, N, a_mn, b_mn, bk, k_iters, splits, nstages, b_batched;
   int m_tiles, n_tiles, gy, total_work, k_per_split;
+  int m_tiles_cta;  // 128-row tiles of the problem; m_tiles counts work-item rows (pairs of tiles in the pair variant)
+  int kblk, kb_total;  // 64-deep k-blocks per pipeline stage of a K-major operand (1; 2 in the pair variant) and in the whole contraction
   int kc_per_tap;
   int Ho, Wo, th, tw, tiles_h, tiles_w, stride;
   int ntaps;
@@ -366,19 +375,26 @@ GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], 
 // Persistent kernel: each CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ... (an item = one
 // 128 x BN output tile of one batch/tap and one K split).  Two TMEM accumulator buffers let the epilogue of item j
 // overlap the TMA/MMA main loop of item j+1.
-template <int BN, int F>
+template <int BN, int F, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Pair variant: rank 0 (the leader) issues the MMAs for both CTAs; work items are walked per pair.
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int first_work = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int BNC = PAIR ? BN / 2 : BN;   // B columns this CTA stages
 
   // ---- shared memory carve-up ----------------------------------------------------------------------
   const int rowsA = (p.mode == 1) ? p.th * p.tw : BM;
-  const uint32_t a_bytes = p.a_mn ? 2u * p.bk * 128u : 128u * 128u;  // reserved per stage
-  const uint32_t b_bytes = p.b_mn ? (uint32_t)(BN / 64) * p.bk * 128u : (uint32_t)BN * 128u;
-  const uint32_t a_tx = p.a_mn ? a_bytes : (uint32_t)rowsA * 128u;    // bytes TMA actually writes
+  const uint32_t a_blk = 128u * 128u;                  // one 64-deep k-block of a K-major A tile (reserved; conv tiles may write less)
+  const uint32_t b_blk = (uint32_t)BNC * 128u;         // one 64-deep k-block of a K-major B tile
+  const uint32_t a_bytes = p.a_mn ? 2u * p.bk * 128u : (uint32_t)p.kblk * a_blk;  // reserved per stage
+  const uint32_t b_bytes = p.b_mn ? (uint32_t)(BNC / 64) * p.bk * 128u : (uint32_t)p.kblk * b_blk;
+  const uint32_t a_tx = p.a_mn ? a_bytes : (uint32_t)p.kblk * rowsA * 128u;    // bytes TMA actually writes
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int S = p.nstages;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)S * stage_bytes);
@@ -399,16 +415,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], kEpiWarps);
+      mbar_init(&acc_empty[b], PAIR ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run while
@@ -423,9 +445,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // work item will read (the producer runs 2+ tiles ahead of the epilogue, so they are L2 hits by then).
     const bool pf_r = p.pf_mode && p.coal && p.residual != nullptr, pf_a = p.pf_mode && p.coal && p.aux_mode != GPVB200_AUX_NONE;
     int gi = 0;  // stage-use counter, runs across work items
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-      const Work wk = decode_work(p, w);
-      const int n0 = wk.nt * BN, m0 = wk.mt * BM, bz = wk.bz;
+    for (int w = first_work; w < p.total_work; w += work_step) {
+      Work wk = decode_work(p, w);
+      if constexpr (PAIR) wk.mt = 2 * wk.mt + rank;   // may be one past the last tile: TMA zero-fills, the epilogue skips it
+      const int n0 = wk.nt * BN + rank * BNC, m0 = wk.mt * BM, bz = wk.bz;
       if (pf_r || pf_a) {
         const uint32_t bytes = (uint32_t)(min(BN, p.N - n0) * 2) & ~15u;
         const long long row_off = (long long)bz * p.d_batch_stride + n0;
@@ -455,6 +478,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
+          if constexpr (PAIR) {
+            // both CTAs' bytes land on the leader's barrier; K-major A (modes 0 and 1), 128-deep stages
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (a_tx + b_bytes));
+            const uint32_t fb = leader_smem_addr(smem_u32(&full_bar[s]));
+            const int bzB = p.b_batched ? bz : 0;
+            for (int kb = 0; kb < p.kblk; ++kb) {
+              const int kbi = it * p.kblk + kb;         // 64-deep k-block of the contraction; past the end: zero-filled
+              if (p.mode == 0) {
+                tma_load_4d_pair(sa + kb * a_blk, &tmA, fb, kbi * 64, m0, bz, 0);
+                if (!p.b_mn) tma_load_4d_pair(sb + kb * b_blk, &tmB, fb, kbi * 64, n0, bzB, 0);
+              } else {
+                const bool live = kbi < p.kb_total;
+                const int tap = live ? kbi / p.kc_per_tap : 0, kc = live ? kbi % p.kc_per_tap : p.kc_per_tap;
+                tma_load_4d_pair(sa + kb * a_blk, &tmA, fb, kc * 64, wo0 * p.stride + p.tap_dw[tap], ho0 * p.stride + p.tap_dh[tap], img);
+                if (!p.b_mn) tma_load_4d_pair(sb + kb * b_blk, &tmB, fb, kc * 64, n0, p.tap_w[tap], 0);
+              }
+            }
+            if (p.b_mn) {   // MN-major B: per 64 columns a [bk rows of K][64] slab (LBO = bk * 128); one 64-row box per k-block
+              for (int kb = 0; kb < p.kblk; ++kb) {
+                const int kbi = it * p.kblk + kb;
+                const bool live = p.mode == 0 || kbi < p.kb_total;
+                const int tap = (p.mode == 1 && live) ? kbi / p.kc_per_tap : 0;
+                const int krow = p.mode == 0 ? kbi * 64 : (live ? (kbi % p.kc_per_tap) * 64 : p.kc_per_tap * 64);
+                const int c2 = p.mode == 0 ? bzB : p.tap_w[tap];
+#pragma unroll
+                for (int j = 0; j < BNC / 64; ++j)
+                  tma_load_4d_pair(sb + j * p.bk * 128 + kb * 64 * 128, &tmB, fb, n0 + 64 * j, krow, c2, 0);
+              }
+            }
+            continue;
+          }
           mbar_expect_tx(&full_bar[s], a_tx + b_bytes);
           if (p.mode == 0) {
             const int k0 = it * p.bk;
@@ -501,14 +555,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, p.a_mn, p.b_mn);
     const uint32_t a_lbo = p.a_mn ? (uint32_t)p.bk * 128u : 0u;
     const uint32_t b_lbo = p.b_mn ? (uint32_t)p.bk * 128u : 0u;
     const uint32_t a_kstep = p.a_mn ? 2048u : 32u;  // bytes per UMMA_K = 16 step
     const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
     const int ksteps = p.bk / 16;
     int gi = 0, j = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
+    for (int w = first_work; w < p.total_work && (!PAIR || rank == 0); w += work_step, ++j) {
       const Work wk = decode_work(p, w);
       const int buf = j & 1;
       mbar_wait(&acc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
@@ -522,13 +576,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_sdesc_sw128(sa + k * a_kstep, a_lbo, 1024u);
-            const uint64_t bd = make_sdesc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-            umma_f16(tacc, ad, bd, idesc, (it > wk.it0 || k > 0) ? 1u : 0u);
+          if constexpr (PAIR) {
+            for (int k = 0; k < ksteps; ++k) {
+              // K-major operands: 64-deep k-blocks (4 steps of 32 bytes inside the 128-byte swizzle row), one after the other
+              const uint32_t ao = (uint32_t)(k >> 2) * a_blk + (uint32_t)(k & 3) * 32u;          // A is K-major in the pair variant
+              const uint32_t bo = p.b_mn ? k * b_kstep : (uint32_t)(k >> 2) * b_blk + (uint32_t)(k & 3) * 32u;
+              const uint64_t ad = make_sdesc_sw128(sa + ao, a_lbo, 1024u);
+              const uint64_t bd = make_sdesc_sw128(sb + bo, b_lbo, 1024u);
+              umma_f16_pair(tacc, ad, bd, idesc, (it > wk.it0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+            // the issue rate of this one thread bounds narrow tiles (a 128 x 64 x 16 MMA lasts 32 clocks): keep the loop minimal
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_sdesc_sw128(sa + k * a_kstep, a_lbo, 1024u);
+              const uint64_t bd = make_sdesc_sw128(sb + k * b_kstep, b_lbo, 1024u);
+              umma_f16(tacc, ad, bd, idesc, (it > wk.it0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[s]);                     // frees the smem stage once these MMAs retire
-          if (it == wk.it1 - 1) umma_commit(&acc_full[buf]);  // accumulator complete
+          if constexpr (PAIR) {
+            umma_commit_pair(&empty_bar[s]);                          // frees the stage in both CTAs
+            if (it == wk.it1 - 1) umma_commit_pair(&acc_full[buf]);   // both epilogues
+          } else {
+            umma_commit(&empty_bar[s]);                     // frees the smem stage once these MMAs retire
+            if (it == wk.it1 - 1) umma_commit(&acc_full[buf]);  // accumulator complete
+          }
         }
         __syncwarp();
       }
@@ -554,12 +625,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const long long ldd = p.ldd, ldr = p.ldr, lda = p.ldaux;
     const uint32_t dkey = E::drop(p) ? drop_key(*p.drop.seed, p.drop.site) : 0u;
     int j = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++j) {
-      const Work wk = decode_work(p, w);
+    for (int w = first_work; w < p.total_work; w += work_step, ++j) {
+      Work wk = decode_work(p, w);
+      if constexpr (PAIR) wk.mt = 2 * wk.mt + rank;
       const int n0 = wk.nt * BN, bz = wk.bz;
       const int buf = j & 1;
       long long pix;
-      const bool row_ok = tile_row(p, wk, r, &pix);
+      const bool row_ok = tile_row(p, wk, r, &pix) && wk.mt < p.m_tiles_cta;
       const long long row_off = (long long)bz * p.d_batch_stride;  // mode 0: batch, mode 2: tap, mode 1: bz == 0
       const float rs = p.alpha * ((p.rowscale != nullptr && row_ok && p.mode != 1) ? p.rowscale[wk.mt * BM + r] : 1.0f);
       CoalRows cr;
@@ -641,14 +713,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(leader_smem_addr(smem_u32(&acc_empty[buf])));
+        else mbar_arrive(&acc_empty[buf]);
+      }
     }
   }
 
   // ---- teardown ------------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (PAIR) {
+    cluster_sync_all();   // neither CTA leaves while its peer may still read its shared memory or write its TMEM
+    if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // =====================================================================================================
@@ -780,18 +860,20 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int F>
+template <int BN, int F, bool PAIR = false>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, F, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
       return GPV_ERR_CUDA;
     }
     configured = true;
   }
-  const int grid = kp.total_work < num_sms() ? kp.total_work : num_sms();
+  // one persistent CTA per SM; the pair variant launches clusters of two CTAs (the two SMs of a TPC), one pair per work item
+  const int slots = PAIR ? num_sms() / 2 : num_sms();
+  const int grid = (kp.total_work < slots ? kp.total_work : slots) * (PAIR ? 2 : 1);
   static int pdl = -1;   // GPVB200_PDL=0 disables programmatic dependent launch
   if (pdl < 0) {
     const char* e = getenv("GPVB200_PDL");
@@ -802,12 +884,23 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, F>, ma, mb, kp);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, F, PAIR>, ma, mb, kp);
   if (e != cudaSuccess) {
     set_last_error("umma_gemm_kernel launch failed: %s", cudaGetErrorString(e));
     return GPV_ERR_CUDA;
@@ -819,14 +912,29 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
 // the run-time-flag kernel (F = -1).  bit 0 bias, bit 1 residual, bits 2-3 act, bits 4-5 aux, bit 6 D2.
 #define GPV_EPI_VARIANTS(X) X(0) X(1) X(2) X(3) X(5) X(7) X(16) X(18) X(32) X(73) X(131) X(261)   // 131 / 261: + dropout before the residual / after ReLU
 
-template <int BN>
+template <int BN, bool PAIR = false>
 static int launch_bn(int f, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, size_t smem, cudaStream_t st) {
   switch (f) {
-#define GPV_CASE(V) case V: return launch<BN, V>(ma, mb, kp, smem, st);
+#define GPV_CASE(V) case V: return launch<BN, V, PAIR>(ma, mb, kp, smem, st);
     GPV_EPI_VARIANTS(GPV_CASE)
 #undef GPV_CASE
-    default: return launch<BN, -1>(ma, mb, kp, smem, st);
+    default: return launch<BN, -1, PAIR>(ma, mb, kp, smem, st);
   }
+}
+
+// Pair variant (cta_group::2) for contractions at least this many 64-deep k-blocks long; 0 = never (the default).
+// GPVB200_PAIR overrides.  Measured (profiles/r1H_summary.md): as a stand-alone kernel the pair main loop is 1.12-1.33x
+// faster on the deep-K shapes of the trunk, but with the threshold at 16 the whole step got 4.5 % SLOWER (19.81 vs 18.92
+// ms): a pair launch costs ~2 us more (cluster scheduling, two cluster barriers), needs both SMs of a TPC free while the
+// weight-gradient lane occupies single SMs, halves the work-item count (worse tail waves), and the two-ring epilogue
+// variants keep only two 64 KB stages.  Opt-in until the scheduling side is solved.
+static int pair_min_kblocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPVB200_PAIR");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 }  // namespace gpv
@@ -834,6 +942,9 @@ static int launch_bn(int f, const CUtensorMap& ma, const CUtensorMap& mb, const 
 using namespace gpv;
 
 extern "C" size_t gpvb200_gemm_desc_size(void) { return sizeof(gpvb200_gemm_desc); }
+
+static long long g_pair_launches = 0;   // statistics only (tests assert that the pair variant really ran)
+extern "C" int64_t gpvb200_gemm_pair_launches(void) { return (int64_t)g_pair_launches; }
 
 extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   int rc = ensure_arch();
@@ -964,13 +1075,21 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   if (BN == 256 && d->residual && d->aux_mode != GPVB200_AUX_NONE && k_iters_pre > 0 && k_iters_pre <= 4 && splits == 1)
     BN = 128;   // both epilogue input streams on a shallow-K item: full slab prefetch fits only with two chunks per warp
 
+  // ---- pair variant: K-major A (plain GEMM / implicit-GEMM convolution), bf16 or fp32 stores, deep contraction, 256 columns
+  const int kb_total_pre = d->mode == 0 ? (d->K + 63) / 64 : k_iters_pre;
+  const bool pair = pair_min_kblocks() > 0 && d->mode != 2 && !kp.a_mn && BN >= 128 && splits == 1 && !d->d_atomic &&
+                    kb_total_pre >= pair_min_kblocks() && m_tiles_pre >= 2;
+  kp.kblk = pair ? 2 : 1;
+  const uint32_t BNC = pair ? BN / 2 : BN;   // B columns one CTA stages
+
   CUtensorMap ma, mb;
   const uint32_t one4[4] = {1, 1, 1, 1};
 
   if (d->mode == 0) {
     GPV_REQUIRE(d->M > 0 && d->K > 0 && d->batch > 0, "gemm: bad plain shape");
-    kp.bk = 64;
-    kp.k_iters = (d->K + 63) / 64;
+    kp.bk = 64 * kp.kblk;
+    kp.kb_total = (d->K + 63) / 64;
+    kp.k_iters = (kp.kb_total + kp.kblk - 1) / kp.kblk;
     kp.b_batched = d->b_batch_stride != 0;
     {
       uint64_t dims[4], str[3];
@@ -991,7 +1110,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       uint64_t dims[4], str[3];
       uint32_t box[4];
       if (!kp.b_mn) {
-        dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = BN;
+        dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = BNC;
       } else {
         dims[0] = d->N; dims[1] = d->K; box[0] = 64; box[1] = 64;
       }
@@ -1003,16 +1122,18 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       rc = make_map(&mb, d->B, dims, str, box, one4);
       if (rc) return rc;
     }
-    kp.m_tiles = (d->M + BM - 1) / BM;
+    kp.m_tiles_cta = (d->M + BM - 1) / BM;
+    kp.m_tiles = pair ? (kp.m_tiles_cta + 1) / 2 : kp.m_tiles_cta;
     kp.gy = d->batch;
   } else if (d->mode == 1) {
     GPV_REQUIRE(d->n_img > 0 && d->Hi > 0 && d->Wi > 0 && d->Ho > 0 && d->Wo > 0, "gemm: bad conv geometry");
     GPV_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "gemm: ntaps must be 1..9");
     GPV_REQUIRE(!kp.a_mn, "gemm: conv A must be channel-contiguous");
     GPV_REQUIRE(kp.stride <= 2, "gemm: conv stride > 2 unsupported");
-    kp.bk = 64;
+    kp.bk = 64 * kp.kblk;
     kp.kc_per_tap = (d->K + 63) / 64;
-    kp.k_iters = d->ntaps * kp.kc_per_tap;
+    kp.kb_total = d->ntaps * kp.kc_per_tap;
+    kp.k_iters = (kp.kb_total + kp.kblk - 1) / kp.kblk;
     pick_tile(d->Ho, d->Wo, 128 / 1, false, &kp.th, &kp.tw);
     if (kp.tw * kp.stride > 256 || kp.th * kp.stride > 256) {
       set_last_error("gemm: conv tile exceeds TMA box limit");
@@ -1034,7 +1155,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       uint64_t dims[4], str[3];
       uint32_t box[4];
       if (!kp.b_mn) {
-        dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = BN;
+        dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = BNC;
       } else {
         dims[0] = d->N; dims[1] = d->K; box[0] = 64; box[1] = 64;
       }
@@ -1046,7 +1167,8 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       if (rc) return rc;
     }
     if (kp.OH == 0) { kp.OH = d->Ho; kp.OW = d->Wo; }
-    kp.m_tiles = d->n_img * kp.tiles_h * kp.tiles_w;
+    kp.m_tiles_cta = d->n_img * kp.tiles_h * kp.tiles_w;
+    kp.m_tiles = pair ? (kp.m_tiles_cta + 1) / 2 : kp.m_tiles_cta;
     kp.gy = 1;
   } else {
     GPV_REQUIRE(d->n_img > 0 && d->Hi > 0 && d->Wi > 0 && d->Ho > 0 && d->Wo > 0, "gemm: bad wgrad geometry");
@@ -1076,7 +1198,8 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       rc = make_map(&mb, d->B, dims, str, box, es);
       if (rc) return rc;
     }
-    kp.m_tiles = (d->M + BM - 1) / BM;
+    kp.m_tiles = kp.m_tiles_cta = (d->M + BM - 1) / BM;
+    kp.kb_total = kp.k_iters;
     kp.gy = d->ntaps;
   }
   // K splits: equal chunks of k_per_split iterations, none empty
@@ -1101,7 +1224,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   {
     const int rings = (kp.coal && d->residual ? 1 : 0) + (kp.coal && d->aux_mode != GPVB200_AUX_NONE ? 1 : 0);
     const int chunks = BN / 2 / kChunk;
-    kp.epi_full = rings > 0 && kp.k_per_split <= 4 && rings * chunks <= 4;
+    kp.epi_full = rings > 0 && kp.k_per_split <= 4 && rings * chunks <= 4 && !pair;   // pair items are deep-K by construction
     const int depth = kp.epi_full ? chunks : 2;
     kp.epi_warp_bytes = rings ? 2048u * depth * rings : 2048u;
     kp.epi_aux_off = (d->residual && rings == 2) ? 2048u * depth : 0u;
@@ -1109,8 +1232,8 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   }
 
   // ---- pipeline depth ---------------------------------------------------------------------------------
-  const uint32_t a_bytes = kp.a_mn ? 2u * kp.bk * 128u : 128u * 128u;
-  const uint32_t b_bytes = kp.b_mn ? (uint32_t)(BN / 64) * kp.bk * 128u : (uint32_t)BN * 128u;
+  const uint32_t a_bytes = kp.a_mn ? 2u * kp.bk * 128u : (uint32_t)kp.kblk * 128u * 128u;
+  const uint32_t b_bytes = kp.b_mn ? (BNC / 64) * kp.bk * 128u : (uint32_t)kp.kblk * BNC * 128u;
   const uint32_t stage = a_bytes + b_bytes;
   const uint32_t epi_smem = kEpiWarps * kp.epi_warp_bytes + 128;     // 16 / 32 / 64 KB of epilogue slabs
   int nst = (int)((227u * 1024u - 1024u - 256u - epi_smem) / stage);
@@ -1123,6 +1246,10 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   int f = -1;
   if (kp.coal)
     f = (d->bias ? 1 : 0) | (d->residual ? 2 : 0) | ((d->act & 3) << 2) | ((d->aux_mode & 3) << 4) | (d->D2 ? 64 : 0) | (kp.drop_mode << 7);
+  if (pair) {
+    ++g_pair_launches;
+    return BN == 256 ? launch_bn<256, true>(f, ma, mb, kp, smem, st) : launch_bn<128, true>(f, ma, mb, kp, smem, st);
+  }
   if (BN == 256) return launch_bn<256>(f, ma, mb, kp, smem, st);
   if (BN == 128) return launch_bn<128>(f, ma, mb, kp, smem, st);
   return launch_bn<64>(f, ma, mb, kp, smem, st);

@@ -99,6 +99,9 @@ typedef struct gpvb200_gemm_desc {
 
 size_t gpvb200_gemm_desc_size(void);
 int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream);
+/* Number of gpvb200_gemm calls of this process that ran the CTA-pair variant (`cta_group::2`: two SMs share the B tile;
+ * chosen for deep contractions with K-major A and N > 128; GPVB200_PAIR=<min 64-deep k-blocks>, 0 = off). */
+int64_t gpvb200_gemm_pair_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Hungarian matcher (utils/matcher.py:32-77, utils/box_ops.py:9-59, scipy.optimize.linear_sum_assignment)

@@ -138,3 +138,18 @@ def test_conv_bwd(cuda, n, H, W, Cin, Cout, ks, stride):
     dw = torch.zeros(ks * ks, Cout, Cin, device=cuda)
     k.conv_wgrad(dy, x, dw, ksize=ks, stride=stride)
     _close(dw, wf.grad, tol=3e-3, name="conv wgrad")
+
+
+def test_pair_variant_matches_references(cuda):
+    """The CTA-pair variant (`cta_group::2`, umma_gemm_kernel<BN, F, true>: two SMs share the B tile, DESIGN.md 3.1) over
+    plain / ragged / batched GEMMs, MN-major B and implicit-GEMM convolutions with fused epilogues, in a process of its
+    own with the selection threshold lowered (GPVB200_PAIR is read once per process) so that every eligible shape takes it.
+    tools/check_pair.py compares each result with a PyTorch fp32 reference and fails if the variant never ran."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GPVB200_PAIR="8")
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_pair.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "failures: 0" in res.stdout

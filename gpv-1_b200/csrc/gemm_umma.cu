@@ -13,7 +13,7 @@
 // 64-deep k-block instead of 48 KB: the main loop of the single-CTA kernel is bound by the chip's L2 -> SM throughput);
 // the leader issues one M = 256 MMA per k-step that reads both halves of B through the pair's shared memory and writes
 // each CTA's 128 accumulator rows into that CTA's TMEM; stages are 128 deep.  Measured on the prototype
-// (tools/proto/gemm_2cta.cu, profiles/r1H_proto_2cta.md): 1.12-1.33x on the deep-K shapes of the trunk.
+// (tools/proto/gemm_2cta.cu, profiles/r1H_summary.md): 1.12-1.33x on the deep-K shapes of the trunk.
 //
 // Replaces the cuDNN / cuBLAS calls behind every nn.Conv2d / nn.Linear of the reference hot path
 // (backbone.py:72, detr_roi_head.py:79-84, transformer.py:153-160,218-231, vilbert.py:748-761,847-898,

@@ -222,6 +222,37 @@ def gemm_algorithmic_flop(d):
     return 2.0 * pix * d.M * d.N * d.ntaps
 
 
+# position of (B, H, Sq, Sk, dh) in the argument list of each attention entry point (include/gpvb200.h, gpv1_b200/kernels.py)
+_ATTENTION_ARGS = {"gpvb200_attention_fwd": 10, "gpvb200_attention_fwd_drop": 10, "gpvb200_attention_fwd_bs": 14,
+                   "gpvb200_attention_bwd": 18, "gpvb200_attention_bwd_drop": 18}
+
+
+def attention_summary(rows, peak_tflops):
+    """BASELINE.json's metric also asks for the attention kernel's share of peak.  rows: (entry point, ctypes args, ms) of one
+    traced step.  Algorithmic FLOPs of one launch: 4 B H Sq Sk dh forward (Q K^T and P V), 10 B H Sq Sk dh backward (S
+    recomputed, dV, dP, dQ, dK), masks and causality not discounted.  Grouped by direction and head width: d_h = 32 is
+    the DETR encoder / decoder, 48 the co-attention, 64 BERT, 96 the text decoder."""
+    agg = {}
+    for name, a, ms in rows:
+        i = _ATTENTION_ARGS.get(name)
+        if i is None:
+            continue
+        B, H, Sq, Sk, dh = (int(getattr(x, "value", x)) for x in a[i:i + 5])
+        if not (0 < dh <= 256 and 0 < H <= 64 and B > 0 and Sq > 0 and Sk > 0):
+            raise ValueError(f"unexpected attention arguments at {name}: {(B, H, Sq, Sk, dh)}")
+        kind = "bwd" if "_bwd" in name else "fwd"
+        c = agg.setdefault(f"{kind}_dh{dh}", [0, 0.0, 0.0])
+        c[0] += 1
+        c[1] += (10.0 if kind == "bwd" else 4.0) * B * H * Sq * Sk * dh
+        c[2] += ms
+    out = {}
+    for key, (n, flop, ms) in sorted(agg.items()):
+        tf = flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        out[key] = {"launches_per_step": n, "flop_per_launch": flop / n, "avg_launch_us": 1e3 * ms / n, "achieved": tf,
+                    "unit": "TFLOP/s", "frac": tf / peak_tflops}
+    return out
+
+
 def trace_gemm_kernel(model, lib, step_fn):
     """Live, in this run: one extra EAGER step (no graph replay, no concurrent lanes) with every C-ABI call bracketed by
     CUDA events on its launching stream (_C._Counting.trace).  Returns the tcgen05 GEMM kernel's launch count, summed
@@ -250,7 +281,7 @@ def trace_gemm_kernel(model, lib, step_fn):
             n += 1
             flop += gemm_algorithmic_flop(a[0]._obj)
             ms_gemm += t
-    return n, flop, ms_gemm, ms_all, len(tr)
+    return n, flop, ms_gemm, ms_all, len(tr), [(name, a, e0.elapsed_time(e1)) for name, a, e0, e1 in tr if name in _ATTENTION_ARGS]
 
 
 def workload_name(B, workload="configs[1]"):
@@ -475,8 +506,12 @@ def main():
                        "ms_per_step_untraced": ms / args.steps, "entries": breakdown}, f, indent=1)
 
     gemm_trace = None
-    if not args.breakdown:                              # every rank (keeps the ranks in step); rank 0's numbers are reported
-        gemm_trace = trace_gemm_kernel(model, lib, step_resident)
+    if not args.breakdown and world == 1:               # N = 1 only: the scaling lines carry the whole-step roofline
+        try:
+            gemm_trace = trace_gemm_kernel(model, lib, step_resident)
+        except Exception as e:                          # the per-kernel breakdown must never cost the bench line
+            note(f"kernel trace failed: {e!r}")
+            gemm_trace = None
 
     if rank != 0:
         if world > 1:
@@ -506,8 +541,17 @@ def main():
                              "time (graph replay); traffic = DRAM bytes of one step summed over its launches by ncu "
                              f"(profiles/step_traffic.json); peak = {peak_src}"}
     roofline = step_roofline
+    attention = None
+    if gemm_trace is not None:
+        try:                                     # "attn kernel %peak" of BASELINE.json's metric: attn_fwd / attn_bwd kernels by head width
+            attention = attention_summary(gemm_trace[5], peak)
+            attention["what"] = ("gpv::attn_fwd_kernel / attn_bwd_kernel (mma.sync, scores on chip): algorithmic FLOPs per launch / "
+                                 "average launch duration in the same traced eager step as `roofline`; frac of the measured bf16 "
+                                 "tensor peak; dh32 = DETR encoder / decoder, dh48 = co-attention, dh64 = BERT, dh96 = text decoder")
+        except Exception as e:                   # never lose the bench line over the breakdown
+            attention = {"error": repr(e)}
     if gemm_trace is not None and gemm_trace[0] > 0 and gemm_trace[2] > 0:
-        n_g, flop_g, ms_g, ms_all, n_all = gemm_trace
+        n_g, flop_g, ms_g, ms_all, n_all = gemm_trace[:5]
         ach_g = flop_g / (ms_g * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gpv::umma_gemm_kernel<BN,F> (tcgen05 contraction: every nn.Linear / nn.Conv2d forward, data "
                                                   "gradient and weight gradient of the step)",
@@ -546,7 +590,7 @@ def main():
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
             "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
                           "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},
-            "roofline": roofline, "roofline_step": step_roofline,
+            "roofline": roofline, "roofline_step": step_roofline, "attention_kernel": attention,
             "cpu_baseline": cpu}
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_per_step

@@ -81,3 +81,44 @@ def test_algorithmic_flop_accounting():
     fwd, both = bench.algorithmic_gflop(32)
     assert abs(fwd - 69.4) < 0.5 and abs(both - 179.6) < 1.0
     assert bench.algorithmic_gflop(32, S=12)[1] < both
+
+
+def test_attention_summary_from_trace_rows():
+    """bench.attention_summary reads (B, H, Sq, Sk, dh) at the positions the wrappers in gpv1_b200/kernels.py pass them
+    (checked here against the wrappers' source) and turns (entry point, args, ms) rows into per-kernel rates."""
+    import ctypes
+    import inspect
+    import re
+    import bench
+    from gpv1_b200 import kernels
+    # the positions in bench._ATTENTION_ARGS must be where `B, H, Sq, Sk, dh` sit in each call of kernels.py
+    src = inspect.getsource(kernels)
+    for name, pos in bench._ATTENTION_ARGS.items():
+        m = re.search(name + r"\((.*?)\),\s*\"attention", src, re.S)
+        if m is None:
+            assert name == "gpvb200_attention_fwd"          # only reached through the _bs form
+            continue
+        depth, args, cur = 0, [], ""
+        for ch in m.group(1):
+            if ch == "," and depth == 0:
+                args.append(cur.strip())
+                cur = ""
+                continue
+            depth += ch in "([" 
+            depth -= ch in ")]"
+            cur += ch
+        args.append(cur.strip())
+        assert args[pos:pos + 5] == ["B", "H", "Sq", "Sk", "dh"], (name, args[pos:pos + 5])
+    p0 = ctypes.c_void_p(0)
+    i64 = ctypes.c_int64
+    fwd = ("gpvb200_attention_fwd_bs", (p0,) * 6 + (i64(768),) * 4 + (i64(0),) * 4 + (32, 8, 300, 300, 32, 0, ctypes.c_float(0.1), p0), 0.035)
+    bwd = ("gpvb200_attention_bwd_drop", (p0,) * 10 + (i64(768),) * 8 + (32, 8, 300, 300, 32, 0, ctypes.c_float(0.1), p0, ctypes.c_uint32(1),
+                                                                  ctypes.c_float(0.1), p0), 0.087)
+    other = ("gpvb200_gemm", (p0, p0), 1.0)
+    out = bench.attention_summary([fwd, fwd, bwd, other], 1386.5)
+    f = 4.0 * 32 * 8 * 300 * 300 * 32
+    assert set(out) == {"fwd_dh32", "bwd_dh32"}
+    assert out["fwd_dh32"]["launches_per_step"] == 2 and abs(out["fwd_dh32"]["flop_per_launch"] - f) < 1
+    assert abs(out["fwd_dh32"]["achieved"] - f / 35e-6 / 1e12) < 1e-6 * out["fwd_dh32"]["achieved"]
+    assert abs(out["bwd_dh32"]["achieved"] - 2.5 * f / 87e-6 / 1e12) < 1e-6 * out["bwd_dh32"]["achieved"]
+    assert abs(out["bwd_dh32"]["frac"] - out["bwd_dh32"]["achieved"] / 1386.5) < 1e-12

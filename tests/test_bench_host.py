@@ -122,3 +122,30 @@ def test_attention_summary_from_trace_rows():
     assert abs(out["fwd_dh32"]["achieved"] - f / 35e-6 / 1e12) < 1e-6 * out["fwd_dh32"]["achieved"]
     assert abs(out["bwd_dh32"]["achieved"] - 2.5 * f / 87e-6 / 1e12) < 1e-6 * out["bwd_dh32"]["achieved"]
     assert abs(out["bwd_dh32"]["frac"] - out["bwd_dh32"]["achieved"] / 1386.5) < 1e-12
+
+
+def test_backward_depth_follows_the_frozen_set():
+    """Engine._backward_depth (the frozen-tail cut of the first training phase, train_distr.py:136-140) on the real
+    parameter list: which prefix of the DETR sub-graph still needs gradients decides where backward stops."""
+    from gpv1_b200.config import load_config
+    from gpv1_b200.model.engine import Engine
+    from gpv1_b200.model.spec import gpv_specs, never_gets_grad
+    specs = gpv_specs(load_config().model, 64)
+    live = [s.name for s in specs if s.kind == "param" and not never_gets_grad(s.name)]
+    eng = types.SimpleNamespace(G={n: None for n in live}, frozen=set())
+    depth = lambda: Engine._backward_depth(eng)
+    assert depth() == 4
+    detr = [n for n in live if n.startswith("detr.")]
+    assert any(n.startswith("detr.backbone.") for n in detr) and "detr.query_embed.weight" in detr
+    eng.frozen = set(detr)
+    assert depth() == 0                                                  # freeze_detr_params with a full DETR checkpoint
+    eng.frozen = set(detr) - {"detr.class_embed.weight", "detr.class_embed.bias"}
+    assert depth() == 1                                                  # the 2-way class head does not match DETR's 92 classes
+    eng.frozen = {n for n in detr if not n.startswith("detr.transformer.decoder.layers.5.")}
+    assert depth() == 2
+    eng.frozen = {n for n in detr if n.startswith("detr.backbone.")}
+    assert depth() == 3
+    eng.frozen = {n for n in detr if n.startswith("detr.backbone.") and ".layer4." not in n}
+    assert depth() == 4
+    eng.frozen = {n for n in live if not n.startswith("detr.")}           # freezing everything else never cuts the DETR backward
+    assert depth() == 4

@@ -479,14 +479,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           if constexpr (PAIR) {
-            // both CTAs' bytes land on the leader's barrier; K-major A (modes 0 and 1), 128-deep stages
+            // both CTAs' bytes land on the leader's barrier; 128-deep stages (modes 0 and 1)
             if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (a_tx + b_bytes));
             const uint32_t fb = leader_smem_addr(smem_u32(&full_bar[s]));
             const int bzB = p.b_batched ? bz : 0;
             for (int kb = 0; kb < p.kblk; ++kb) {
               const int kbi = it * p.kblk + kb;         // 64-deep k-block of the contraction; past the end: zero-filled
               if (p.mode == 0) {
-                tma_load_4d_pair(sa + kb * a_blk, &tmA, fb, kbi * 64, m0, bz, 0);
+                if (!p.a_mn) {
+                  tma_load_4d_pair(sa + kb * a_blk, &tmA, fb, kbi * 64, m0, bz, 0);
+                } else {   // MN-major A (weight gradients): two 64-column slabs of [bk rows of K][64], one 64-row box per k-block
+                  tma_load_4d_pair(sa + kb * 64 * 128, &tmA, fb, m0, kbi * 64, bz, 0);
+                  tma_load_4d_pair(sa + p.bk * 128 + kb * 64 * 128, &tmA, fb, m0 + 64, kbi * 64, bz, 0);
+                }
                 if (!p.b_mn) tma_load_4d_pair(sb + kb * b_blk, &tmB, fb, kbi * 64, n0, bzB, 0);
               } else {
                 const bool live = kbi < p.kb_total;
@@ -579,7 +584,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if constexpr (PAIR) {
             for (int k = 0; k < ksteps; ++k) {
               // K-major operands: 64-deep k-blocks (4 steps of 32 bytes inside the 128-byte swizzle row), one after the other
-              const uint32_t ao = (uint32_t)(k >> 2) * a_blk + (uint32_t)(k & 3) * 32u;          // A is K-major in the pair variant
+              const uint32_t ao = p.a_mn ? k * a_kstep : (uint32_t)(k >> 2) * a_blk + (uint32_t)(k & 3) * 32u;
               const uint32_t bo = p.b_mn ? k * b_kstep : (uint32_t)(k >> 2) * b_blk + (uint32_t)(k & 3) * 32u;
               const uint64_t ad = make_sdesc_sw128(sa + ao, a_lbo, 1024u);
               const uint64_t bd = make_sdesc_sw128(sb + bo, b_lbo, 1024u);
@@ -1077,7 +1082,15 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
 
   // ---- pair variant: K-major A (plain GEMM / implicit-GEMM convolution), bf16 or fp32 stores, deep contraction, 256 columns
   const int kb_total_pre = d->mode == 0 ? (d->K + 63) / 64 : k_iters_pre;
-  const bool pair = pair_min_kblocks() > 0 && d->mode != 2 && !kp.a_mn && BN >= 128 && splits == 1 && !d->d_atomic &&
+  // GPVB200_PAIR_WGRAD=1 (experimental, not yet validated on hardware) extends it to MN-major A with split-K / fp32 atomic
+  // output: the weight gradients of mode 0, whose two streamed operands make them the most L2-bound launches of the step.
+  static int pair_wgrad = -1;
+  if (pair_wgrad < 0) {
+    const char* e = getenv("GPVB200_PAIR_WGRAD");
+    pair_wgrad = e ? atoi(e) : 0;
+  }
+  const bool pair_shape_ok = pair_wgrad ? (d->mode == 0 || !kp.a_mn) : (!kp.a_mn && splits == 1 && !d->d_atomic);
+  const bool pair = pair_min_kblocks() > 0 && d->mode != 2 && pair_shape_ok && BN >= 128 &&
                     kb_total_pre >= pair_min_kblocks() && m_tiles_pre >= 2;
   kp.kblk = pair ? 2 : 1;
   const uint32_t BNC = pair ? BN / 2 : BN;   // B columns one CTA stages

@@ -4,11 +4,15 @@ implicit-GEMM convolutions with fused epilogues.  The variant is selected inside
 threshold (GPVB200_PAIR, read once per process) so that every eligible shape below takes it, and checks that it did.
 
     python tools/check_pair.py            # exit code 0 = all shapes match and the pair variant ran
+    python tools/check_pair.py --wgrad    # + the experimental MN-major-A / split-K / atomic extension (GPVB200_PAIR_WGRAD=1)
 """
 import os
 import sys
 
 os.environ.setdefault("GPVB200_PAIR", "8")
+WGRAD = "--wgrad" in sys.argv
+if WGRAD:
+    os.environ["GPVB200_PAIR_WGRAD"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
@@ -81,6 +85,16 @@ def main():
         dy = bf(*y.shape)
         y.backward(dy.float())
         close(f"conv dgrad {n}x{H}x{W} {Cout}->{Cin} k{ks} s{stride}", convops.conv_dgrad(dy, w, ksize=ks, stride=stride, in_hw=(H, W)), xf.grad)
+    if WGRAD:   # weight gradients dW[N,K] += dy[M,N]^T x[M,K]: MN-major A and B, contraction over the rows, split-K with fp32 atomics
+        for M, N, K in [(9600, 256, 2048), (38400, 256, 1024), (38400, 1024, 256), (3200, 768, 2304), (9600, 2048, 256), (640, 2048, 768)]:
+            dy, x = bf(M, N), bf(M, K)
+            dw = torch.zeros(N, K, device=dev)
+            n_before = lib.gpvb200_gemm_pair_launches()
+            k.linear_wgrad(dy, x, dw)
+            ref = dy.float().t() @ x.float()
+            close(f"wgrad {M}: {N}x{K} (pair: {lib.gpvb200_gemm_pair_launches() > n_before})", dw, ref, tol=2e-3)
+            k.linear_wgrad(dy, x, dw)
+            close(f"wgrad {M}: {N}x{K} accumulate", dw, 2 * ref, tol=2e-3)
     torch.cuda.synchronize()
     n_pair = lib.gpvb200_gemm_pair_launches()
     print(f"pair launches: {n_pair}; failures: {len(fails)}")

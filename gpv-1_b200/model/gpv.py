@@ -84,9 +84,11 @@ class HostTargets:
     loss weight, ragged target offsets, normalisers.  Built from Python-side shapes only -- no device sync.
 
     With `static` (a dict of preallocated device buffers from `alloc_static`) the results are copied into those fixed
-    addresses (CUDA-graph replay) and the normalisers are left to the device (weight_sum = num_boxes = -1)."""
+    addresses (CUDA-graph replay) and the normalisers are left to the device (weight_sum = num_boxes = -1).  Host-resident
+    targets (what a loader hands over) are packed on the host and cross PCIe as ONE copy; targets already on the device are
+    gathered there piece by piece (`fast=False` forces that path for host tensors too: the reference for tests)."""
 
-    def __init__(self, targets, B, S, Q, loss_wts, eos_coef, device, static=None):
+    def __init__(self, targets, B, S, Q, loss_wts, eos_coef, device, static=None, fast=True):
         self.device = device
         # ---- text losses: CE(reduction none).mean(0).sum(0).sum() per task (losses.py:20-26) -> weight wt/B' per row
         counts = {}
@@ -94,19 +96,14 @@ class HostTargets:
             if "answer" in t and t.get("task") in TASK_LOSS:
                 counts[t["task"]] = counts.get(t["task"], 0) + 1
         roww = np.zeros((B, S), np.float32)
-        tg_rows = []
-        zero_row = None
+        answers = [None] * B                           # answer_token_ids of the rows that are supervised
         for b, t in enumerate(targets):
             if "answer" in t and t.get("task") in TASK_LOSS:
                 roww[b, :S - 1] = loss_wts[TASK_LOSS[t["task"]]] / counts[t["task"]]
                 ids = t["answer_token_ids"]
                 if ids.shape[0] != S - 1:
                     raise ValueError("targets[i]['answer_token_ids'] must be answer_token_ids[i, 1:] (train_distr.py:410-412)")
-                tg_rows.append(ids.to(device=device, dtype=torch.int64, non_blocking=True))
-            else:
-                if zero_row is None:
-                    zero_row = torch.zeros(S - 1, dtype=torch.int64, device=device)
-                tg_rows.append(zero_row)
+                answers[b] = ids
         self.n_text = sum(counts.values())
         # ---- localisation: images that have a 'boxes' key (losses.py:101-121); T_b may be 0
         sizes = [int(t["boxes"].shape[0]) if "boxes" in t else 0 for t in targets]
@@ -121,17 +118,31 @@ class HostTargets:
         host = np.zeros(B + 1 + B, np.int32)
         host[1:B + 1] = np.cumsum(sizes)
         host[B + 1:] = valid
-        hb = torch.from_numpy(np.concatenate([host.view(np.float32), roww.reshape(-1)])).pin_memory()
+        head = np.concatenate([host.view(np.float32), roww.reshape(-1)])      # offsets | loc_valid | CE row weights
         with_boxes = [t for t in targets if "boxes" in t and t["boxes"].shape[0]]
+        on_host = all(not v.is_cuda for t in targets for kk, v in t.items()
+                      if kk in ("boxes", "labels", "answer_token_ids") and torch.is_tensor(v))
+
+        def pinned(a):
+            h = torch.from_numpy(a)
+            return h.pin_memory() if torch.device(device).type == "cuda" else h
+
+        def ce_rows():                                  # [B, S-1] int64 on the device, zero rows where nothing is supervised
+            zero = torch.zeros(S - 1, dtype=torch.int64, device=device)
+            return torch.stack([zero if a is None else a.to(device=device, dtype=torch.int64, non_blocking=True) for a in answers])
+
+        def cat_boxes():
+            return (torch.cat([t["boxes"].to(device=device, dtype=torch.float32, non_blocking=True).reshape(-1, 4) for t in with_boxes]),
+                    torch.cat([t["labels"].to(device=device, dtype=torch.int64, non_blocking=True) for t in with_boxes]))
+
         if static is None:
-            dv = hb.to(device, non_blocking=True)
+            dv = pinned(head).to(device, non_blocking=True)
             tg = torch.zeros((B, S), dtype=torch.int64, device=device)
             if S > 1:
-                tg[:, :S - 1] = torch.stack(tg_rows)
+                tg[:, :S - 1] = ce_rows()
             self.ce_targets = tg.view(-1)
             if sumT:
-                self.boxes = torch.cat([t["boxes"].to(device=device, dtype=torch.float32, non_blocking=True).reshape(-1, 4) for t in with_boxes])
-                self.labels = torch.cat([t["labels"].to(device=device, dtype=torch.int64, non_blocking=True) for t in with_boxes])
+                self.boxes, self.labels = cat_boxes()
             else:
                 self.boxes = torch.zeros((1, 4), device=device)
                 self.labels = torch.zeros(1, dtype=torch.int64, device=device)
@@ -139,13 +150,20 @@ class HostTargets:
             if static["ce_targets"].numel() != B * S or self.Tmax > static["Tcap"]:
                 raise ValueError("batch does not fit the captured step (B, S or boxes per image)")
             dv = static["packed"]
-            dv.copy_(hb, non_blocking=True)
-            if S > 1:
-                static["ce_targets"].view(B, S)[:, :S - 1] = torch.stack(tg_rows)
+            staged = False
+            if fast and on_host and not static.get("stage_failed"):
+                try:
+                    self._stage_host(static, head, answers, with_boxes, sumT, B, S)
+                    staged = True
+                except (RuntimeError, TypeError, ValueError) as e:      # e.g. no pinned memory left: the piecewise device path still works
+                    static["stage_failed"] = repr(e)
+            if not staged:
+                dv.copy_(pinned(head), non_blocking=True)
+                if S > 1:
+                    static["ce_targets"].view(B, S)[:, :S - 1] = ce_rows()
+                if sumT:
+                    static["boxes"][:sumT], static["labels"][:sumT] = cat_boxes()
             self.ce_targets = static["ce_targets"]
-            if sumT:
-                static["boxes"][:sumT] = torch.cat([t["boxes"].to(device=device, dtype=torch.float32, non_blocking=True).reshape(-1, 4) for t in with_boxes])
-                static["labels"][:sumT] = torch.cat([t["labels"].to(device=device, dtype=torch.int64, non_blocking=True) for t in with_boxes])
             self.boxes, self.labels = static["boxes"], static["labels"]
             self.Tmax = static["Tcap"]
             self.n_loc = max(self.n_loc, 1)            # the graph always runs the localisation kernels
@@ -160,11 +178,54 @@ class HostTargets:
         self.ce_row_weight = dv[2 * B + 1:]
 
     @staticmethod
+    def _stage_host(static, head, answers, with_boxes, sumT, B, S):
+        """Pack head | CE targets | boxes | labels into the next of two pinned staging buffers laid out like the device blob
+        and enqueue ONE host-to-device copy.  A staging buffer is rewritten only after the copy that last read it completed."""
+        lay = static["layout"]
+        turn = static["turn"] = (static["turn"] + 1) % len(static["stage"])
+        ev = static["stage_ev"][turn]
+        if ev is not None:
+            ev.synchronize()
+        stage = static["stage"][turn]
+        buf = stage.numpy()
+        o, n = lay["packed"]
+        buf[o:o + n].view(np.float32)[:] = head
+        o, n = lay["ce_targets"]
+        ce = buf[o:o + n].view(np.int64).reshape(B, S)
+        ce[:] = 0
+        for b, a in enumerate(answers):
+            if a is not None:
+                ce[b, :S - 1] = a.numpy()
+        if sumT:
+            o, n = lay["boxes"]
+            buf[o:o + n].view(np.float32).reshape(-1, 4)[:sumT] = np.concatenate([t["boxes"].numpy().reshape(-1, 4) for t in with_boxes])
+            o, n = lay["labels"]
+            buf[o:o + n].view(np.int64)[:sumT] = np.concatenate([t["labels"].numpy().reshape(-1) for t in with_boxes])
+        static["blob"].copy_(stage, non_blocking=True)
+        if static["blob"].is_cuda:
+            ev = static["stage_ev"][turn] = ev if ev is not None else torch.cuda.Event()
+            ev.record()
+
+    @staticmethod
     def alloc_static(B, S, Tcap, device):
-        return {"Tcap": Tcap, "packed": torch.zeros(2 * B + 1 + B * S, dtype=torch.float32, device=device),
-                "ce_targets": torch.zeros(B * S, dtype=torch.int64, device=device),
-                "boxes": torch.zeros((B * Tcap, 4), dtype=torch.float32, device=device),
-                "labels": torch.zeros(B * Tcap, dtype=torch.int64, device=device),
+        """Fixed-address buffers of one captured step: ONE device blob with typed views (so that host-resident targets arrive
+        in a single copy) and two pinned staging buffers of the same layout."""
+        sizes = [("packed", (2 * B + 1 + B * S) * 4), ("ce_targets", B * S * 8), ("boxes", B * Tcap * 16), ("labels", B * Tcap * 8)]
+        layout, off = {}, 0
+        for name, n in sizes:
+            layout[name] = (off, n)
+            off += (n + 15) // 16 * 16
+        blob = torch.zeros(off, dtype=torch.uint8, device=device)
+        cuda = torch.device(device).type == "cuda"
+
+        def view(name, dtype):
+            o, n = layout[name]
+            return blob[o:o + n].view(dtype)
+
+        return {"Tcap": Tcap, "blob": blob, "layout": layout, "turn": 0, "stage_ev": [None, None],
+                "stage": [torch.zeros(off, dtype=torch.uint8, pin_memory=cuda) for _ in range(2)],
+                "packed": view("packed", torch.float32), "ce_targets": view("ce_targets", torch.int64),
+                "boxes": view("boxes", torch.float32).view(B * Tcap, 4), "labels": view("labels", torch.int64),
                 "loc_valid": torch.zeros(B, dtype=torch.uint8, device=device)}
 
 

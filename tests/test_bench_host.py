@@ -149,3 +149,45 @@ def test_backward_depth_follows_the_frozen_set():
     assert depth() == 4
     eng.frozen = {n for n in live if not n.startswith("detr.")}           # freezing everything else never cuts the DETR backward
     assert depth() == 4
+
+
+def test_host_targets_single_copy_staging_equals_piecewise_path():
+    """HostTargets under a captured step: host-resident targets are packed into one staging buffer and copied once
+    (gpv.py HostTargets._stage_host); the result must equal the piecewise gather used for device-resident targets, for
+    mixed tasks, ragged boxes, samples without answers / without boxes, and across reuse of the two staging buffers."""
+    import bench
+    from gpv1_b200.model.gpv import HostTargets
+    loss_wts = {"loss_caption": 5e-2, "loss_vqa": 1.0, "loss_cls": 1.0, "loss_ce": 1.0, "loss_bbox": 5.0, "loss_giou": 2.0}
+    B, Q, Tcap = 12, 100, 16
+    hw = bench.H_IMG, bench.W_IMG
+    bench.H_IMG, bench.W_IMG = 8, 8                    # the images play no role here
+    try:
+        batches = bench.make_multitask_batches(24, B, seed=9, V=64)
+    finally:
+        bench.H_IMG, bench.W_IMG = hw
+    lengths = collections.Counter(b[2].shape[1] for b in batches)
+    S = lengths.most_common(1)[0][0]
+    batches = [b for b in batches if b[2].shape[1] == S][:4]
+    assert len(batches) >= 3                            # both staging buffers get reused
+    fast_static = HostTargets.alloc_static(B, S, Tcap, "cpu")
+    slow_static = HostTargets.alloc_static(B, S, Tcap, "cpu")
+    for images, qids, ans, targets in batches + batches[:1]:
+        f = HostTargets(targets, B, S, Q, loss_wts, 0.1, "cpu", static=fast_static)
+        g = HostTargets(targets, B, S, Q, loss_wts, 0.1, "cpu", static=slow_static, fast=False)
+        sumT = sum(f.sizes)
+        assert f.sizes == g.sizes and f.n_text == g.n_text and f.n_loc == g.n_loc and f.Tmax == g.Tmax == Tcap
+        assert torch.equal(f.offsets, g.offsets) and torch.equal(f.loc_valid, g.loc_valid)
+        assert torch.equal(f.ce_row_weight, g.ce_row_weight) and torch.equal(f.ce_targets, g.ce_targets)
+        assert torch.equal(f.boxes[:sumT], g.boxes[:sumT]) and torch.equal(f.labels[:sumT], g.labels[:sumT])
+        # against the batch itself
+        assert int(f.offsets[-1]) == sumT == sum(t["boxes"].shape[0] for t in targets if "boxes" in t)
+        ce = f.ce_targets.view(B, S)
+        for b, t in enumerate(targets):
+            if "answer" in t:
+                assert torch.equal(ce[b, :S - 1], ans[b, 1:]) and ce[b, S - 1] == 0
+            else:
+                assert not ce[b].any() and not f.ce_row_weight.view(B, S)[b].any()
+    # the un-captured path (fresh tensors per step) gives the same values
+    h = HostTargets(targets, B, S, Q, loss_wts, 0.1, "cpu")
+    assert torch.equal(h.ce_targets, f.ce_targets) and torch.equal(h.offsets, f.offsets) and torch.equal(h.ce_row_weight, f.ce_row_weight)
+    assert torch.equal(h.boxes, f.boxes[:sumT]) and torch.equal(h.labels, f.labels[:sumT])

@@ -222,8 +222,11 @@ class HostTargets:
             o, n = layout[name]
             return blob[o:o + n].view(dtype)
 
-        return {"Tcap": Tcap, "blob": blob, "layout": layout, "turn": 0, "stage_ev": [None, None],
-                "stage": [torch.zeros(off, dtype=torch.uint8, pin_memory=cuda) for _ in range(2)],
+        try:
+            stage, failed = [torch.zeros(off, dtype=torch.uint8, pin_memory=cuda) for _ in range(2)], None
+        except RuntimeError as e:                       # no pinned memory: targets take the piecewise path
+            stage, failed = [], repr(e)
+        return {"Tcap": Tcap, "blob": blob, "layout": layout, "turn": 0, "stage_ev": [None, None], "stage": stage, "stage_failed": failed,
                 "packed": view("packed", torch.float32), "ce_targets": view("ce_targets", torch.int64),
                 "boxes": view("boxes", torch.float32).view(B * Tcap, 4), "labels": view("labels", torch.int64),
                 "loc_valid": torch.zeros(B, dtype=torch.uint8, device=device)}

@@ -1090,7 +1090,15 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
     pair_wgrad = e ? atoi(e) : 0;
   }
   const bool pair_shape_ok = pair_wgrad ? (d->mode == 0 || !kp.a_mn) : (!kp.a_mn && splits == 1 && !d->d_atomic);
-  const bool pair = pair_min_kblocks() > 0 && d->mode != 2 && pair_shape_ok && BN >= 128 &&
+  // GPVB200_PAIR_BN=128 also pairs the 128-column tiles (per CTA: A 16 KB + B 8 KB per k-block -- the L2 traffic of the single-CTA
+  // 256-column tile, so only the halved item count remains; default 256)
+  static int pair_min_bn = -1;
+  if (pair_min_bn < 0) {
+    const char* e = getenv("GPVB200_PAIR_BN");
+    pair_min_bn = e ? atoi(e) : 256;
+    if (pair_min_bn < 128) pair_min_bn = 128;
+  }
+  const bool pair = pair_min_kblocks() > 0 && d->mode != 2 && pair_shape_ok && BN >= pair_min_bn &&
                     kb_total_pre >= pair_min_kblocks() && m_tiles_pre >= 2;
   kp.kblk = pair ? 2 : 1;
   const uint32_t BNC = pair ? BN / 2 : BN;   // B columns one CTA stages

@@ -10,6 +10,7 @@ import os
 import sys
 
 os.environ.setdefault("GPVB200_PAIR", "8")
+os.environ.setdefault("GPVB200_PAIR_BN", "128")     # cover the 128-column pair tiles too
 WGRAD = "--wgrad" in sys.argv
 if WGRAD:
     os.environ["GPVB200_PAIR_WGRAD"] = "1"

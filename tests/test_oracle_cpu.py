@@ -17,7 +17,7 @@ def state():
     return TO.make_state([tuple(s) for s in g["specs"]], seed=0)
 
 
-@pytest.mark.parametrize("name", ["train_small", "train_padded"])
+@pytest.mark.parametrize("name", ["train_small", "train_padded", "train_mixed", "train_full"])
 def test_oracle_loss_and_outputs_equal_reference(state, name):
     from oracle import torch_oracle as TO
     from oracle.make_golden import crop_list, make_inputs
@@ -36,3 +36,41 @@ def test_oracle_loss_and_outputs_equal_reference(state, name):
         assert (out[key] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 2e-3 * (fix[key].dtype == torch.float16), key
     for (q, t), (rq, rt) in zip(ld["_indices"], fix["indices"]):
         assert torch.equal(q, rq) and torch.equal(t, rt)
+
+
+def test_oracle_greedy_decode_equals_reference(state):
+    """Greedy generation (gpv.py:178-196 through inference.py): the oracle's token ids equal the reference's, the logits of
+    every step and the detection outputs agree to fp32 round-off (fixture: tests/golden/gpv_greedy.pt)."""
+    from oracle import torch_oracle as TO
+    from oracle.make_golden import make_inputs
+    fix = torch.load(os.path.join(GOLD, "gpv_greedy.pt"), weights_only=False)
+    m = fix["meta"]
+    images, qids, _, _ = make_inputs(m["B"], m["H"], m["W"], m["Tl"], 4, m["seed"], ["CocoVqa"])
+    with torch.no_grad():
+        out = TO.gpv_forward(state, images, qids, None, None, max_text_len=m["max_text_len"])
+    lg = out["answer_logits"]
+    assert lg.shape == fix["answer_logits"].shape
+    assert torch.equal(lg.argmax(-1)[0], fix["ids"])
+    for key in ("answer_logits", "pred_boxes", "pred_relevance_logits"):
+        ref = fix[key].float()
+        assert (out[key] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), key
+
+
+def test_oracle_beam_search_equals_reference(state):
+    """forward_beam_search (gpv.py:256-328): same K sequences in the same order, same log-probabilities
+    (fixture: tests/golden/gpv_beam.pt; max_text_len 5 as scripts/eval.sh uses, so exp(log p) does not underflow)."""
+    from oracle import torch_oracle as TO
+    from oracle.make_golden import make_inputs
+    fix = torch.load(os.path.join(GOLD, "gpv_beam.pt"), weights_only=False)
+    m = fix["meta"]
+    images, qids, _, _ = make_inputs(m["B"], m["H"], m["W"], m["Tl"], 4, m["seed"], ["CocoVqa"])
+    with torch.no_grad():
+        _, memory = TO.gpv_encode(state, images, qids)
+        seqs, log_prob = TO.beam_search(state, memory, m["K"], max_text_len=m["max_text_len"])
+    assert torch.equal(seqs, fix["seqs"])
+    assert (log_prob - fix["log_prob"]).abs().max().item() <= 1e-4
+    assert seqs.tolist() == fix["answers_ids"]
+    probs = log_prob.exp()
+    for b in range(m["B"]):
+        for kk in range(m["K"]):
+            assert abs(probs[b, kk].item() - fix["answer_probs"][b][kk]) <= 1e-3 * fix["answer_probs"][b][kk]

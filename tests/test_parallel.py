@@ -49,6 +49,45 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _frozen_worker(rank, world, port, out):
+    """First training phase (freeze_detr_params): backward stops after gradient stage 2, so only buckets 0..2 are reduced;
+    the rest of the arena (frozen parameters: zeros) is never touched by a collective."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gpv1_b200.parallel import GradSync
+    ends = [8, 8, 24, 40, 48, 56, 64]
+    eng = _FakeEngine(64, ends)
+    sync = GradSync()
+    sync.attach(eng)
+    torch.manual_seed(10 + rank)
+    g = torch.randn(64)
+    g[24:] = 0.0                                         # Engine.backward zeroes the arena and never writes past the cut
+    eng.grad_arena[40:] = float(rank + 1)                # sentinel: a reduction over these buckets would average it to 1.5
+    for st in range(3):
+        lo = ends[st - 1] if st else 0
+        eng.grad_arena[lo:ends[st]] = g[lo:ends[st]]
+        eng.on_stage_done(st)
+    eng.on_backward_end()
+    gathered = [torch.zeros(64) for _ in range(world)]
+    dist.all_gather(gathered, g)
+    mean = torch.stack(gathered).mean(0)
+    ok = torch.allclose(eng.grad_arena[:24], mean[:24], atol=1e-6) and bool((eng.grad_arena[40:] == float(rank + 1)).all())
+    flag = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        with open(out, "w") as f:
+            f.write("ok" if flag.item() == 1.0 else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_gradsync_frozen_tail_gloo_world2(tmp_path):
+    out = str(tmp_path / "res.txt")
+    port = 29700 + os.getpid() % 250
+    mp.spawn(_frozen_worker, args=(2, port, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+
+
 def test_gradsync_gloo_world2(tmp_path):
     out = str(tmp_path / "res.txt")
     port = 29500 + os.getpid() % 1000

@@ -14,6 +14,15 @@ typedef __nv_bfloat16 bf16;
 
 GPV_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  ptxas recognises elect.sync: code guarded by it is known to run in a single thread, so the
+// operands of warp-level (uniform-datapath) instructions such as UTCHMMA / UTMALDG move to uniform registers with one R2UR each
+// instead of a per-active-lane "waterfall" loop (which is what `if (lane == 0)` compiles to).
+GPV_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 GPV_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -134,6 +143,28 @@ GPV_DEVINL void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32
 GPV_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Same with the A operand in tensor memory (lane = row, 32-bit column c = elements 2c (low half), 2c + 1 of the row): no
+// shared-memory read for A, which is what bounds narrow-N SS-mode MMAs (A is 4 KB per 128 x N x 16 step).
+GPV_DEVINL void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> tensor memory: thread t writes lane (base_lane + t), 32 consecutive 32-bit columns
+GPV_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+GPV_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 GPV_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 16 consecutive fp32 columns: thread t gets lane (base_lane + t), columns [col, col+16).
@@ -246,5 +277,65 @@ GPV_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.707106
 GPV_DEVINL float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
 }
+
+// ---------------------------------------------------------------- shared-memory slabs, cp.async, bf16 vectors
+// (used by the epilogues of gemm_umma.cu and layer_umma.cu; see the coalesced-epilogue note in gemm_umma.cu)
+GPV_DEVINL uint4 ldg_u4(const bf16* ptr) { return __ldg(reinterpret_cast<const uint4*>(ptr)); }
+
+GPV_DEVINL int slab_slot(int row, int c) { return row * 4 + (c ^ ((row >> 1) & 3)); }
+GPV_DEVINL void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+GPV_DEVINL uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+GPV_DEVINL void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+GPV_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+GPV_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+GPV_DEVINL void cp_async_wait_n(int n) {   // n is a compile-time value after unrolling
+  if (n <= 0) cp_async_wait<0>();
+  else if (n == 1) cp_async_wait<1>();
+  else if (n == 2) cp_async_wait<2>();
+  else cp_async_wait<3>();
+}
+GPV_DEVINL void prefetch_l2_bulk(const void* g, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
+GPV_DEVINL void prefetch_l2_line(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g) : "memory"); }
+// One row slice of `bytes` bytes into L2: mode 1 = one bulk (TMA-engine) request, mode 2 = one LSU prefetch per 128-byte line.
+GPV_DEVINL void prefetch_l2_row(const bf16* g, uint32_t bytes, int mode) {
+  if (mode == 1) {
+    prefetch_l2_bulk(g, bytes);
+  } else {
+    for (uint32_t b = 0; b < bytes; b += 128) prefetch_l2_line(reinterpret_cast<const uint8_t*>(g) + b);
+  }
+}
+
+GPV_DEVINL void unpack8(const uint4& q, float* v, bool add) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    if (add) {
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    } else {
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  }
+}
+GPV_DEVINL uint4 pack8(const float* v) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  return o;
+}
+
 
 }  // namespace gpv

@@ -458,14 +458,17 @@ __global__ void __launch_bounds__(256) relevance_mix_bwd_kernel(const bf16* __re
 // (AnswerInputEmbedding gpv.py:53; BERT embeddings)
 // ------------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, const float* __restrict__ pos,
-                                   const float* __restrict__ cst, bf16* __restrict__ out, long long ldo, long long M, int D, int T) {
+                                   const float* __restrict__ cst, bf16* __restrict__ out, long long ldo, long long M, int D, int T,
+                                   uint8_t* __restrict__ pad_mask, long long pad_id) {
   pdl_sync();
   const int nch = D >> 2;
   const long long total = M * nch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / nch;
     const int c = (int)(i % nch);
-    float4 v = *reinterpret_cast<const float4*>(table + ids[m] * (long long)D + c * 4);
+    const long long id = ids[m];
+    if (pad_mask != nullptr && c == 0) pad_mask[m] = id == pad_id ? 1 : 0;   // key-padding mask of the token row (bert.py:12-15, padding=True)
+    float4 v = *reinterpret_cast<const float4*>(table + id * (long long)D + c * 4);
     if (pos) {
       const float4 q = *reinterpret_cast<const float4*>(pos + (m % T) * (long long)D + c * 4);
       v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
@@ -665,14 +668,20 @@ extern "C" int gpvb200_relevance_mix_bwd(const void* dy, int64_t lddy, const flo
   return check_launch("relevance_mix_bwd_kernel");
 }
 
-extern "C" int gpvb200_gather_rows(const float* table, const int64_t* ids, const float* pos, const float* cst, void* out, int64_t ldo,
-                                   int64_t M, int32_t D, int32_t T, void* stream) {
+extern "C" int gpvb200_gather_rows_mask(const float* table, const int64_t* ids, const float* pos, const float* cst, void* out, int64_t ldo,
+                                        int64_t M, int32_t D, int32_t T, uint8_t* pad_mask, int64_t pad_id, void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
   GPV_REQUIRE(table && ids && out && D % 4 == 0 && ldo % 4 == 0, "gather_rows: bad arguments");
   if (M == 0) return GPV_OK;
-  launch_k(gather_rows_kernel, dim3(grid_for(M * (D / 4), 256)), dim3(256), 0, ST, table, ids, pos, cst, (bf16*)out, ldo, M, D, T > 0 ? T : 1);
+  launch_k(gather_rows_kernel, dim3(grid_for(M * (D / 4), 256)), dim3(256), 0, ST, table, ids, pos, cst, (bf16*)out, ldo, M, D, T > 0 ? T : 1,
+           pad_mask, (long long)pad_id);
   return check_launch("gather_rows_kernel");
+}
+
+extern "C" int gpvb200_gather_rows(const float* table, const int64_t* ids, const float* pos, const float* cst, void* out, int64_t ldo,
+                                   int64_t M, int32_t D, int32_t T, void* stream) {
+  return gpvb200_gather_rows_mask(table, ids, pos, cst, out, ldo, M, D, T, nullptr, 0, stream);
 }
 
 extern "C" int gpvb200_copy_rows(const void* src, int64_t lds, int32_t sG, int32_t sgs, int32_t soff, void* dst, int64_t ldd, int32_t dG,

@@ -42,6 +42,7 @@ struct KParams {
   int OH, OW, os, ooh, oow;
   int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal, pf_mode;
   uint32_t epi_warp_bytes, epi_aux_off, epi_slot_stride;   // per-warp epilogue slabs (coalesced path)
+  int nprod;      // producer warps in use (1..kProducers; GPVB200_PRODUCERS, default kProducers)
   int drop_mode;  // 0 none, 1 before the residual add, 2 after the activation (DropArgs below)
   DropArgs drop;
   int epi_full;   // 1: every slab of a work item is requested up front (one slot per chunk); 0: two-slot ring, one slab ahead
@@ -56,7 +57,15 @@ struct KParams {
 };
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (2 + kEpiWarps);
+// TMA producer warps.  Measured on B200 (tools/proto/mma_rate.cu, profiles/r2_tma_issue.md): the bulk-tensor loads issued by ONE
+// thread complete one after the other, ~650 clocks each whatever the box size (8-32 KB) and however many stages are free, while
+// loads issued from different warps overlap (2 warps: 330 clocks per box, 4 warps: 175).  A single producer thread therefore caps a
+// 128 x 256 x 64 stage (two boxes) at ~1300 clocks against 512 clocks of MMA time.  Stages are dealt round-robin to kProducers
+// warps (one lane each); 12 warps cost the same registers as 10 (allocation is per 128 threads).
+constexpr int kProducers = 3;
+constexpr int kMmaWarp = kProducers;
+constexpr int kEpiWarp0 = kProducers + 1;
+constexpr int kThreads = 32 * (kProducers + 1 + kEpiWarps);
 constexpr int BM = 128;
 constexpr int kChunk = 32;  // accumulator columns per epilogue step
 
@@ -77,8 +86,6 @@ GPV_DEVINL Work decode_work(const KParams& p, int w) {
   return k;
 }
 
-GPV_DEVINL uint4 ldg_u4(const bf16* ptr) { return __ldg(reinterpret_cast<const uint4*>(ptr)); }
-
 // ---- coalesced epilogue -----------------------------------------------------------------------------------
 // Each epilogue warp owns a 32-row x 32-column slab of the tile per step.  A thread's natural view is one ROW
 // (tcgen05.ld 32x32b: lane = row), but one row-slice is only 64 bytes of global memory, so row-per-thread accesses
@@ -90,60 +97,7 @@ GPV_DEVINL uint4 ldg_u4(const bf16* ptr) { return __ldg(reinterpret_cast<const u
 // into a two-slot ring per warp; the TMA producer warp L2-prefetches the tile's residual / aux rows several tiles
 // earlier, so the cp.async traffic hits L2.  (ncu on the first version, which prefetched into registers with LDG:
 // every epilogue warp sat on long-scoreboard stalls because later loads share scoreboards with the prefetch.)
-GPV_DEVINL int slab_slot(int row, int c) { return row * 4 + (c ^ ((row >> 1) & 3)); }
-GPV_DEVINL void sts128(uint32_t a, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-GPV_DEVINL uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-  return v;
-}
-GPV_DEVINL void cp_async16(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-GPV_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-GPV_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-GPV_DEVINL void cp_async_wait_n(int n) {   // n is a compile-time value after unrolling
-  if (n <= 0) cp_async_wait<0>();
-  else if (n == 1) cp_async_wait<1>();
-  else if (n == 2) cp_async_wait<2>();
-  else cp_async_wait<3>();
-}
-GPV_DEVINL void prefetch_l2_bulk(const void* g, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
-}
-GPV_DEVINL void prefetch_l2_line(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g) : "memory"); }
-// One row slice of `bytes` bytes into L2: mode 1 = one bulk (TMA-engine) request, mode 2 = one LSU prefetch per 128-byte line.
-GPV_DEVINL void prefetch_l2_row(const bf16* g, uint32_t bytes, int mode) {
-  if (mode == 1) {
-    prefetch_l2_bulk(g, bytes);
-  } else {
-    for (uint32_t b = 0; b < bytes; b += 128) prefetch_l2_line(reinterpret_cast<const uint8_t*>(g) + b);
-  }
-}
-
-GPV_DEVINL void unpack8(const uint4& q, float* v, bool add) {
-  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = unpack_bf16x2(w[j]);
-    if (add) {
-      v[2 * j] += f.x;
-      v[2 * j + 1] += f.y;
-    } else {
-      v[2 * j] = f.x;
-      v[2 * j + 1] = f.y;
-    }
-  }
-}
-GPV_DEVINL uint4 pack8(const float* v) {
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-  return o;
-}
+// (slab_slot, sts128 / lds128, cp.async and bf16 pack helpers: common.cuh)
 
 // Global row (pixel) index of tile row r of work item wk, and whether it exists.
 GPV_DEVINL bool tile_row(const KParams& p, const Work& wk, int r, long long* pix) {
@@ -419,7 +373,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if constexpr (PAIR) {
       tmem_alloc_pair(tmem_slot, kTmemCols);
       tmem_relinquish_pair();
@@ -439,8 +393,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == 0) {
-    // ================================================================== TMA producer
+  if (warp < kProducers) {
+    // ================================================================== TMA producers (stage gi belongs to warp gi % kProducers)
     // Lane 0 issues the TMA loads; before that, all 32 lanes L2-prefetch the residual / aux rows the epilogue of this
     // work item will read (the producer runs 2+ tiles ahead of the epilogue, so they are L2 hits by then).
     const bool pf_r = p.pf_mode && p.coal && p.residual != nullptr, pf_a = p.pf_mode && p.coal && p.aux_mode != GPVB200_AUX_NONE;
@@ -449,7 +403,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       Work wk = decode_work(p, w);
       if constexpr (PAIR) wk.mt = 2 * wk.mt + rank;   // may be one past the last tile: TMA zero-fills, the epilogue skips it
       const int n0 = wk.nt * BN + rank * BNC, m0 = wk.mt * BM, bz = wk.bz;
-      if (pf_r || pf_a) {
+      if ((pf_r || pf_a) && warp == 0) {
         const uint32_t bytes = (uint32_t)(min(BN, p.N - n0) * 2) & ~15u;
         const long long row_off = (long long)bz * p.d_batch_stride + n0;
         if (bytes > 0) {
@@ -463,7 +417,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if (lane == 0) {
+      if (elect_one()) {
         int img = 0, ho0 = 0, wo0 = 0;
         if (p.mode == 1) {
           const int tpi = p.tiles_h * p.tiles_w;
@@ -473,6 +427,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           wo0 = (r % p.tiles_w) * p.tw;
         }
         for (int it = wk.it0; it < wk.it1; ++it, ++gi) {
+          if (gi % p.nprod != warp) continue;
           const int s = gi % S;
           const uint32_t ph = (uint32_t)(gi / S) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -558,7 +513,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer
     const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, p.a_mn, p.b_mn);
     const uint32_t a_lbo = p.a_mn ? (uint32_t)p.bk * 128u : 0u;
@@ -578,7 +533,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t ph = (uint32_t)(gi / S) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
           if constexpr (PAIR) {
@@ -610,15 +565,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ================================================================== epilogue (warps 2..9)
+    // ================================================================== epilogue (warps kEpiWarp0 .. kEpiWarp0 + 7)
     typedef EpiFlags<F> E;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;       // which half of the BN columns
+    const int half = (warp - kEpiWarp0) >> 2;       // which half of the BN columns
     const int r = q * 32 + lane;
     constexpr int kChunksPerHalf = BN / 2 / kChunk;
     const int cbase = half * (BN / 2);
     const bool coal = F >= 0 || p.coal != 0;
-    const uint32_t res_ring = stg_base + (uint32_t)(warp - 2) * p.epi_warp_bytes, aux_ring = res_ring + p.epi_aux_off;
+    const uint32_t res_ring = stg_base + (uint32_t)(warp - kEpiWarp0) * p.epi_warp_bytes, aux_ring = res_ring + p.epi_aux_off;
     const uint32_t slot_stride = p.epi_slot_stride;
     const bool full_pf = p.epi_full != 0;
     const bool pre_r = E::res(p) && !E::res_fp32(p), pre_a = E::aux(p) != GPVB200_AUX_NONE;
@@ -729,10 +684,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   if constexpr (PAIR) {
     cluster_sync_all();   // neither CTA leaves while its peer may still read its shared memory or write its TMEM
-    if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+    if (warp == kMmaWarp) tmem_dealloc_pair(tmem_base, kTmemCols);
   } else {
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -772,7 +727,8 @@ struct MapKeyHash {
 };
 
 // 4-D bf16 tensor map, SWIZZLE_128B, zero OOB fill. dims/strides innermost first; strides in elements for dims 1..3.
-static int make_map(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_el[3],
+// (declared in host_util.h: layer_umma.cu builds its maps through the same cache)
+int make_map(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_el[3],
                     const uint32_t box[4], const uint32_t estr[4]) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
@@ -1001,6 +957,16 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       pf = e ? atoi(e) : 0;
     }
     kp.pf_mode = pf;
+  }
+  {
+    static int nprod = -1;   // GPVB200_PRODUCERS=1 reproduces the single-producer kernel (A/B measurements)
+    if (nprod < 0) {
+      const char* e = getenv("GPVB200_PRODUCERS");
+      nprod = e ? atoi(e) : kProducers;
+      if (nprod < 1) nprod = 1;
+      if (nprod > kProducers) nprod = kProducers;
+    }
+    kp.nprod = nprod;
   }
   kp.drop_mode = 0;
   if (d->drop_mode != 0 && d->drop_p > 0.f) {
@@ -1268,6 +1234,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   if (kp.coal)
     f = (d->bias ? 1 : 0) | (d->residual ? 2 : 0) | ((d->act & 3) << 2) | ((d->aux_mode & 3) << 4) | (d->D2 ? 64 : 0) | (kp.drop_mode << 7);
   if (pair) {
+    kp.nprod = 1;   // the pair hand-shake (both CTAs' bytes on the leader's barrier) was validated with one producer warp only
     ++g_pair_launches;
     return BN == 256 ? launch_bn<256, true>(f, ma, mb, kp, smem, st) : launch_bn<128, true>(f, ma, mb, kp, smem, st);
   }

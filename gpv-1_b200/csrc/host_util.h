@@ -1,6 +1,8 @@
 // Host-side helpers shared by the C-ABI translation units: error reporting and launch checks.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -38,6 +40,11 @@ inline void launch_k(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, args...);   // errors surface through check_launch() (cudaGetLastError)
 }
+
+// 4-D bf16 tensor map (SWIZZLE_128B, zero out-of-bounds fill), cached by (pointer, shape); gemm_umma.cu.  dims / box /
+// element strides innermost first; strides_el = element strides of dims 1..3.
+int make_map(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_el[3], const uint32_t box[4],
+             const uint32_t estr[4]);
 
 #define GPV_REQUIRE(cond, ...)            \
   do {                                    \

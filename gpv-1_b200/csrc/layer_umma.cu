@@ -1,0 +1,549 @@
+// Row-tile-resident transformer sub-layer kernels for sm_100a (tcgen05 + TMA): one CTA owns a 128-token tile of the
+// d_model = 256 DETR encoder / decoder stream and keeps it in shared memory across the whole sub-layer, so the hidden
+// activation of the feed-forward network never has to be a GEMM operand read back from HBM and bias / ReLU / dropout /
+// residual / LayerNorm ride in the epilogues.
+//
+//   mlp_block_fwd:   y = LN(x + drop(W2 drop_h(relu(W1 x + b1)) + b2))        transformer.py:157-160, 228-231
+//
+// Roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane), warps 2-9 = epilogue
+// (TMEM lane quarter = warp & 3, column half = (warp - 2) >> 2).
+//
+// mlp_block_fwd pipeline, per 64-wide chunk j of the hidden dimension (d_ff / 64 chunks):
+//   FFN1(j):  acc1[j&1] (TMEM, 64 cols)  = X[128x256] (smem, resident) . W1[64j..64j+63, :]^T        16 MMAs 128x64x16
+//   epi(j):   h = drop_h(relu(acc1 + b1)) -> bf16 -> H[j&1] (smem, SWIZZLE_128B K-major: an A operand) (+ global copy
+//             for the backward pass)
+//   FFN2(j):  acc2 (TMEM, 256 cols)     += H[j&1][128x64] . W2[:, 64j..64j+63]^T                       4 MMAs 128x256x16
+// issued as FFN1(0) FFN1(1) FFN2(0) FFN1(2) FFN2(1) ..., so the tensor pipe runs FFN1(j+1) while the epilogue warps turn
+// chunk j around.  W1 / W2 chunks (32 KB each) stream through a 4-slot TMA ring in exactly that order.  The final epilogue
+// adds b2, the dropout mask and the residual (read back from the resident X tile), computes the LayerNorm statistics of
+// the row across the two column halves (shared-memory exchange) and writes y, the pre-norm sum and (mean, rstd).
+//
+// Algorithmic work per 128-row tile: 4 * 128 * 256 * d_ff FLOP (268 MFLOP at d_ff = 2048) against 2 * 256 * d_ff * 2 B of
+// weights from L2 (2 MB) and 128 * (256 * 3 + d_ff) * 2 B of HBM traffic (x in; y, pre, h out).
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/gpvb200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace gpv {
+
+constexpr int kLtProducers = 3;            // TMA producer warps (see gemm_umma.cu: bulk loads of one thread do not overlap)
+constexpr int kLtMmaWarp = kLtProducers;
+constexpr int kLtEpiWarp0 = kLtProducers + 1;
+constexpr int kLtThreads = 32 * (kLtProducers + 1 + 8);
+constexpr int kLtEpiThreads = 256;
+constexpr int kRingSlots = 4;
+constexpr uint32_t kSlotBytes = 32768u;   // one W1 chunk [64 x 256] (4 k-blocks of 8 KB) or one W2 chunk [256 x 64]
+constexpr uint32_t kTileBytes = 65536u;   // [128 x 256] bf16 as 4 k-blocks of [128 x 64] (16 KB each), SWIZZLE_128B
+constexpr uint32_t kKblkBytes = 16384u;
+constexpr uint32_t kHBytes = 16384u;      // one hidden chunk [128 x 64]
+
+struct MlpParams {
+  int M, S, tps;        // rows; rows per sequence and 128-row tiles per sequence (flat tiling: S = M)
+  int nchunk, dff;
+  float eps;
+  const float* b1;
+  const float* b2;
+  const float* gamma;
+  const float* beta;
+  bf16* y;
+  bf16* h;              // [M, dff] hidden activation (post ReLU / dropout) for the backward pass, or null
+  bf16* pre;            // [M, 256] pre-LayerNorm sum for the backward pass, or null
+  float* stats;         // [M, 2] (mean, rstd) or null
+  long long ldy, ldh, ldpre;
+  DropArgs drop_h, drop_o;
+  long long* trace;     // developer timeline (tools/trace_layer.py): [3 roles][nchunk + 1][8] clock64 stamps of CTA 0, or null
+};
+
+#define LT_STAMP(role, j, slot) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[((role) * (p.nchunk + 1) + (j)) * 8 + (slot)] = clock64(); } while (0)
+
+GPV_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 64] bf16 SWIZZLE_128B K-major block whose base is 1024-aligned
+GPV_DEVINL uint32_t sw128_off(int r, int c) { return (uint32_t)r * 128u + ((uint32_t)(c ^ (r & 7)) << 4); }
+
+template <bool DROP>
+__global__ void __launch_bounds__(kLtThreads, 1)
+mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                       // TMA landing zone of the X tile; once X sits in TMEM: H buffers + output slabs
+  uint8_t* sH = sX;                         // 2 x 16 KB
+  uint8_t* sSlab = sX + 32768;              // 8 warps x 2 x 2 KB (final epilogue)
+  uint8_t* sRing = sX + kTileBytes;
+  uint64_t* bars = (uint64_t*)(sRing + kRingSlots * kSlotBytes);
+  uint64_t* ring_full = bars;          // [kRingSlots]
+  uint64_t* ring_empty = bars + 6;     // [kRingSlots]
+  uint64_t* acc1_full = bars + 12;     // [2]
+  uint64_t* acc1_empty = bars + 14;    // [2]
+  uint64_t* h_full = bars + 16;        // [2]
+  uint64_t* h_empty = bars + 18;       // [2]
+  uint64_t* x_full = bars + 20;
+  uint64_t* xt_full = bars + 21;       // X copied into tensor memory (8 epilogue warps)
+  uint64_t* acc2_full = bars + 22;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 23);
+  float* sVec = reinterpret_cast<float*>(bars + 32);   // b2 | gamma | beta (256 each) | b1 (dff): staged once, read by every epilogue step
+  float* sB2 = sVec;
+  float* sGamma = sVec + 256;
+  float* sBeta = sVec + 512;
+  float* sB1 = sVec + 768;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.nchunk;
+
+  const int tile = blockIdx.x;
+  const int seq = tile / p.tps, tt = tile % p.tps;
+  const int m0 = seq * p.S + tt * 128;
+  int rows_valid = p.S - tt * 128;
+  rows_valid = rows_valid > 128 ? 128 : rows_valid;
+  if (m0 + rows_valid > p.M) rows_valid = p.M - m0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int s = 0; s < kRingSlots; ++s) {
+      mbar_init(&ring_full[s], 1);
+      mbar_init(&ring_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc1_full[b], 1);
+      mbar_init(&acc1_empty[b], 4);
+      mbar_init(&h_full[b], 4);
+      mbar_init(&h_empty[b], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(xt_full, 8);
+    mbar_init(acc2_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kLtMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // tensor memory: [0,256) FFN2 accumulator, [256,384) two FFN1 accumulators, [384,512) the X tile as packed bf16 pairs
+  const uint32_t t_acc2 = tmem_base, t_acc1 = tmem_base + 256u, t_x = tmem_base + 384u;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp < kLtProducers) {
+    // ================================================================== TMA producers.  Ring item g = W1 chunk / W2 chunk in the
+    // order the MMA warp consumes them (W1(0) W1(1) W2(0) W1(2) W2(1) ...); item g belongs to warp g % kLtProducers: the bulk loads
+    // issued by one thread complete one after the other (~650 clocks each), loads of different warps overlap.  Every item is ONE
+    // 32 KB box: W1 rows [64j, 64j+64) as [4 k-blocks][64 rows][64] through a 3-D map, W2 columns [64j, 64j+64) as [256 rows][64].
+    if (elect_one()) {
+      if (warp == 0) {
+        mbar_expect_tx(x_full, kTileBytes);
+        tma_load_4d(sX, &tmX, x_full, 0, m0, 0, 0);           // [4 k-blocks][128 rows][64]: one 64 KB box
+      }
+      int g = 0;
+      for (int j = 0; j <= n; ++j) {
+        if (j < n) {
+          if (g % kLtProducers == warp) {
+            const int s = g % kRingSlots;
+            mbar_wait(&ring_empty[s], (((uint32_t)(g / kRingSlots)) & 1u) ^ 1u);
+            LT_STAMP(0, j, 0);
+            mbar_expect_tx(&ring_full[s], kSlotBytes);
+            tma_load_4d(sRing + (size_t)s * kSlotBytes, &tmW1, &ring_full[s], 0, j * 64, 0, 0);
+          }
+          ++g;
+        }
+        if (j >= 1) {
+          if (g % kLtProducers == warp) {
+            const int s = g % kRingSlots;
+            mbar_wait(&ring_empty[s], (((uint32_t)(g / kRingSlots)) & 1u) ^ 1u);
+            LT_STAMP(0, j - 1, 1);
+            mbar_expect_tx(&ring_full[s], kSlotBytes);
+            tma_load_4d(sRing + (size_t)s * kSlotBytes, &tmW2, &ring_full[s], (j - 1) * 64, 0, 0, 0);
+          }
+          ++g;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kLtMmaWarp) {
+    // ================================================================== MMA issuer
+    const uint32_t idesc1 = make_idesc_bf16(128, 64, 0, 0), idesc2 = make_idesc_bf16(128, 256, 0, 0);
+    mbar_wait(xt_full, 0);
+    tc_fence_after();
+    int g = 0;
+    for (int j = 0; j <= n; ++j) {
+      if (j < n) {
+        const int s = g % kRingSlots, b = j & 1;
+        mbar_wait(&ring_full[s], ((uint32_t)(g / kRingSlots)) & 1u);
+        if (lane == 0) LT_STAMP(1, j, 0);
+        mbar_wait(&acc1_empty[b], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        if (lane == 0) LT_STAMP(1, j, 1);
+        tc_fence_after();
+        if (elect_one()) {
+          // A = X from tensor memory (8 columns per 16-deep k-step): no shared-memory read for the 4 KB A slice of every step
+          const uint64_t bd0 = make_sdesc_sw128(smem_u32(sRing + (size_t)s * kSlotBytes), 0u, 1024u);
+          const uint32_t d = t_acc1 + (uint32_t)(b * 64);
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_f16_ts(d, t_x + (uint32_t)(k * 8), bd0 + (uint64_t)(((k >> 2) * 8192 + (k & 3) * 32) >> 4), idesc1, k > 0 ? 1u : 0u);
+          umma_commit(&ring_empty[s]);
+          umma_commit(&acc1_full[b]);
+          LT_STAMP(1, j, 2);
+        }
+        __syncwarp();
+        ++g;
+      }
+      if (j >= 1) {
+        const int jj = j - 1, s = g % kRingSlots, b = jj & 1;
+        mbar_wait(&ring_full[s], ((uint32_t)(g / kRingSlots)) & 1u);
+        if (lane == 0) LT_STAMP(1, jj, 3);
+        mbar_wait(&h_full[b], ((uint32_t)jj >> 1) & 1u);
+        if (lane == 0) LT_STAMP(1, jj, 4);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad0 = make_sdesc_sw128(smem_u32(sH + (size_t)b * kHBytes), 0u, 1024u);
+          const uint64_t bd0 = make_sdesc_sw128(smem_u32(sRing + (size_t)s * kSlotBytes), 0u, 1024u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(t_acc2, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc2, (jj > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&ring_empty[s]);
+          umma_commit(&h_empty[b]);
+          if (jj == n - 1) umma_commit(acc2_full);
+          LT_STAMP(1, jj, 5);
+        }
+        __syncwarp();
+        ++g;
+      }
+    }
+  } else {
+    // ================================================================== epilogue warps
+    // Main loop: two groups of four warps take alternate hidden chunks (group = chunk parity = FFN1 accumulator = H buffer), so the
+    // latency chain of one chunk (accumulator ready -> tcgen05.ld -> bias / ReLU / dropout -> H tile -> proxy fence -> barrier)
+    // overlaps the other group's.  A thread owns one tile row (its TMEM lane) and all 64 hidden columns of the chunk.
+    // Final epilogue: (lane quarter, column half) as in the GEMM kernel.
+    const int e = warp - kLtEpiWarp0;
+    const int q = warp & 3, half = e >> 2, grp = e >> 2;
+    const int r = q * 32 + lane;                       // tile row of this thread (= its TMEM lane)
+    const long long grow = (long long)m0 + r;          // global row
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const uint32_t dkey_h = DROP && p.drop_h.seed ? drop_key(*p.drop_h.seed, p.drop_h.site) : 0u;
+    const uint32_t dkey_o = DROP && p.drop_o.seed ? drop_key(*p.drop_o.seed, p.drop_o.site) : 0u;
+    // rows this lane stores in the coalesced arrangement: 8jj + (lane >> 2) of the warp's 32-row group, chunk lane & 3
+    uint32_t ok = 0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (q * 32 + 8 * jj + (lane >> 2) < rows_valid) ok |= 1u << jj;
+    const long long crow0 = (long long)m0 + q * 32 + (lane >> 2);
+
+    // ---- bias / LayerNorm vectors -> shared memory (one cold L2 round trip here instead of one per epilogue step)
+    {
+      const int t = threadIdx.x - kLtEpiWarp0 * 32;     // 0..255
+      if (t < 64) reinterpret_cast<float4*>(sB2)[t] = __ldg(reinterpret_cast<const float4*>(p.b2) + t);
+      else if (t < 128) reinterpret_cast<float4*>(sGamma)[t - 64] = __ldg(reinterpret_cast<const float4*>(p.gamma) + t - 64);
+      else if (t < 192) reinterpret_cast<float4*>(sBeta)[t - 128] = __ldg(reinterpret_cast<const float4*>(p.beta) + t - 128);
+      for (int i = t; i < p.dff / 4; i += kLtEpiThreads) reinterpret_cast<float4*>(sB1)[i] = __ldg(reinterpret_cast<const float4*>(p.b1) + i);
+    }
+    // ---- X tile: shared memory (TMA, SWIZZLE_128B) -> tensor memory, packed bf16 pairs; this warp copies columns
+    // [128 half, 128 half + 128) of its 32 rows = TMEM columns [64 half, 64 half + 64)
+    mbar_wait(x_full, 0);
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int kb = half * 2 + kk;
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 v = lds128(smem_u32(sX) + (uint32_t)kb * kKblkBytes + sw128_off(r, i));
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+      }
+      tmem_st_32x32b_x32(t_x + t_lane + (uint32_t)(kb * 32), w);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(xt_full);     // also: this warp no longer reads sX (the H buffers and slabs reuse it)
+    named_bar_sync(1, kLtEpiThreads);        // the staged vectors are visible to every epilogue warp
+
+    for (int j = grp; j < n; j += 2) {
+      const int b = grp;
+      const uint32_t use = (uint32_t)(j >> 1);           // how many times this group's buffers were used before
+      const bool tr = e == 0 && lane == 0;
+      if (tr) LT_STAMP(2, j, 0);
+      mbar_wait(&acc1_full[b], use & 1u);
+      if (tr) LT_STAMP(2, j, 1);
+      tc_fence_after();
+      uint32_t acc[2][32];
+      tmem_ld_32x32b_x32(t_acc1 + t_lane + (uint32_t)(b * 64), acc[0]);
+      tmem_ld_32x32b_x32(t_acc1 + t_lane + (uint32_t)(b * 64 + 32), acc[1]);
+      tmem_ld_wait();
+      if (tr) LT_STAMP(2, j, 2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc1_empty[b]);
+      const int nb = j * 64;                             // first hidden column of the chunk
+      uint4 pk[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        const float4* b4 = reinterpret_cast<const float4*>(sB1 + nb + hh * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = b4[i];
+          v[4 * i] = fmaxf(__uint_as_float(acc[hh][4 * i]) + bb.x, 0.f);
+          v[4 * i + 1] = fmaxf(__uint_as_float(acc[hh][4 * i + 1]) + bb.y, 0.f);
+          v[4 * i + 2] = fmaxf(__uint_as_float(acc[hh][4 * i + 2]) + bb.z, 0.f);
+          v[4 * i + 3] = fmaxf(__uint_as_float(acc[hh][4 * i + 3]) + bb.w, 0.f);
+        }
+        if (DROP && p.drop_h.seed) {
+          const uint32_t base = (uint32_t)grow * (uint32_t)((p.dff + 1) >> 1) + (uint32_t)((nb + hh * 32) >> 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) drop_pair(v[2 * i], v[2 * i + 1], dkey_h, base + i, p.drop_h.thresh16, p.drop_h.scale);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[hh * 4 + i] = pack8(v + 8 * i);
+      }
+      if (tr) LT_STAMP(2, j, 3);
+      mbar_wait(&h_empty[b], (use & 1u) ^ 1u);           // FFN2(j-2) has finished reading this buffer
+      if (tr) LT_STAMP(2, j, 4);
+      const uint32_t hb = smem_u32(sH + (size_t)b * kHBytes);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sts128(hb + sw128_off(r, i), pk[i]);
+      if (tr) LT_STAMP(2, j, 5);
+      fence_proxy_async();            // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_full[b]);
+      if (tr) LT_STAMP(2, j, 6);
+      if (p.h != nullptr) {           // saved for the backward pass: re-read this warp's 32 rows x 128 bytes coalesced (4 rows per instruction)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int rr = q * 32 + 4 * jj + (lane >> 3);
+          const uint4 o = lds128(hb + sw128_off(rr, lane & 7));
+          if (rr < rows_valid) *reinterpret_cast<uint4*>(p.h + ((long long)m0 + rr) * p.ldh + nb + (lane & 7) * 8) = o;
+        }
+      }
+    }
+
+    // ---- final epilogue: pre = acc2 + b2 (dropout) + x;  y = LayerNorm(pre)
+    // pass 1: pre in fp32, written back over the accumulator (tcgen05.st) and out as bf16; row statistics.
+    // pass 2: re-read, normalise, store y.  The TMEM load of the next 32-column slice is in flight while this one is processed.
+    if (e == 0 && lane == 0) LT_STAMP(2, n, 0);
+    mbar_wait(acc2_full, 0);
+    if (e == 0 && lane == 0) LT_STAMP(2, n, 1);
+    tc_fence_after();
+    const uint32_t slab = smem_u32(sSlab) + (uint32_t)e * 4096u;
+    const uint32_t co = 16u * slab_slot(lane >> 2, lane & 3);
+    uint32_t own[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) own[i] = 16u * slab_slot(lane, i);
+    float sum = 0.f, sq = 0.f;
+    {
+      uint32_t acc[2][32], xr[2][16];
+      tmem_ld_32x32b_x32(t_acc2 + t_lane + (uint32_t)(half * 128), acc[0]);
+      tmem_ld_32x32b_x16(t_x + t_lane + (uint32_t)(half * 64), xr[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = half * 128 + c * 32;
+        tmem_ld_wait();
+        if (c < 3) {
+          tmem_ld_32x32b_x32(t_acc2 + t_lane + (uint32_t)(col0 + 32), acc[(c + 1) & 1]);
+          tmem_ld_32x32b_x16(t_x + t_lane + (uint32_t)((col0 + 32) >> 1), xr[(c + 1) & 1]);
+        }
+        float v[32];
+        const float4* b4 = reinterpret_cast<const float4*>(sB2 + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = b4[i];
+          v[4 * i] = __uint_as_float(acc[c & 1][4 * i]) + bb.x;
+          v[4 * i + 1] = __uint_as_float(acc[c & 1][4 * i + 1]) + bb.y;
+          v[4 * i + 2] = __uint_as_float(acc[c & 1][4 * i + 2]) + bb.z;
+          v[4 * i + 3] = __uint_as_float(acc[c & 1][4 * i + 3]) + bb.w;
+        }
+        if (DROP && p.drop_o.seed) {
+          const uint32_t base = (uint32_t)grow * 128u + (uint32_t)(col0 >> 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) drop_pair(v[2 * i], v[2 * i + 1], dkey_o, base + i, p.drop_o.thresh16, p.drop_o.scale);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 f = unpack_bf16x2(xr[c & 1][i]);
+          v[2 * i] += f.x;
+          v[2 * i + 1] += f.y;
+        }
+        uint32_t wv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          sum += v[i];
+          sq += v[i] * v[i];
+          wv[i] = __float_as_uint(v[i]);
+        }
+        tmem_st_32x32b_x32(t_acc2 + t_lane + (uint32_t)col0, wv);
+        if (p.pre != nullptr) {
+          const uint32_t sl = slab + 2048u * (uint32_t)(c & 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts128(sl + own[i], pack8(v + 8 * i));
+          __syncwarp();
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            if ((ok >> jj) & 1u)
+              *reinterpret_cast<uint4*>(p.pre + (crow0 + 8 * jj) * p.ldpre + col0 + (lane & 3) * 8) = lds128(sl + co + 512u * jj);
+        }
+      }
+    }
+    tmem_st_wait();
+    float2* part = reinterpret_cast<float2*>(sH);     // [2][128]: the H buffers are idle once acc2 is complete
+    part[half * 128 + r] = make_float2(sum, sq);
+    named_bar_sync(1, kLtEpiThreads);
+    const float2 other = part[(half ^ 1) * 128 + r];
+    const float mean = (sum + other.x) * (1.0f / 256.0f);
+    const float var = fmaxf((sq + other.y) * (1.0f / 256.0f) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    if (half == 0 && r < rows_valid && p.stats != nullptr) {
+      p.stats[grow * 2] = mean;
+      p.stats[grow * 2 + 1] = rstd;
+    }
+    {
+      uint32_t acc[2][32];
+      tmem_ld_32x32b_x32(t_acc2 + t_lane + (uint32_t)(half * 128), acc[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = half * 128 + c * 32;
+        tmem_ld_wait();
+        if (c < 3) tmem_ld_32x32b_x32(t_acc2 + t_lane + (uint32_t)(col0 + 32), acc[(c + 1) & 1]);
+        float v[32];
+        const float4* g4 = reinterpret_cast<const float4*>(sGamma + col0);
+        const float4* e4 = reinterpret_cast<const float4*>(sBeta + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 gg = g4[i], ee = e4[i];
+          v[4 * i] = (__uint_as_float(acc[c & 1][4 * i]) - mean) * rstd * gg.x + ee.x;
+          v[4 * i + 1] = (__uint_as_float(acc[c & 1][4 * i + 1]) - mean) * rstd * gg.y + ee.y;
+          v[4 * i + 2] = (__uint_as_float(acc[c & 1][4 * i + 2]) - mean) * rstd * gg.z + ee.z;
+          v[4 * i + 3] = (__uint_as_float(acc[c & 1][4 * i + 3]) - mean) * rstd * gg.w + ee.w;
+        }
+        const uint32_t sl = slab + 2048u * (uint32_t)(c & 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts128(sl + own[i], pack8(v + 8 * i));
+        __syncwarp();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if ((ok >> jj) & 1u)
+            *reinterpret_cast<uint4*>(p.y + (crow0 + 8 * jj) * p.ldy + col0 + (lane & 3) * 8) = lds128(sl + co + 512u * jj);
+      }
+    }
+    if (e == 0 && lane == 0) LT_STAMP(2, n, 2);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kLtMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+// Launch with programmatic dependent launch allowed (GPVB200_PDL=0 turns it off), opting in to the full shared memory.
+template <typename K, typename... A>
+static int launch_layer(K kern, const char* what, int grid, size_t smem, cudaStream_t st, A... args) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_last_error("%s: cudaFuncSetAttribute(%zu bytes of shared memory) failed: %s", what, smem, cudaGetErrorString(e));
+    return GPV_ERR_CUDA;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kLtThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) {
+    set_last_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return GPV_ERR_CUDA;
+  }
+  return check_launch(what);
+}
+
+static int map2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  const uint64_t dims[4] = {cols, rows, 1, 1};
+  const uint64_t str[3] = {ld, ld * rows, ld * rows};
+  const uint32_t box[4] = {box_cols, box_rows, 1, 1};
+  const uint32_t one4[4] = {1, 1, 1, 1};
+  return make_map(m, ptr, dims, str, box, one4);
+}
+
+static void fill_drop(DropArgs* d, const void* seed, uint32_t site, float p) {
+  d->seed = nullptr;
+  d->site = 0;
+  d->thresh16 = 0;
+  d->scale = 1.f;
+  if (seed != nullptr && p > 0.f) {
+    d->seed = (const unsigned long long*)seed;
+    d->site = site;
+    d->thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
+    d->scale = 1.0f / (1.0f - p);
+  }
+}
+
+}  // namespace gpv
+
+using namespace gpv;
+
+static long long* g_layer_trace = nullptr;
+/* developer hook (tools/trace_layer.py): device buffer that CTA 0 of the next layer kernels fills with clock64 stamps; NULL = off */
+extern "C" int gpvb200_layer_trace(void* buf) {
+  g_layer_trace = (long long*)buf;
+  return GPV_OK;
+}
+
+extern "C" int gpvb200_mlp_block_fwd(const void* x, int64_t ldx, const void* w1, int64_t ldw1, const float* b1, const void* w2,
+                                     int64_t ldw2, const float* b2, const float* gamma, const float* beta, float eps, void* y,
+                                     int64_t ldy, void* h, int64_t ldh, void* pre, int64_t ldpre, float* stats, int64_t M,
+                                     int32_t d_model, int32_t d_ff, int32_t seq_len, const void* drop_seed, uint32_t site_h,
+                                     float p_h, uint32_t site_o, float p_o, void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(x && w1 && b1 && w2 && b2 && gamma && beta && y, "mlp_block_fwd: null operand");
+  GPV_REQUIRE(d_model == 256, "mlp_block_fwd: d_model must be 256 (got %d)", d_model);
+  GPV_REQUIRE(d_ff >= 64 && d_ff % 64 == 0, "mlp_block_fwd: d_ff must be a multiple of 64 (got %d)", d_ff);
+  GPV_REQUIRE(M > 0 && M < (1ll << 31), "mlp_block_fwd: bad M");
+  GPV_REQUIRE((ldy & 7) == 0 && (ldh & 7) == 0 && (ldpre & 7) == 0, "mlp_block_fwd: output row strides must be multiples of 8");
+  GPV_REQUIRE((((uintptr_t)y | (uintptr_t)h | (uintptr_t)pre | (uintptr_t)b1 | (uintptr_t)b2 | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+              "mlp_block_fwd: outputs / vectors must be 16-byte aligned");
+  GPV_REQUIRE(p_h < 1.f && p_o < 1.f, "mlp_block_fwd: dropout p must be < 1");
+  MlpParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M;
+  p.S = seq_len > 0 ? seq_len : (int)M;
+  GPV_REQUIRE(p.M % p.S == 0, "mlp_block_fwd: M (%d) is not a multiple of seq_len (%d)", p.M, p.S);
+  p.tps = (p.S + 127) / 128;
+  p.dff = d_ff;
+  p.nchunk = d_ff / 64;
+  p.eps = eps;
+  p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta;
+  p.y = (bf16*)y; p.h = (bf16*)h; p.pre = (bf16*)pre; p.stats = stats;
+  p.ldy = ldy; p.ldh = ldh; p.ldpre = ldpre;
+  fill_drop(&p.drop_h, drop_seed, site_h, p_h);
+  fill_drop(&p.drop_o, drop_seed, site_o, p_o);
+  p.trace = g_layer_trace;
+  GPV_REQUIRE(d_ff <= 4096, "mlp_block_fwd: d_ff > 4096 does not fit the shared-memory bias stage");
+  CUtensorMap mx, m1, m2;
+  {
+    // X tile and W1 chunk as ONE box each: [4 k-blocks][rows][64] (k-block stride 64 elements), i.e. exactly the SWIZZLE_128B
+    // K-major operand layout of four 64-deep k-blocks
+    const uint32_t one4[4] = {1, 1, 1, 1};
+    const uint64_t dx[4] = {64, (uint64_t)M, 4, 1}, sx[3] = {(uint64_t)ldx, 64, 256};
+    const uint32_t bx[4] = {64, 128, 4, 1};
+    if ((rc = make_map(&mx, x, dx, sx, bx, one4))) return rc;
+    const uint64_t d1[4] = {64, (uint64_t)d_ff, 4, 1}, s1[3] = {(uint64_t)ldw1, 64, 256};
+    const uint32_t b1x[4] = {64, 64, 4, 1};
+    if ((rc = make_map(&m1, w1, d1, s1, b1x, one4))) return rc;
+  }
+  if ((rc = map2d(&m2, w2, (uint64_t)d_ff, 256, (uint64_t)ldw2, 64, 256))) return rc;
+  const int grid = (p.M / p.S) * p.tps;
+  const size_t smem = 1024 + kTileBytes + kRingSlots * kSlotBytes + 256 + (768 + (size_t)d_ff) * 4;
+  const bool drop = p.drop_h.seed != nullptr || p.drop_o.seed != nullptr;
+  if (drop) return launch_layer(mlp_block_fwd_kernel<true>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
+  return launch_layer(mlp_block_fwd_kernel<false>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
+}

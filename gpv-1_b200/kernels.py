@@ -301,6 +301,32 @@ def layernorm_bwd(dy, x, stats, gamma, dgamma, dbeta, *, out=None, drop=None):
     return dx
 
 
+# ------------------------------------------------------------------------------------------------ fused sub-layers
+def mlp_block_fwd(x, w1, b1, w2, b2, gamma, beta, eps, *, save=True, seq_len=0, drop_h=None, drop_o=None):
+    """y = LN(x + drop_o(W2 drop_h(relu(W1 x + b1)) + b2)) in ONE kernel (d_model = 256).  Returns (y, h, pre, stats);
+    h / pre / stats (what the backward pass reads) are None when save is False."""
+    M, D = x.shape
+    dff = w1.shape[0]
+    dev = x.device
+    y = torch.empty((M, D), device=dev, dtype=BF16)
+    h = torch.empty((M, dff), device=dev, dtype=BF16) if save else None
+    pre = torch.empty((M, D), device=dev, dtype=BF16) if save else None
+    stats = torch.empty((M, 2), device=dev, dtype=torch.float32) if save else None
+    d0 = drop_h if drop_h is not None else drop_o
+    if drop_h is not None and drop_o is not None:
+        assert drop_h.seed.data_ptr() == drop_o.seed.data_ptr()
+    i64, f32, u32 = ctypes.c_int64, ctypes.c_float, ctypes.c_uint32
+    _C.check(_C.lib().gpvb200_mlp_block_fwd(
+        _C.ptr(_req(x, BF16)), i64(x.stride(0)), _C.ptr(_req(w1, BF16)), i64(w1.stride(0)), _C.ptr(_req(b1, torch.float32)),
+        _C.ptr(_req(w2, BF16)), i64(w2.stride(0)), _C.ptr(_req(b2, torch.float32)), _C.ptr(_req(gamma, torch.float32)),
+        _C.ptr(_req(beta, torch.float32)), f32(eps), _C.ptr(y), i64(y.stride(0)), _C.ptr(h), i64(dff), _C.ptr(pre), i64(D),
+        _C.ptr(stats), i64(M), D, dff, seq_len, _C.ptr(d0.seed) if d0 is not None else ctypes.c_void_p(0),
+        u32(drop_h.site if drop_h is not None else 0), f32(drop_h.p if drop_h is not None else 0.0),
+        u32(drop_o.site if drop_o is not None else 0), f32(drop_o.p if drop_o is not None else 0.0), _C.stream_ptr()),
+        "mlp_block_fwd")
+    return y, h, pre, stats
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def add_rowbcast(x, p, *, M=None, out=None):
     """out[m] = x[m] + p[m % P]; x may be None (pure broadcast of p over M rows)."""
@@ -420,12 +446,14 @@ def relevance_mix_bwd(dy, logits, tok, dlogits, dtok, *, M, G, gstride, off):
              "relevance_mix_bwd")
 
 
-def gather_rows(table, ids, *, pos=None, cst=None, T=1, out=None):
+def gather_rows(table, ids, *, pos=None, cst=None, T=1, out=None, pad_mask=None, pad_id=0):
+    """pad_mask: optional uint8 [M] output, 1 where ids == pad_id (the key-padding mask of the gathered token rows)."""
     M = ids.numel()
     D = table.shape[1]
     y = out if out is not None else torch.empty((M, D), device=table.device, dtype=BF16)
-    _C.check(_C.lib().gpvb200_gather_rows(_C.ptr(_req(table, torch.float32)), _C.ptr(_req(ids, torch.int64)), _C.ptr(pos), _C.ptr(cst),
-                                          _C.ptr(y), ctypes.c_int64(y.stride(0)), ctypes.c_int64(M), D, T, _C.stream_ptr()),
+    _C.check(_C.lib().gpvb200_gather_rows_mask(_C.ptr(_req(table, torch.float32)), _C.ptr(_req(ids, torch.int64)), _C.ptr(pos), _C.ptr(cst),
+                                               _C.ptr(y), ctypes.c_int64(y.stride(0)), ctypes.c_int64(M), D, T,
+                                               _C.ptr(_req(pad_mask, torch.uint8)), ctypes.c_int64(pad_id), _C.stream_ptr()),
              "gather_rows")
     return y
 

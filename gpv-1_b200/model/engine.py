@@ -19,6 +19,7 @@ HungarianMatcher matcher.py:32-77, and autograd's backward of all of it.
 """
 import contextlib
 import math
+import os
 import re
 import zlib
 
@@ -110,6 +111,7 @@ class Engine:
         self.frozen = set()                                   # names with requires_grad = False: no weight / bias gradient kernels
         self.last_stage = N_STAGES - 1                        # last gradient stage backward() reaches (lower when the tail is frozen)
         self.concurrent = True                                # run independent branches on side streams (lanes)
+        self.fused_layers = os.environ.get("GPVB200_FUSED", "1") != "0"   # row-tile-resident sub-layer kernels (layer_umma.cu)
         self._lanes, self._dirty, self._keep = {}, set(), []
 
     # ================================================================================================ weights
@@ -621,10 +623,17 @@ class Engine:
             dx = k.add(dpre, dq_in, out=dq_in)
         return dx, dmem
 
-    def _ffn_fwd(self, w1, w2, ln, x, eps, act=RELU, p_out=None):
+    def _ffn_fwd(self, w1, w2, ln, x, eps, act=RELU, p_out=None, save=True):
         """y = LN(x + drop(W2 drop_h(act(W1 x + b1)) + b2)).  Train mode: the ReLU networks (DETR, text decoder) drop
         the hidden activation too (transformer.py:158); the GELU ones (ViLBERT / BERT intermediate) only the output."""
         W, Pm = self.W, self.P
+        if act == RELU and x.shape[1] == 256 and self.fused_layers and x.shape[0] >= 48 * 128:
+            # (below ~48 row tiles the three-launch path spreads over more SMs: 3200 decoder rows are 25 tiles)
+            # one kernel for the whole sub-layer (csrc/layer_umma.cu): the hidden activation never returns as a GEMM operand
+            y, h, pre, st = k.mlp_block_fwd(x, W[w1 + ".weight"], Pm[w1 + ".bias"], W[w2 + ".weight"], Pm[w2 + ".bias"],
+                                            Pm[ln + ".weight"], Pm[ln + ".bias"], eps, save=save,
+                                            drop_h=self._drop(w1 + ".hidden"), drop_o=self._drop(ln + ".in", p_out))
+            return y, (x, h, h, pre, st)
         if act == GELU:
             hpre = torch.empty((x.shape[0], W[w1 + ".weight"].shape[0]), device=self.dev, dtype=BF16)
             h = k.linear(x, W[w1 + ".weight"], Pm[w1 + ".bias"], act=GELU, out2=hpre)
@@ -652,8 +661,12 @@ class Engine:
         P, W = self.P, self.W
         b = "bert.model"
         B, T = ids.shape
+        # key-padding mask: BertTokenizer(padding=True) pads with [PAD] = 0 and hands BertModel attention_mask = (ids != 0)
+        # (bert.py:12-21), so [PAD] keys are masked in all 12 self-attention layers; the PAD *rows* still flow on into the
+        # co-attention, which is unmasked in the reference (gpv.py:150-154)
+        kmask = torch.empty((B, T), device=self.dev, dtype=torch.uint8)
         e = k.gather_rows(P[f"{b}.embeddings.word_embeddings.weight"], ids.reshape(-1), pos=P[f"{b}.embeddings.position_embeddings.weight"],
-                          cst=P[f"{b}.embeddings.token_type_embeddings.weight"], T=T)
+                          cst=P[f"{b}.embeddings.token_type_embeddings.weight"], T=T, pad_mask=kmask, pad_id=0)
         # bert.py:11-22 runs under no_grad but in the module's train/eval mode: HF's dropouts (embeddings, attention
         # probabilities, both dense outputs) are active while training
         x, _ = k.layernorm_fwd(e, P[f"{b}.embeddings.LayerNorm.weight"], P[f"{b}.embeddings.LayerNorm.bias"], 1e-12, need_stats=False,
@@ -663,7 +676,7 @@ class Engine:
             p = f"{b}.encoder.layer.{i}"
             qkv = k.linear(x, W[p + ".qkv"], self.Bcat[p + ".qkv"])
             o, _ = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=12, Sq=T, Sk=T, dh=64, scale=0.125, need_lse=False,
-                                   drop=self._drop(p + ".attention.probs"))
+                                   key_mask=kmask, drop=self._drop(p + ".attention.probs"))
             pre = k.linear(o, W[p + ".attention.output.dense.weight"], P[p + ".attention.output.dense.bias"], residual=x,
                            drop=self._drop(p + ".attention.output.in"), drop_mode=k.DROP_PRE_RESIDUAL)
             x1, _ = k.layernorm_fwd(pre, P[p + ".attention.output.LayerNorm.weight"], P[p + ".attention.output.LayerNorm.bias"], 1e-12,
@@ -769,7 +782,7 @@ class Engine:
         for i in range(self.n_enc):
             p = f"detr.transformer.encoder.layers.{i}"
             x, sa = self._self_attn_fwd(p, x, pos, P_rows, B, S, self.h_detr, kmask=kmask)
-            x, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm2", x, 1e-5)
+            x, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm2", x, 1e-5, save=save)
             enc.append((sa, sf))
         mem = x
         mem_pos = k.add_rowbcast(mem, pos)
@@ -784,7 +797,7 @@ class Engine:
             if i == 0:
                 self._join(1)
             t, sc = self._cross_attn_fwd(p, t, qe, mem_pos, mem, B, Q, S, self.h_detr, kv=kvs[i], kmask=kmask)
-            t, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm3", t, 1e-5)
+            t, sf = self._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm3", t, 1e-5, save=save)
             dec.append((sa, sc, sf))
         # heads (detr_roi_head.py:81-92).  detr_hs = [LN(roi) | hs] is written in place, no cat.
         M = B * Q

@@ -164,6 +164,28 @@ int gpvb200_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
                           void* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Row-tile-resident transformer sub-layers (layer_umma.cu): one CTA keeps a 128-token tile of the d_model = 256
+ * stream in shared memory across the whole sub-layer (tcgen05.mma + TMA; bias / ReLU / dropout / residual /
+ * LayerNorm in the epilogues).  SURVEY 8b: `mlp_block`, `attn_block`.
+ * ------------------------------------------------------------------------------------------------ */
+/* y = LayerNorm(x + drop_o(W2 drop_h(relu(W1 x + b1)) + b2)): TransformerEncoderLayer.forward_post transformer.py:157-160,
+ * TransformerDecoderLayer.forward_post transformer.py:228-231 (linear1 -> ReLU -> dropout -> linear2 -> dropout ->
+ * residual -> norm).  x [M, 256] bf16, w1 [d_ff, 256] bf16, w2 [256, d_ff] bf16 (nn.Linear layouts), b1 / b2 / gamma / beta fp32.
+ * Outputs: y [M, 256] bf16; optional (NULL to skip) h [M, d_ff] bf16 = the hidden activation after ReLU / dropout,
+ * pre [M, 256] bf16 = the pre-norm sum, stats [M, 2] fp32 = (mean, rstd) -- what the backward pass reads.
+ * seq_len > 0: rows are tiled per sequence of seq_len rows (128-row tiles never straddle two sequences); 0: flat tiles.
+ * drop_seed: device uint64 step counter or NULL (eval); site_h / p_h: hidden dropout; site_o / p_o: output dropout. */
+int gpvb200_mlp_block_fwd(const void* x, int64_t ldx, const void* w1, int64_t ldw1, const float* b1, const void* w2, int64_t ldw2,
+                          const float* b2, const float* gamma, const float* beta, float eps, void* y, int64_t ldy, void* h,
+                          int64_t ldh, void* pre, int64_t ldpre, float* stats, int64_t M, int32_t d_model, int32_t d_ff,
+                          int32_t seq_len, const void* drop_seed, uint32_t site_h, float p_h, uint32_t site_o, float p_o,
+                          void* stream);
+
+/* Developer hook: a device buffer of int64 that CTA 0 of the layer kernels fills with clock64() stamps of its producer /
+ * MMA / epilogue roles ([3][chunks + 1][8]); NULL switches it off (the default).  tools/trace_layer.py. */
+int gpvb200_layer_trace(void* buf);
+
+/* ------------------------------------------------------------------------------------------------
  * HBM-bound helpers (elementwise.cu)
  * ------------------------------------------------------------------------------------------------ */
 /* out[m] = x[m] + p[m % P]  (x may be NULL): q = k = src + pos, transformer.py:153,218,223-224 */
@@ -200,6 +222,10 @@ int gpvb200_relevance_mix_bwd(const void* dy, int64_t lddy, const float* logits,
 /* out[m] = table[ids[m]] (+ pos[m % T]) (+ cst): AnswerInputEmbedding gpv.py:53, BERT embeddings */
 int gpvb200_gather_rows(const float* table, const int64_t* ids, const float* pos, const float* cst, void* out, int64_t ldo,
                         int64_t M, int32_t D, int32_t T, void* stream);
+/* Same, and also writes pad_mask[m] = (ids[m] == pad_id): the key-padding mask HF's BertTokenizer(padding=True) hands to
+ * BertModel as attention_mask (bert.py:12-21; [PAD] = 0), produced by the embedding gather that reads the ids anyway. */
+int gpvb200_gather_rows_mask(const float* table, const int64_t* ids, const float* pos, const float* cst, void* out, int64_t ldo,
+                             int64_t M, int32_t D, int32_t T, uint8_t* pad_mask, int64_t pad_id, void* stream);
 /* row-remapped bf16 copy: row(m) = (m / G) * gstride + off + m % G on either side */
 int gpvb200_copy_rows(const void* src, int64_t lds, int32_t sG, int32_t sgs, int32_t soff, void* dst, int64_t ldd, int32_t dG,
                       int32_t dgs, int32_t doff, int64_t M, int32_t D, void* stream);

@@ -1,0 +1,88 @@
+"""Row-tile-resident fused sub-layer kernels (csrc/layer_umma.cu) against plain torch fp32 arithmetic on identical
+bf16-representable inputs.  Reference semantics: TransformerEncoderLayer.forward_post transformer.py:148-161,
+TransformerDecoderLayer.forward_post transformer.py:211-232.
+
+Tolerance: the kernels keep fp32 accumulators and round the hidden activation to bf16 once (it is an MMA operand);
+outputs are stored in bf16 -> relative L2 <= 6e-3 (one bf16 rounding is 2^-9 = 2e-3 rms).  Train-mode dropout is
+checked with the masks the kernels themselves regenerate, exported by gpvb200_dropout_mask."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _mlp_inputs(cuda, M, dff, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g).to(cuda)
+    x = r(M, 256).to(BF)
+    w1 = (r(dff, 256) / 16).to(BF)
+    w2 = (r(256, dff) / dff ** 0.5).to(BF)
+    b1, b2 = 0.1 * r(dff), 0.1 * r(256)
+    gamma, beta = 1 + 0.1 * r(256), 0.1 * r(256)
+    return x, w1, b1, w2, b2, gamma, beta
+
+
+def _mlp_ref(x, w1, b1, w2, b2, gamma, beta, eps, mask_h=None, mask_o=None, scale=1.0):
+    h = torch.relu(x.float() @ w1.float().t() + b1)
+    if mask_h is not None:
+        h = h * mask_h * scale
+    hb = h.to(BF).float()                       # the kernel feeds FFN2 with the bf16 hidden activation
+    f = hb @ w2.float().t() + b2
+    if mask_o is not None:
+        f = f * mask_o * scale
+    pre = x.float() + f
+    mean = pre.mean(1, keepdim=True)
+    var = pre.var(1, unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    y = (pre - mean) * rstd * gamma + beta
+    return y, h, pre, torch.cat([mean, rstd], 1)
+
+
+@pytest.mark.parametrize("M,dff,seq", [(9600, 2048, 0), (1200, 2048, 300), (3200, 2048, 100), (77, 128, 0), (128, 64, 0)])
+def test_mlp_block_fwd(cuda, M, dff, seq):
+    from gpv1_b200 import kernels as k
+    x, w1, b1, w2, b2, gamma, beta = _mlp_inputs(cuda, M, dff, 1)
+    y, h, pre, st = k.mlp_block_fwd(x, w1, b1, w2, b2, gamma, beta, 1e-5, seq_len=seq)
+    torch.cuda.synchronize()
+    ry, rh, rpre, rst = _mlp_ref(x, w1, b1, w2, b2, gamma, beta, 1e-5)
+    errs = {"y": _rel(y, ry), "h": _rel(h, rh), "pre": _rel(pre, rpre), "mean": _rel(st[:, 0], rst[:, 0]), "rstd": _rel(st[:, 1], rst[:, 1])}
+    print("mlp_block_fwd", (M, dff, seq), {kk: f"{v:.2e}" for kk, v in errs.items()})
+    assert errs["y"] < 6e-3 and errs["h"] < 6e-3 and errs["pre"] < 6e-3, errs
+    assert errs["mean"] < 2e-3 and errs["rstd"] < 2e-3, errs
+    # inference form: nothing saved, same y
+    y2, h2, pre2, st2 = k.mlp_block_fwd(x, w1, b1, w2, b2, gamma, beta, 1e-5, seq_len=seq, save=False)
+    assert h2 is None and pre2 is None and st2 is None and torch.equal(y, y2)
+
+
+def test_mlp_block_fwd_matches_unfused_kernels(cuda):
+    """Same inputs through the three-launch path (GEMM + GEMM + LayerNorm) the engine used before."""
+    from gpv1_b200 import kernels as k
+    M, dff = 9600, 2048
+    x, w1, b1, w2, b2, gamma, beta = _mlp_inputs(cuda, M, dff, 2)
+    y, h, pre, st = k.mlp_block_fwd(x, w1, b1, w2, b2, gamma, beta, 1e-5)
+    h0 = k.linear(x, w1, b1, act=k.ACT_RELU)
+    pre0 = k.linear(h0, w2, b2, residual=x)
+    y0, st0 = k.layernorm_fwd(pre0, gamma, beta, 1e-5)
+    assert (h != h0).float().mean().item() < 1e-3 and _rel(h, h0) < 1e-3   # same k order, same rounding: (nearly) bit-identical
+    assert _rel(pre, pre0) < 4e-3 and _rel(y, y0) < 6e-3 and _rel(st, st0) < 2e-3
+
+
+def test_mlp_block_fwd_dropout(cuda):
+    from gpv1_b200 import kernels as k
+    M, dff = 1200, 2048
+    x, w1, b1, w2, b2, gamma, beta = _mlp_inputs(cuda, M, dff, 3)
+    seed = torch.tensor([5], dtype=torch.int64, device=cuda)
+    dh, do = k.Drop(seed, 41, 0.1), k.Drop(seed, 42, 0.1)
+    y, h, pre, st = k.mlp_block_fwd(x, w1, b1, w2, b2, gamma, beta, 1e-5, seq_len=300, drop_h=dh, drop_o=do)
+    mh, mo = k.dropout_mask(M, dff, dh).float(), k.dropout_mask(M, 256, do).float()
+    ry, rh, rpre, _ = _mlp_ref(x, w1, b1, w2, b2, gamma, beta, 1e-5, mh, mo, dh.scale)
+    assert h.float()[mh == 0].abs().max().item() == 0
+    assert _rel(h, rh) < 6e-3 and _rel(pre, rpre) < 6e-3 and _rel(y, ry) < 6e-3
+    # the GEMM-epilogue dropout of the unfused path draws the same masks from the same (seed, site, row, col)
+    h0 = k.linear(x, w1, b1, act=k.ACT_RELU, drop=dh, drop_mode=k.DROP_POST_ACT)
+    assert (h != h0).float().mean().item() < 1e-3 and _rel(h, h0) < 1e-3

@@ -1048,14 +1048,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
 
   // ---- pair variant: K-major A (plain GEMM / implicit-GEMM convolution), bf16 or fp32 stores, deep contraction, 256 columns
   const int kb_total_pre = d->mode == 0 ? (d->K + 63) / 64 : k_iters_pre;
-  // GPVB200_PAIR_WGRAD=1 (experimental, not yet validated on hardware) extends it to MN-major A with split-K / fp32 atomic
-  // output: the weight gradients of mode 0, whose two streamed operands make them the most L2-bound launches of the step.
-  static int pair_wgrad = -1;
-  if (pair_wgrad < 0) {
-    const char* e = getenv("GPVB200_PAIR_WGRAD");
-    pair_wgrad = e ? atoi(e) : 0;
-  }
-  const bool pair_shape_ok = pair_wgrad ? (d->mode == 0 || !kp.a_mn) : (!kp.a_mn && splits == 1 && !d->d_atomic);
+  const bool pair_shape_ok = !kp.a_mn && splits == 1 && !d->d_atomic;
   // GPVB200_PAIR_BN=128 also pairs the 128-column tiles (per CTA: A 16 KB + B 8 KB per k-block -- the L2 traffic of the single-CTA
   // 256-column tile, so only the halved item count remains; default 256)
   static int pair_min_bn = -1;

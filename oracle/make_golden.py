@@ -36,10 +36,16 @@ def specs_from_model(model):
     return out
 
 
-def make_inputs(B, H, W, Tl, S, seed, tasks):
+def make_inputs(B, H, W, Tl, S, seed, tasks, qpad=None):
+    """qpad: per-sample number of trailing [PAD] = 0 query tokens (what BertTokenizer(padding=True) appends to the shorter
+    queries of a batch, bert.py:12-15); drawn after everything else so that fixtures made without it are unchanged."""
     g = torch.Generator().manual_seed(seed)
     images = torch.randn(B, 3, H, W, generator=g)
     qids = torch.randint(1000, 30000, (B, Tl), generator=g)
+    if qpad is not None:
+        for b, npad in enumerate(qpad):
+            if npad:
+                qids[b, Tl - npad:] = 0
     ans = torch.randint(4, V, (B, S), generator=g)
     ans[:, 0] = 1
     ans[:, -1] = 2
@@ -76,8 +82,8 @@ def crop_list(images, sizes):
     return [images[b, :, :h, :w].clone() for b, (h, w) in enumerate(sizes)]
 
 
-def train_case(model, P, name, B, H, W, Tl, S, seed, tasks, sizes=None):
-    images, qids, ans, targets = make_inputs(B, H, W, Tl, S, seed, tasks)
+def train_case(model, P, name, B, H, W, Tl, S, seed, tasks, sizes=None, qpad=None):
+    images, qids, ans, targets = make_inputs(B, H, W, Tl, S, seed, tasks, qpad)
     model.zero_grad()
     t0 = time.time()
     # outputs (teacher forced), then the loss + grads through the reference's own criterion
@@ -116,7 +122,7 @@ def train_case(model, P, name, B, H, W, Tl, S, seed, tasks, sizes=None):
         if v.requires_grad and v.grad is not None and v.grad.abs().max() > 0:
             assert k in grads, f"oracle has a grad the reference lacks: {k}"
     fix = {
-        "meta": {"B": B, "H": H, "W": W, "Tl": Tl, "S": S, "seed": seed, "tasks": tasks, "V": V, "weights_seed": 0, "sizes": sizes,
+        "meta": {"B": B, "H": H, "W": W, "Tl": Tl, "S": S, "seed": seed, "tasks": tasks, "V": V, "weights_seed": 0, "sizes": sizes, "qpad": qpad,
                  "ref_seconds": t_ref, "oracle_max_err": errs},
         "loss": loss.detach(), "losses": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in ld.items() if v is not None and k != "class_error"},
         "indices": [(q.clone(), t.clone()) for q, t in ind],
@@ -172,6 +178,27 @@ def beam_case(model, P, name, B, H, W, Tl, seed, K, max_text_len):
     print(f"[{name}] beam probs[0] = {out['answer_probs'][0]}")
 
 
+def answers_case(model):
+    """GPV.encode_answers / token_ids_to_words of the reference (gpv.py:377-441) on answers that exercise lower-casing,
+    padding to the batch maximum, truncation to max_text_len, out-of-vocabulary words and the empty answer."""
+    model.cfg.max_text_len = 20
+    vocab = model.vocab
+    words = [w for w in vocab if not w.startswith("__")]
+    long_answer = " ".join(words[i % len(words)] for i in range(3, 3 + 25))      # > max_text_len - 2 words
+    cases = {
+        "mixed": [{"answer": f"{words[0]} {words[5]}"}, {"answer": words[7].upper()}, {"answer": ""}, {"answer": f"{words[2]} zzzunknownzzz {words[9]}"}],
+        "single": [{"answer": words[11]}],
+        "long": [{"answer": long_answer}, {"answer": words[1]}],
+    }
+    out = {}
+    for name, targets in cases.items():
+        padded, ids = model.encode_answers(targets)
+        out[name] = {"targets": targets, "padded": [list(p) for p in padded], "ids": ids.cpu().tolist(),
+                     "words": model.token_ids_to_words(ids.cpu())}
+    json.dump({"V": V, "max_text_len": int(model.cfg.max_text_len), "cases": out}, open(os.path.join(GOLD, "gpv_answers.json"), "w"), indent=1)
+    print("[answers]", {k: [len(r) for r in v["ids"]] for k, v in out.items()})
+
+
 def main():
     assert ref_harness.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
@@ -181,7 +208,7 @@ def main():
     P = TO.make_state(specs, seed=0)
     model.load_state_dict(P, strict=True)
     model.eval()
-    which = sys.argv[1:] or ["train_small", "train_mixed", "greedy", "beam", "train_full", "train_padded"]
+    which = sys.argv[1:] or ["train_small", "train_mixed", "greedy", "beam", "train_full", "train_padded", "train_qpad", "beam5", "answers"]
     if "train_small" in which:
         train_case(model, P, "train_small", B=2, H=224, W=288, Tl=6, S=7, seed=11, tasks=["CocoCaptioning"])
     if "train_mixed" in which:
@@ -194,6 +221,13 @@ def main():
     if "train_padded" in which:
         train_case(model, P, "train_padded", B=3, H=192, W=256, Tl=7, S=5, seed=16, tasks=["CocoCaptioning", "CocoVqa", "CocoDetection"],
                    sizes=[(192, 224), (160, 256), (128, 200)])
+    if "train_qpad" in which:     # mixed-length queries: [PAD] keys masked inside BERT (bert.py:12-21)
+        train_case(model, P, "train_qpad", B=3, H=192, W=256, Tl=9, S=5, seed=17, tasks=["CocoVqa", "CocoCaptioning", "CocoClassification"],
+                   qpad=[0, 3, 5])
+    if "beam5" in which:          # SURVEY 8d config 4 parity shape: B=4, K=5, max_text_len=5
+        beam_case(model, P, "beam5", B=4, H=192, W=256, Tl=6, seed=18, K=5, max_text_len=5)
+    if "answers" in which:
+        answers_case(model)
     if "train_full" in which:
         train_case(model, P, "train_full", B=2, H=480, W=640, Tl=20, S=20, seed=15, tasks=["CocoCaptioning"])
 

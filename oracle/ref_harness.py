@@ -159,7 +159,8 @@ class SyntheticBert(torch.nn.Module):
 
     def forward(self, token_ids, device=None):
         ids = torch.as_tensor(token_ids, dtype=torch.long, device=self.model.embeddings.word_embeddings.weight.device)
-        out = self.model(input_ids=ids, attention_mask=torch.ones_like(ids))
+        # what BertTokenizer(padding=True) returns for ids padded with [PAD] = 0 (bert.py:12-15)
+        out = self.model(input_ids=ids, attention_mask=(ids != 0).long())
         return out[0], {"input_ids": ids}
 
 

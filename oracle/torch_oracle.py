@@ -180,8 +180,12 @@ def roi_mean(c5, boxes):
 
 # ------------------------------------------------------------------------------------------------ BERT
 def bert_forward(P, ids, prefix="bert.model", nheads=12, n_layers=12):
-    """HF BertModel (eval): embeddings (word + position + token_type 0) -> LN(1e-12) -> post-LN encoder, erf-GELU."""
+    """HF BertModel (eval): embeddings (word + position + token_type 0) -> LN(1e-12) -> post-LN encoder, erf-GELU.
+    bert.py:12-21 tokenizes with padding=True and hands BertModel the tokenizer's attention_mask, i.e. (ids != [PAD] = 0):
+    HF adds (1 - mask) * -10000 to the scores of padded KEYS in every layer (transformers 3.0.2 get_extended_attention_mask);
+    padded query rows are still computed and flow on into the (unmasked) co-attention."""
     B, T = ids.shape
+    key_bias = (ids == 0).to(torch.float32)[:, None, None, :] * -10000.0
     e = P[f"{prefix}.embeddings.word_embeddings.weight"][ids] + P[f"{prefix}.embeddings.position_embeddings.weight"][:T][None] \
         + P[f"{prefix}.embeddings.token_type_embeddings.weight"][0][None, None]
     x = ln(P, f"{prefix}.embeddings.LayerNorm", e, 1e-12)
@@ -191,7 +195,7 @@ def bert_forward(P, ids, prefix="bert.model", nheads=12, n_layers=12):
         q = lin(P, p + ".attention.self.query", x).view(B, T, nheads, dh).transpose(1, 2)
         k = lin(P, p + ".attention.self.key", x).view(B, T, nheads, dh).transpose(1, 2)
         v = lin(P, p + ".attention.self.value", x).view(B, T, nheads, dh).transpose(1, 2)
-        a = ((q @ k.transpose(-1, -2)) / math.sqrt(dh)).softmax(-1) @ v
+        a = ((q @ k.transpose(-1, -2)) / math.sqrt(dh) + key_bias).softmax(-1) @ v
         a = a.transpose(1, 2).reshape(B, T, -1)
         x = ln(P, p + ".attention.output.LayerNorm", lin(P, p + ".attention.output.dense", a) + x, 1e-12)
         h = F.gelu(lin(P, p + ".intermediate.dense", x))

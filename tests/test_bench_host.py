@@ -191,3 +191,25 @@ def test_host_targets_single_copy_staging_equals_piecewise_path():
     h = HostTargets(targets, B, S, Q, loss_wts, 0.1, "cpu")
     assert torch.equal(h.ce_targets, f.ce_targets) and torch.equal(h.offsets, f.offsets) and torch.equal(h.ce_row_weight, f.ce_row_weight)
     assert torch.equal(h.boxes, f.boxes[:sumT]) and torch.equal(h.labels, f.labels[:sumT])
+
+
+def test_encode_answers_equals_reference_golden():
+    """GPV.encode_answers / token_ids_to_words against what the REFERENCE's own methods (gpv.py:377-441) returned for the same
+    targets (tests/golden/gpv_answers.json, written by oracle/make_golden.py `answers` from the unmodified reference): lower-casing,
+    `__pad__` up to the batch maximum, truncation to max_text_len, `__unk__` for out-of-vocabulary words, the empty answer."""
+    import json
+    import os
+    from gpv1_b200.model.gpv import GPV
+    from oracle.ref_harness import make_vocab
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gpv_answers.json")))
+    words, _ = make_vocab(gold["V"], 0)
+    stub = types.SimpleNamespace(word_to_idx={w: i for i, w in enumerate(words)}, vocab=list(words), vision_token=torch.zeros(1),
+                                 cfg=types.SimpleNamespace(answering_type="generation", max_text_len=gold["max_text_len"]))
+    for name, case in gold["cases"].items():
+        padded, ids = GPV.encode_answers(stub, case["targets"])
+        assert [list(p) for p in padded] == case["padded"], name
+        assert ids.tolist() == case["ids"], name
+        assert GPV.token_ids_to_words(stub, ids) == case["words"], name
+    assert max(len(r) for r in gold["cases"]["long"]["ids"]) == gold["max_text_len"]          # truncation was exercised
+    unk = stub.word_to_idx["__unk__"]
+    assert any(unk in r for r in gold["cases"]["mixed"]["ids"])                                 # and the OOV path

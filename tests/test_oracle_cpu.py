@@ -17,13 +17,15 @@ def state():
     return TO.make_state([tuple(s) for s in g["specs"]], seed=0)
 
 
-@pytest.mark.parametrize("name", ["train_small", "train_padded", "train_mixed", "train_full"])
+@pytest.mark.parametrize("name", ["train_small", "train_padded", "train_mixed", "train_full", "train_qpad"])
 def test_oracle_loss_and_outputs_equal_reference(state, name):
     from oracle import torch_oracle as TO
     from oracle.make_golden import crop_list, make_inputs
     fix = torch.load(os.path.join(GOLD, f"gpv_{name}.pt"), weights_only=False)
     m = fix["meta"]
-    images, qids, ans, targets = make_inputs(m["B"], m["H"], m["W"], m["Tl"], m["S"], m["seed"], m["tasks"])
+    images, qids, ans, targets = make_inputs(m["B"], m["H"], m["W"], m["Tl"], m["S"], m["seed"], m["tasks"], m.get("qpad"))
+    if name == "train_qpad":
+        assert (qids == 0).sum().item() == sum(m["qpad"]) > 0       # the fixture really exercises [PAD] keys inside BERT
     mask = None
     if m.get("sizes"):
         images, mask = TO.nested(crop_list(images, m["sizes"]))
@@ -56,12 +58,14 @@ def test_oracle_greedy_decode_equals_reference(state):
         assert (out[key] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), key
 
 
-def test_oracle_beam_search_equals_reference(state):
+@pytest.mark.parametrize("name", ["beam", "beam5"])
+def test_oracle_beam_search_equals_reference(state, name):
     """forward_beam_search (gpv.py:256-328): same K sequences in the same order, same log-probabilities
-    (fixture: tests/golden/gpv_beam.pt; max_text_len 5 as scripts/eval.sh uses, so exp(log p) does not underflow)."""
+    (fixtures: tests/golden/gpv_beam.pt B=2 K=3, gpv_beam5.pt B=4 K=5 -- SURVEY 8d config 4's parity shape; max_text_len 5
+    as scripts/eval.sh uses, so exp(log p) does not underflow)."""
     from oracle import torch_oracle as TO
     from oracle.make_golden import make_inputs
-    fix = torch.load(os.path.join(GOLD, "gpv_beam.pt"), weights_only=False)
+    fix = torch.load(os.path.join(GOLD, f"gpv_{name}.pt"), weights_only=False)
     m = fix["meta"]
     images, qids, _, _ = make_inputs(m["B"], m["H"], m["W"], m["Tl"], 4, m["seed"], ["CocoVqa"])
     with torch.no_grad():
@@ -100,3 +104,25 @@ def test_oracle_gradients_equal_reference(state, name):
         # floor: gradients that cancel analytically (query / key projections of the first decoder layer, whose input is zero) are
         # pure round-off in both implementations
         assert (g.reshape(-1)[idx] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-5 * gn + 1e-8 * scale, k
+
+
+def test_bert_key_padding_mask_changes_the_encoding(state):
+    """bert.py:12-21: [PAD] keys are masked inside BERT.  The oracle with padded queries must differ from the same ids treated
+    as ordinary tokens (what an implementation that drops attention_mask computes) by far more than round-off."""
+    from oracle import torch_oracle as TO
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(1000, 30000, (2, 9), generator=g)
+    ids[1, 5:] = 0
+    with torch.no_grad():
+        masked = TO.bert_forward(state, ids)
+        k = math_bias = None
+        # un-masked variant: same embeddings, no key bias -> emulate by giving the pad positions a non-zero id with the PAD embedding
+        P2 = dict(state)
+        w = state["bert.model.embeddings.word_embeddings.weight"].clone()
+        w[1] = w[0]
+        P2["bert.model.embeddings.word_embeddings.weight"] = w
+        ids2 = ids.clone()
+        ids2[ids2 == 0] = 1
+        unmasked = TO.bert_forward(P2, ids2)
+    assert torch.allclose(masked[0], unmasked[0], atol=1e-5)                  # the unpadded sample is unaffected
+    assert (masked[1, :5] - unmasked[1, :5]).abs().max().item() > 1e-2         # real tokens of the padded sample see different keys

@@ -4,16 +4,13 @@ implicit-GEMM convolutions with fused epilogues.  The variant is selected inside
 threshold (GPVB200_PAIR, read once per process) so that every eligible shape below takes it, and checks that it did.
 
     python tools/check_pair.py            # exit code 0 = all shapes match and the pair variant ran
-    python tools/check_pair.py --wgrad    # + the experimental MN-major-A / split-K / atomic extension (GPVB200_PAIR_WGRAD=1)
 """
 import os
 import sys
 
 os.environ.setdefault("GPVB200_PAIR", "8")
 os.environ.setdefault("GPVB200_PAIR_BN", "128")     # cover the 128-column pair tiles too
-WGRAD = "--wgrad" in sys.argv
-if WGRAD:
-    os.environ["GPVB200_PAIR_WGRAD"] = "1"
+WGRAD = False   # (the weight-gradient extension of the pair variant was removed in round 2: it never ran on hardware)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 

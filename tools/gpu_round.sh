@@ -16,15 +16,11 @@ timeout 300 python tools/profile_step.py --out $out/${tag}_timeline > $out/${tag
 echo "timeline exit $?"
 # CTA-pair variant: the validated set, then the experimental weight-gradient extension, then both inside the step
 timeout 200 python tools/check_pair.py > $out/${tag}_pair.log 2>&1; echo "pair check exit $?"
-timeout 200 python tools/check_pair.py --wgrad > $out/${tag}_pair_wgrad.log 2>&1; wg=$?; echo "pair wgrad check exit $wg"; tail -3 $out/${tag}_pair_wgrad.log
 # production kernel, single-CTA vs pair, shape by shape (graph-replayed launches)
 timeout 300 python tools/prof_pair.py > $out/${tag}_prof_pair.txt 2>&1; cat $out/${tag}_prof_pair.txt
 GPVB200_PAIR=16 GPVB200_PAIR_BN=128 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/${tag}_bench_pair16_bn128.json 2>> $out/${tag}_bench.err
 for thr in 16 32; do
   GPVB200_PAIR=$thr timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/${tag}_bench_pair$thr.json 2>> $out/${tag}_bench.err
-  if [ $wg -eq 0 ]; then
-    GPVB200_PAIR=$thr GPVB200_PAIR_WGRAD=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/${tag}_bench_pair${thr}_wgrad.json 2>> $out/${tag}_bench.err
-  fi
 done
 python - <<PY
 import glob, json

@@ -107,7 +107,7 @@ def child(reps=10):
 def main():
     if "--child" in sys.argv:
         return child()
-    settings = [("single", {"GPVB200_PAIR": "0"}), ("pair", {"GPVB200_PAIR": "8"}), ("pair+wgrad", {"GPVB200_PAIR": "8", "GPVB200_PAIR_WGRAD": "1"})]
+    settings = [("single", {"GPVB200_PAIR": "0"}), ("pair", {"GPVB200_PAIR": "8"})]
     rows = {}
     for name, env in settings:
         res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=dict(os.environ, **env), capture_output=True, text=True)

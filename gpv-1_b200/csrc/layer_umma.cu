@@ -439,6 +439,469 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == kLtMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================================================
+// attn_block_fwd: multi-head attention core on tcgen05 for d_model = 256, 8 heads of 32 (DETR encoder / decoder,
+// transformer.py:153-156, 216-227), optionally fused with the output projection, the residual and the LayerNorm:
+//     o = concat_h softmax(scale Q_h K_h^T + key mask) V_h          y = LN(x + drop(o Wo^T + bo))
+// One CTA owns 128 query rows of one image and walks the 8 heads:
+//   S_h  (TMEM [0,320), fp32)  = Q_h K_h^T        SS MMAs, K = 32: A = Q tile (shared memory, resident), B = K tile of the head pair
+//   P_h  (TMEM [320,480), packed bf16 pairs)       softmax by the 8 epilogue warps: row = TMEM lane = thread, the two warps of a
+//                                                  lane quarter split the keys; row maxima / sums cross through shared memory
+//   O_h  (TMEM [480,512))      = P_h V_h           TS MMAs (A = P from tensor memory), B = V tile read MN-major, N = 32
+//   O tile (shared memory, over the Q tile: head h's 32 columns replace Q_h, which is dead by then) = O_h / rowsum, bf16
+// K / V of a head PAIR ([Sk x 64] each, one 128-byte swizzle row per key) stream through a 2-slot ring; scores never leave the
+// chip.  Fused tail: acc (TMEM [0,256)) = O tile . Wo^T (Wo's four k-blocks land in the K/V ring), epilogue as mlp_block_fwd.
+// Dropout on the probabilities uses the same counter-based mask as attention.cu (row = (b H + h) Sq + q, col = key), so the
+// backward kernel regenerates it.
+// =====================================================================================================================
+constexpr uint32_t kKvTileBytes = 38912u;     // [304 keys x 64] bf16
+constexpr uint32_t kKvSlotBytes = 2 * kKvTileBytes;
+
+struct AttnBlkParams {
+  int B, H, Sq, Sk, Skp, split, tps;     // Skp = Sk rounded up to 16; split = first key of column-half 1 (multiple of 32)
+  int nbox, box_rows;                    // a K / V pair tile is loaded as nbox boxes of box_rows keys
+  int fuse;                              // 1: + out-proj + residual + LayerNorm
+  float sl2, eps;
+  const uint8_t* kmask;                  // [B, Sk], 1 = masked key, or null
+  const float* bo;
+  const float* gamma;
+  const float* beta;
+  const bf16* xres;
+  bf16* o;
+  float* lse;
+  bf16* pre;
+  bf16* y;
+  float* stats;
+  long long ldx, ldo, ldpre, ldy;
+  DropArgs drop_p, drop_o;
+  long long* trace;
+  int nchunk;                            // (trace layout only: rows of 8 stamps per role = nchunk + 1)
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(kLtThreads, 1)
+attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmWo,
+                      const __grid_constant__ AttnBlkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                         // Q tile, then O tile (A operand of the output projection)
+  uint8_t* sKV = smem + kTileBytes;           // 2 slots x (K pair tile | V pair tile); later Wo (4 x 32 KB), then output slabs
+  uint64_t* bars = (uint64_t*)(sKV + 2 * kKvSlotBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;       // [2]
+  uint64_t* v_full = bars + 3;       // [2]
+  uint64_t* kv_empty = bars + 5;     // [2]
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint64_t* o_empty = bars + 10;
+  uint64_t* otile_full = bars + 11;
+  uint64_t* wo_full = bars + 12;
+  uint64_t* acc_full = bars + 13;
+  uint64_t* kv_done = bars + 14;     // every MMA that reads the K / V ring has completed (Wo may land there)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+  float* sVec = reinterpret_cast<float*>(bars + 32);   // bo | gamma | beta
+  float* sBo = sVec;
+  float* sGamma = sVec + 256;
+  float* sBeta = sVec + 512;
+  float* sMax = sVec + 768;          // [2 head parity][2 halves][128]
+  float* sSum = sMax + 512;          // [2][2][128]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x;
+  const int img = tile / p.tps, tt = tile % p.tps;
+  const int m0 = img * p.Sq + tt * 128;                 // first query row (global)
+  int rows_valid = p.Sq - tt * 128;
+  rows_valid = rows_valid > 128 ? 128 : rows_valid;
+  const int k0 = img * p.Sk;                            // first key row (global)
+  const int nks = p.Skp >> 4;                           // 16-key steps of P V
+  const int n1 = p.Skp > 256 ? 256 : p.Skp, n2 = p.Skp - n1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    if (p.fuse) tma_prefetch_desc(&tmWo);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], p.nbox);
+      mbar_init(&v_full[i], p.nbox);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 8);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 8);
+    mbar_init(otile_full, 8);
+    mbar_init(wo_full, 4);
+    mbar_init(acc_full, 1);
+    mbar_init(kv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kLtMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_s = tmem_base, t_p = tmem_base + 320u, t_o = tmem_base + 480u;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp < kLtProducers) {
+    // ================================================================== TMA producers: operations dealt round-robin to the warps
+    if (elect_one()) {
+      int op = 0;
+      if (op++ % kLtProducers == warp) {
+        mbar_expect_tx(q_full, kTileBytes);
+        tma_load_4d(sQ, &tmQ, q_full, 0, m0, 0, 0);
+      }
+      const uint32_t box_bytes = (uint32_t)p.box_rows * 128u;
+      for (int g = 0; g < 4; ++g) {
+        const int slot = g & 1;
+        uint8_t* dk = sKV + (size_t)slot * kKvSlotBytes;
+        uint8_t* dv = dk + kKvTileBytes;
+        for (int kv = 0; kv < 2; ++kv) {
+          for (int i = 0; i < p.nbox; ++i) {
+            if (op++ % kLtProducers != warp) continue;
+            mbar_wait(&kv_empty[slot], (((uint32_t)g >> 1) & 1u) ^ 1u);
+            uint64_t* bar = kv ? &v_full[slot] : &k_full[slot];
+            mbar_expect_tx(bar, box_bytes);
+            tma_load_4d((kv ? dv : dk) + (size_t)i * box_bytes, kv ? &tmV : &tmK, bar, g * 64, k0 + i * p.box_rows, 0, 0);
+          }
+        }
+      }
+      if (p.fuse) {
+        for (int kb = 0; kb < 4; ++kb) {
+          if (op++ % kLtProducers != warp) continue;
+          mbar_wait(kv_done, 0);
+          mbar_expect_tx(wo_full, 32768u);
+          tma_load_4d(sKV + (size_t)kb * 32768u, &tmWo, wo_full, kb * 64, 0, 0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kLtMmaWarp) {
+    // ================================================================== MMA issuer
+    const uint32_t idesc_s1 = make_idesc_bf16(128, n1, 0, 0), idesc_s2 = make_idesc_bf16(128, n2 > 0 ? n2 : 16, 0, 0);
+    const uint32_t idesc_pv = make_idesc_bf16(128, 32, 0, 1), idesc_out = make_idesc_bf16(128, 256, 0, 0);
+    const uint32_t qa = smem_u32(sQ);
+    auto issue_s = [&](int h) {       // S = Q_h K_h^T  (two 16-deep steps over d_h = 32)
+      const uint32_t kb = smem_u32(sKV + (size_t)((h >> 1) & 1) * kKvSlotBytes) + (uint32_t)(h & 1) * 64u;
+      const uint32_t ab = qa + (uint32_t)(h >> 1) * kKblkBytes + (uint32_t)(h & 1) * 64u;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint64_t ad = make_sdesc_sw128(ab + ks * 32u, 0u, 1024u);
+        umma_f16(t_s, ad, make_sdesc_sw128(kb + ks * 32u, 0u, 1024u), idesc_s1, ks > 0 ? 1u : 0u);
+        if (n2 > 0) umma_f16(t_s + 256u, ad, make_sdesc_sw128(kb + 32768u + ks * 32u, 0u, 1024u), idesc_s2, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(s_full);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) issue_s(0);
+    __syncwarp();
+    for (int h = 0; h < 8; ++h) {
+      const int slot = (h >> 1) & 1;
+      if (lane == 0) LT_STAMP(1, h, 0);
+      mbar_wait(p_full, (uint32_t)h & 1u);                       // P_h is in tensor memory; S is free again
+      if (lane == 0) LT_STAMP(1, h, 1);
+      if (h < 7 && ((h + 1) & 1) == 0) mbar_wait(&k_full[((h + 1) >> 1) & 1], ((uint32_t)(h + 1) >> 2) & 1u);
+      if ((h & 1) == 0) mbar_wait(&v_full[slot], ((uint32_t)h >> 2) & 1u);
+      mbar_wait(o_empty, ((uint32_t)h & 1u) ^ 1u);               // O_{h-1} has been read out
+      if (lane == 0) LT_STAMP(1, h, 2);
+      tc_fence_after();
+      if (elect_one()) {
+        if (h < 7) issue_s(h + 1);
+        const uint32_t vb = smem_u32(sKV + (size_t)slot * kKvSlotBytes + kKvTileBytes) + (uint32_t)(h & 1) * 64u;
+        for (int ks = 0; ks < nks; ++ks)
+          umma_f16_ts(t_o, t_p + (uint32_t)(ks * 8), make_sdesc_sw128(vb + (uint32_t)ks * 2048u, 1024u, 1024u), idesc_pv, ks > 0 ? 1u : 0u);
+        umma_commit(o_full);
+        LT_STAMP(1, h, 3);
+        if (h & 1) umma_commit(&kv_empty[slot]);
+        if (h == 7) umma_commit(kv_done);
+      }
+      __syncwarp();
+    }
+    if (p.fuse) {
+      mbar_wait(otile_full, 0);
+      mbar_wait(wo_full, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ad0 = make_sdesc_sw128(qa, 0u, 1024u);
+        const uint64_t bd0 = make_sdesc_sw128(smem_u32(sKV), 0u, 1024u);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          umma_f16(t_s, ad0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4), bd0 + (uint64_t)(((k >> 2) * 32768 + (k & 3) * 32) >> 4), idesc_out,
+                   k > 0 ? 1u : 0u);
+        umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================== softmax / epilogue warps
+    const int e = warp - kLtEpiWarp0;
+    const int q = warp & 3, half = e >> 2;
+    const int r = q * 32 + lane;
+    const long long grow = (long long)m0 + r;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const int base_key = half ? p.split : 0;
+    const int nkeys = half ? p.Skp - p.split : p.split;
+    const int nch = (nkeys + 31) >> 5;                 // <= 5
+    const uint32_t dkey_p = DROP && p.drop_p.seed ? drop_key(*p.drop_p.seed, p.drop_p.site) : 0u;
+    const uint32_t dkey_o = DROP && p.drop_o.seed ? drop_key(*p.drop_o.seed, p.drop_o.site) : 0u;
+    uint32_t ok = 0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (q * 32 + 8 * jj + (lane >> 2) < rows_valid) ok |= 1u << jj;
+    const long long crow0 = (long long)m0 + q * 32 + (lane >> 2);
+    if (p.fuse) {
+      const int t = threadIdx.x - kLtEpiWarp0 * 32;
+      if (t < 64) reinterpret_cast<float4*>(sBo)[t] = __ldg(reinterpret_cast<const float4*>(p.bo) + t);
+      else if (t < 128) reinterpret_cast<float4*>(sGamma)[t - 64] = __ldg(reinterpret_cast<const float4*>(p.gamma) + t - 64);
+      else if (t < 192) reinterpret_cast<float4*>(sBeta)[t - 128] = __ldg(reinterpret_cast<const float4*>(p.beta) + t - 128);
+    }
+    // keys this thread's chunks may use: inside [0, Sk) and not masked (same for every head)
+    uint32_t vmask[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      uint32_t m = 0;
+      if (c < nch) {
+        for (int i = 0; i < 32; ++i) {
+          const int key = base_key + c * 32 + i;
+          bool v = key < p.Sk && (c * 32 + i) < nkeys;
+          if (v && p.kmask != nullptr) v = p.kmask[(long long)img * p.Sk + key] == 0;
+          m |= (uint32_t)v << i;
+        }
+      }
+      vmask[c] = m;
+    }
+    const uint32_t hs = (uint32_t)((p.Sk + 1) >> 1);
+    float m_prev = 0.f;
+
+    // O_h (32 fp32 columns; this warp takes 16) / rowsum -> bf16 -> O tile in shared memory (where Q_h was); lse
+    auto o_epilogue = [&](int hh, float m_h) {
+      mbar_wait(o_full, (uint32_t)hh & 1u);
+      tc_fence_after();
+      uint32_t acc[16];
+      tmem_ld_32x32b_x16(t_o + t_lane + (uint32_t)(half * 16), acc);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      const float l = sSum[((hh & 1) * 2 + 0) * 128 + r] + sSum[((hh & 1) * 2 + 1) * 128 + r];
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) * inv;
+      const uint32_t ob = smem_u32(sQ) + (uint32_t)(hh >> 1) * kKblkBytes;
+      sts128(ob + sw128_off(r, (hh & 1) * 4 + half * 2), pack8(v));
+      sts128(ob + sw128_off(r, (hh & 1) * 4 + half * 2 + 1), pack8(v + 8));
+      if (half == 0 && r < rows_valid && p.lse != nullptr)
+        p.lse[((long long)img * p.H + hh) * p.Sq + tt * 128 + r] = m_h * p.sl2 + log2f(l);
+    };
+
+    for (int h = 0; h < 8; ++h) {
+      const bool tr = e == 0 && lane == 0;
+      if (tr) LT_STAMP(2, h, 0);
+      mbar_wait(s_full, (uint32_t)h & 1u);
+      if (tr) LT_STAMP(2, h, 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum over this warp's keys
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (c < nch) {
+          uint32_t sc[32];
+          tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(base_key + c * 32), sc);
+          tmem_ld_wait();
+          const uint32_t vm = vmask[c];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if ((vm >> i) & 1u) mx = fmaxf(mx, __uint_as_float(sc[i]));
+        }
+      }
+      if (tr) LT_STAMP(2, h, 2);
+      sMax[((h & 1) * 2 + half) * 128 + r] = mx;
+      named_bar_sync(1, kLtEpiThreads);
+      if (tr) LT_STAMP(2, h, 3);
+      const float m = fmaxf(mx, sMax[((h & 1) * 2 + (half ^ 1)) * 128 + r]);
+      const float ms = (m == -INFINITY) ? 0.f : m;
+      if (h > 0) o_epilogue(h - 1, m_prev);          // also: P V of head h-1 is complete, so P may be overwritten
+      m_prev = ms;
+      if (tr) LT_STAMP(2, h, 4);
+      // ---- pass 2: p = exp2((s - m) * scale * log2 e), row sum over every key, dropout on what goes into P V
+      float sum = 0.f;
+      const uint32_t prow = ((uint32_t)(img * p.H + h) * (uint32_t)p.Sq + (uint32_t)(tt * 128 + r)) * hs;
+      const float nms = -ms * p.sl2;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (c < nch) {
+          uint32_t sc[32];
+          tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(base_key + c * 32), sc);
+          tmem_ld_wait();
+          const uint32_t vm = vmask[c];
+          float pv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float pe = exp2f(fmaf(__uint_as_float(sc[i]), p.sl2, nms));
+            pv[i] = ((vm >> i) & 1u) ? pe : 0.f;
+            sum += pv[i];
+          }
+          if (DROP && p.drop_p.seed) {
+            const uint32_t cb = prow + (uint32_t)((base_key + c * 32) >> 1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) drop_pair(pv[2 * i], pv[2 * i + 1], dkey_p, cb + i, p.drop_p.thresh16, p.drop_p.scale);
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+          tmem_st_32x32b_x16(t_p + t_lane + (uint32_t)((base_key + c * 32) >> 1), pk);
+        }
+      }
+      if (tr) LT_STAMP(2, h, 5);
+      sSum[((h & 1) * 2 + half) * 128 + r] = sum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (tr) LT_STAMP(2, h, 6);
+    }
+    named_bar_sync(1, kLtEpiThreads);                // the row sums of head 7 are visible
+    o_epilogue(7, m_prev);
+    fence_proxy_async();                             // O tile (generic-proxy stores) -> visible to the output projection's MMAs
+    named_bar_sync(1, kLtEpiThreads);
+    if (lane == 0) mbar_arrive(otile_full);
+    // ---- attention output for the backward pass: this warp's 32 rows x 2 k-blocks, 4 rows x 128 bytes per instruction
+    if (p.o != nullptr) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int kb = half * 2 + kk;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int rr = q * 32 + 4 * jj + (lane >> 3);
+          const uint4 v = lds128(smem_u32(sQ) + (uint32_t)kb * kKblkBytes + sw128_off(rr, lane & 7));
+          if (rr < rows_valid) *reinterpret_cast<uint4*>(p.o + ((long long)m0 + rr) * p.ldo + kb * 64 + (lane & 7) * 8) = v;
+        }
+      }
+    }
+    if (p.fuse) {
+      // ---- pre = acc + bo (dropout) + x;  y = LayerNorm(pre): as mlp_block_fwd's final epilogue, residual read from global memory
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const uint32_t slab = smem_u32(sKV) + (uint32_t)e * 4096u;      // Wo is dead once acc is complete
+      const uint32_t co = 16u * slab_slot(lane >> 2, lane & 3);
+      uint32_t own[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) own[i] = 16u * slab_slot(lane, i);
+      const bf16* xrow = p.xres + grow * p.ldx + half * 128;
+      const bool rv = r < rows_valid;
+      float sum = 0.f, sq = 0.f;
+      {
+        uint32_t acc[2][32];
+        uint4 xr[2][4];
+        tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(half * 128), acc[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xr[0][i] = rv ? ldg_u4(xrow + 8 * i) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = half * 128 + c * 32;
+          tmem_ld_wait();
+          if (c < 3) {
+            tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(col0 + 32), acc[(c + 1) & 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xr[(c + 1) & 1][i] = rv ? ldg_u4(xrow + (c + 1) * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
+          }
+          float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(sBo + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i];
+            v[4 * i] = __uint_as_float(acc[c & 1][4 * i]) + bb.x;
+            v[4 * i + 1] = __uint_as_float(acc[c & 1][4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(acc[c & 1][4 * i + 2]) + bb.z;
+            v[4 * i + 3] = __uint_as_float(acc[c & 1][4 * i + 3]) + bb.w;
+          }
+          if (DROP && p.drop_o.seed) {
+            const uint32_t base = (uint32_t)grow * 128u + (uint32_t)(col0 >> 1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) drop_pair(v[2 * i], v[2 * i + 1], dkey_o, base + i, p.drop_o.thresh16, p.drop_o.scale);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) unpack8(xr[c & 1][i], v + 8 * i, true);
+          uint32_t wv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            sum += v[i];
+            sq += v[i] * v[i];
+            wv[i] = __float_as_uint(v[i]);
+          }
+          tmem_st_32x32b_x32(t_s + t_lane + (uint32_t)col0, wv);
+          if (p.pre != nullptr) {
+            const uint32_t sl = slab + 2048u * (uint32_t)(c & 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sts128(sl + own[i], pack8(v + 8 * i));
+            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if ((ok >> jj) & 1u)
+                *reinterpret_cast<uint4*>(p.pre + (crow0 + 8 * jj) * p.ldpre + col0 + (lane & 3) * 8) = lds128(sl + co + 512u * jj);
+          }
+        }
+      }
+      tmem_st_wait();
+      float2* part = reinterpret_cast<float2*>(sMax);    // [2][128] float2 = 2 KB: the softmax exchange arrays are idle
+      part[half * 128 + r] = make_float2(sum, sq);
+      named_bar_sync(1, kLtEpiThreads);
+      const float2 other = part[(half ^ 1) * 128 + r];
+      const float mean = (sum + other.x) * (1.0f / 256.0f);
+      const float var = fmaxf((sq + other.y) * (1.0f / 256.0f) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      if (half == 0 && rv && p.stats != nullptr) {
+        p.stats[grow * 2] = mean;
+        p.stats[grow * 2 + 1] = rstd;
+      }
+      {
+        uint32_t acc[2][32];
+        tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(half * 128), acc[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = half * 128 + c * 32;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(col0 + 32), acc[(c + 1) & 1]);
+          float v[32];
+          const float4* g4 = reinterpret_cast<const float4*>(sGamma + col0);
+          const float4* e4 = reinterpret_cast<const float4*>(sBeta + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 gg = g4[i], ee = e4[i];
+            v[4 * i] = (__uint_as_float(acc[c & 1][4 * i]) - mean) * rstd * gg.x + ee.x;
+            v[4 * i + 1] = (__uint_as_float(acc[c & 1][4 * i + 1]) - mean) * rstd * gg.y + ee.y;
+            v[4 * i + 2] = (__uint_as_float(acc[c & 1][4 * i + 2]) - mean) * rstd * gg.z + ee.z;
+            v[4 * i + 3] = (__uint_as_float(acc[c & 1][4 * i + 3]) - mean) * rstd * gg.w + ee.w;
+          }
+          const uint32_t sl = slab + 2048u * (uint32_t)(c & 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts128(sl + own[i], pack8(v + 8 * i));
+          __syncwarp();
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            if ((ok >> jj) & 1u)
+              *reinterpret_cast<uint4*>(p.y + (crow0 + 8 * jj) * p.ldy + col0 + (lane & 3) * 8) = lds128(sl + co + 512u * jj);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kLtMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
 // Launch with programmatic dependent launch allowed (GPVB200_PDL=0 turns it off), opting in to the full shared memory.
 template <typename K, typename... A>
 static int launch_layer(K kern, const char* what, int grid, size_t smem, cudaStream_t st, A... args) {
@@ -546,4 +1009,61 @@ extern "C" int gpvb200_mlp_block_fwd(const void* x, int64_t ldx, const void* w1,
   const bool drop = p.drop_h.seed != nullptr || p.drop_o.seed != nullptr;
   if (drop) return launch_layer(mlp_block_fwd_kernel<true>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
   return launch_layer(mlp_block_fwd_kernel<false>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
+}
+
+extern "C" int gpvb200_attn_block_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                      const uint8_t* key_mask, int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh, float scale,
+                                      void* o, int64_t ldo, float* lse, const void* wo, int64_t ldwo, const float* bo, const void* x,
+                                      int64_t ldx, const float* gamma, const float* beta, float eps, void* pre, int64_t ldpre, void* y,
+                                      int64_t ldy, float* stats, const void* drop_seed, uint32_t site_p, float p_p, uint32_t site_o,
+                                      float p_o, void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(q && k && v, "attn_block_fwd: null operand");
+  GPV_REQUIRE(H == 8 && dh == 32, "attn_block_fwd: built for 8 heads of 32 (got %d x %d)", H, dh);
+  GPV_REQUIRE(B > 0 && Sq > 0 && Sk > 0 && Sk <= 304, "attn_block_fwd: needs 1 <= Sk <= 304 (got Sq %d, Sk %d)", Sq, Sk);
+  GPV_REQUIRE(o != nullptr || wo != nullptr, "attn_block_fwd: nothing to write");
+  GPV_REQUIRE((ldo & 7) == 0 && (ldpre & 7) == 0 && (ldy & 7) == 0 && (ldx & 7) == 0, "attn_block_fwd: row strides must be multiples of 8");
+  GPV_REQUIRE((((uintptr_t)o | (uintptr_t)pre | (uintptr_t)y | (uintptr_t)x | (uintptr_t)bo | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+              "attn_block_fwd: outputs / vectors must be 16-byte aligned");
+  GPV_REQUIRE(p_p < 1.f && p_o < 1.f, "attn_block_fwd: dropout p must be < 1");
+  AttnBlkParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
+  p.Skp = (Sk + 15) & ~15;
+  p.split = ((p.Skp / 2) + 31) & ~31;
+  if (p.split > p.Skp) p.split = p.Skp;
+  p.tps = (Sq + 127) / 128;
+  if (p.Skp <= 256) { p.nbox = 1; p.box_rows = p.Skp; } else { p.nbox = 2; p.box_rows = p.Skp / 2; }
+  p.fuse = wo != nullptr;
+  if (p.fuse) GPV_REQUIRE(bo && x && gamma && beta && y, "attn_block_fwd: the fused tail needs bo, x, gamma, beta and y");
+  p.sl2 = scale * 1.4426950408889634f;
+  p.eps = eps;
+  p.kmask = key_mask;
+  p.bo = bo; p.gamma = gamma; p.beta = beta;
+  p.xres = (const bf16*)x; p.o = (bf16*)o; p.lse = lse; p.pre = (bf16*)pre; p.y = (bf16*)y; p.stats = stats;
+  p.ldx = ldx; p.ldo = ldo; p.ldpre = ldpre; p.ldy = ldy;
+  fill_drop(&p.drop_p, drop_seed, site_p, p_p);
+  fill_drop(&p.drop_o, drop_seed, site_o, p_o);
+  p.trace = g_layer_trace;
+  p.nchunk = 8;
+  CUtensorMap mq, mk, mv, mw;
+  {
+    const uint32_t one4[4] = {1, 1, 1, 1};
+    const uint64_t dq[4] = {64, (uint64_t)B * Sq, 4, 1}, sq[3] = {(uint64_t)ldq, 64, 256};
+    const uint32_t bq[4] = {64, 128, 4, 1};
+    if ((rc = make_map(&mq, q, dq, sq, bq, one4))) return rc;
+  }
+  if ((rc = map2d(&mk, k, 256, (uint64_t)B * Sk, (uint64_t)ldk, 64, (uint32_t)p.box_rows))) return rc;
+  if ((rc = map2d(&mv, v, 256, (uint64_t)B * Sk, (uint64_t)ldv, 64, (uint32_t)p.box_rows))) return rc;
+  if (p.fuse) {
+    if ((rc = map2d(&mw, wo, 256, 256, (uint64_t)ldwo, 64, 256))) return rc;
+  } else {
+    mw = mk;
+  }
+  const int grid = B * p.tps;
+  const size_t smem = 1024 + kTileBytes + 2 * kKvSlotBytes + 256 + (768 + 512 + 512) * 4;
+  const bool drop = p.drop_p.seed != nullptr || p.drop_o.seed != nullptr;
+  if (drop) return launch_layer(attn_block_fwd_kernel<true>, "attn_block_fwd", grid, smem, (cudaStream_t)stream, mq, mk, mv, mw, p);
+  return launch_layer(attn_block_fwd_kernel<false>, "attn_block_fwd", grid, smem, (cudaStream_t)stream, mq, mk, mv, mw, p);
 }

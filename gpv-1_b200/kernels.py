@@ -327,6 +327,34 @@ def mlp_block_fwd(x, w1, b1, w2, b2, gamma, beta, eps, *, save=True, seq_len=0, 
     return y, h, pre, stats
 
 
+def attn_block_fwd(q, k, v, *, B, Sq, Sk, scale, key_mask=None, wo=None, bo=None, x=None, gamma=None, beta=None, eps=1e-5,
+                   save=True, drop_p=None, drop_o=None, H=8, dh=32):
+    """tcgen05 attention for d_model = 256 (8 x 32).  wo None: returns (o, lse).  Otherwise the output projection, residual and
+    LayerNorm run in the same kernel: returns (y, o, lse, pre, stats) (o / lse / pre / stats None when save is False)."""
+    dev = q.device
+    D = H * dh
+    fuse = wo is not None
+    need = save or not fuse
+    o = torch.empty((B * Sq, D), device=dev, dtype=BF16) if need else None
+    lse = torch.empty((B, H, Sq), device=dev, dtype=torch.float32) if need else None
+    y = torch.empty((B * Sq, D), device=dev, dtype=BF16) if fuse else None
+    pre = torch.empty((B * Sq, D), device=dev, dtype=BF16) if fuse and save else None
+    stats = torch.empty((B * Sq, 2), device=dev, dtype=torch.float32) if fuse and save else None
+    d0 = drop_p if drop_p is not None else drop_o
+    i64, f32, u32 = ctypes.c_int64, ctypes.c_float, ctypes.c_uint32
+    _C.check(_C.lib().gpvb200_attn_block_fwd(
+        _C.ptr(_req(q, BF16)), i64(q.stride(0)), _C.ptr(_req(k, BF16)), i64(k.stride(0)), _C.ptr(_req(v, BF16)), i64(v.stride(0)),
+        _C.ptr(_req(key_mask, torch.uint8)), B, H, Sq, Sk, dh, f32(scale), _C.ptr(o), i64(D), _C.ptr(lse),
+        _C.ptr(_req(wo, BF16)), i64(wo.stride(0) if fuse else 0), _C.ptr(_req(bo, torch.float32)), _C.ptr(_req(x, BF16)),
+        i64(x.stride(0) if x is not None else 0), _C.ptr(_req(gamma, torch.float32)), _C.ptr(_req(beta, torch.float32)), f32(eps),
+        _C.ptr(pre), i64(D), _C.ptr(y), i64(D), _C.ptr(stats), _C.ptr(d0.seed) if d0 is not None else ctypes.c_void_p(0),
+        u32(drop_p.site if drop_p is not None else 0), f32(drop_p.p if drop_p is not None else 0.0),
+        u32(drop_o.site if drop_o is not None else 0), f32(drop_o.p if drop_o is not None else 0.0), _C.stream_ptr()), "attn_block_fwd")
+    if not fuse:
+        return o, lse
+    return y, o, lse, pre, stats
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def add_rowbcast(x, p, *, M=None, out=None):
     """out[m] = x[m] + p[m % P]; x may be None (pure broadcast of p over M rows)."""

@@ -181,6 +181,21 @@ int gpvb200_mlp_block_fwd(const void* x, int64_t ldx, const void* w1, int64_t ld
                           int32_t seq_len, const void* drop_seed, uint32_t site_h, float p_h, uint32_t site_o, float p_o,
                           void* stream);
 
+/* Multi-head attention for d_model = 256 (8 heads x 32) on tcgen05, optionally with the output projection, residual and LayerNorm
+ * in the same kernel: o = concat_h softmax(scale Q_h K_h^T + key mask) V_h;  y = LayerNorm(x + drop_o(o Wo^T + bo)).
+ * nn.MultiheadAttention core + out_proj + dropout + residual + norm of TransformerEncoderLayer.forward_post transformer.py:153-157
+ * and TransformerDecoderLayer.forward_post transformer.py:216-227.  q [B*Sq, >=256], k / v [B*Sk, >=256] bf16 token-major (slices
+ * of a packed projection buffer: row strides ldq / ldk / ldv), Sk <= 304; key_mask [B, Sk] uint8 (1 = padded key) or NULL.
+ * o [B*Sq, 256] bf16 and lse [B, H, Sq] fp32 (log2 domain) are what gpvb200_attention_bwd reads (either may be NULL).
+ * wo = NULL: attention core only.  Otherwise wo [256, 256] bf16, bo / gamma / beta fp32, x = residual [B*Sq, 256] bf16, outputs
+ * y (required), pre, stats (NULL to skip).  site_p / p_p: dropout on the probabilities (same mask as gpvb200_attention_fwd_drop),
+ * site_o / p_o: dropout on the projected output before the residual. */
+int gpvb200_attn_block_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* key_mask,
+                           int32_t B, int32_t H, int32_t Sq, int32_t Sk, int32_t dh, float scale, void* o, int64_t ldo, float* lse,
+                           const void* wo, int64_t ldwo, const float* bo, const void* x, int64_t ldx, const float* gamma,
+                           const float* beta, float eps, void* pre, int64_t ldpre, void* y, int64_t ldy, float* stats,
+                           const void* drop_seed, uint32_t site_p, float p_p, uint32_t site_o, float p_o, void* stream);
+
 /* Developer hook: a device buffer of int64 that CTA 0 of the layer kernels fills with clock64() stamps of its producer /
  * MMA / epilogue roles ([3][chunks + 1][8]); NULL switches it off (the default).  tools/trace_layer.py. */
 int gpvb200_layer_trace(void* buf);

@@ -165,7 +165,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_steps(steps, warmup, B_cpu=2, seed=1, workload="configs[1]"):
+def cpu_reference_steps(steps, warmup, B_cpu=4, seed=1, workload="configs[1]"):
     """The reference's arithmetic (fp32 oracle port of GPV.forward + criterion + autograd backward) on the host cores.
     Each step is a bounded sample of the workload: B_cpu images of the same shape instead of 32."""
     from oracle import torch_oracle as TO
@@ -198,7 +198,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
+    steps = max(1, min(args.steps, 4))                 # bounded sample: ~3 s per step of 4 samples on 16 host threads
     warmup = max(1, min(args.warmup, 1))
     sps, cores, sample, ms = cpu_reference_steps(steps, warmup, workload=args.workload)
     line = {"impl": "reference", "metric": "samples/sec (img+query fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
@@ -292,6 +292,96 @@ def workload_name(B, workload="configs[1]"):
     return f"configs[1]: batch={B}/GPU synthetic 3x{H_IMG}x{W_IMG} + {T_L}-tok prompts + {S_ANS}-tok answers, full fwd+bwd with SetCriterion, V={V_BENCH}"
 
 
+# ---------------------------------------------------------------------------------------------------- extra measurements
+def torch_eager_gpu(B, dev, steps=3):
+    """The practical bar: the SAME arithmetic executed by stock PyTorch-2.11 eager kernels (cuDNN / cuBLAS / ATen) on
+    this B200 -- the fp32 restatement of GPV.forward + criterion + autograd backward (oracle/torch_oracle.py, pinned against the
+    reference), once in fp32 (torch defaults: TF32 convolutions, fp32 matmuls) and once under torch.autocast(bfloat16), at the
+    bench batch.  A baseline measured next to the product, never on its path."""
+    from oracle import torch_oracle as TO
+    import oracle
+    oracle.build()
+    from gpv1_b200.config import load_config
+    from gpv1_b200.model.spec import gpv_specs
+    specs = gpv_specs(load_config().model, V_BENCH)
+    P = TO.make_state([(s.name, s.shape, s.kind) for s in specs], seed=0)
+    Pg = {n: (t.to(dev).requires_grad_(True) if s.kind == "param" and not n.startswith("bert.") else t.to(dev)) for (n, t), s in zip(P.items(), specs)}
+    images, qids, ans, targets = make_batch(B, seed=1000)
+    images, qids, ans = images.to(dev), qids.to(dev), ans.to(dev)
+    targets = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
+    out = {"batch": B, "what": "oracle/torch_oracle.py (fp32 restatement of the reference modules) run by stock torch eager kernels on this GPU, "
+                               "fwd + criterion + autograd bwd, CUDA events, 1 warm-up"}
+    for name, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def step():
+            for t in Pg.values():
+                t.grad = None
+            if ctx is None:
+                loss = TO.gpv_forward(Pg, images, qids, ans, targets)
+            else:
+                with ctx:
+                    loss = TO.gpv_forward(Pg, images, qids, ans, targets)
+            loss.backward()
+            return loss
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "loss": float(loss.detach())}
+    for t in Pg.values():
+        t.grad = None
+    return out
+
+
+def measure_decode(model, dev, reps=5, K=5):
+    """BASELINE configs[0] (one 480x640 image + a 6-token query, greedy, latency) and configs[3] (beam_size = 5, batch = 64,
+    inference only) through the public API (GPV.forward / GPV.forward_beam_search), inputs in pinned host memory, generated
+    token ids read back to the host inside the timed region; whole-call CUDA graph (model.inference_graphs)."""
+    was_training, graphs = model.training, model.inference_graphs
+    model.eval()
+    model.inference_graphs = True
+    L = model.cfg.max_text_len
+    out = {}
+    try:
+        with torch.no_grad():
+            for key, B in (("configs[0] greedy, 1 image", 1), ("configs[3] beam_size=5, batch=64", 64)):
+                images, qids, _, _ = make_batch(B, seed=4)
+                images, qids = images.pin_memory(), (qids[:, :6] if B == 1 else qids).contiguous().pin_memory()
+                if B == 1:
+                    fn = lambda: model(images.to(dev, non_blocking=True), qids.to(dev, non_blocking=True), None)["answer_logits"].argmax(-1).cpu()
+                else:
+                    fn = lambda: model.forward_beam_search(images.to(dev, non_blocking=True), qids.to(dev, non_blocking=True), K)["answers"]
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                toks = B * (L if B == 1 else K * (L - 1))
+                out[key] = {"ms_per_call": ms, "samples_per_s": B / ms * 1e3, "decoded_tokens_per_s": toks / ms * 1e3, "max_text_len": L,
+                            "h2d_bytes_per_call": images.numel() * 4 + qids.numel() * 8}
+    finally:
+        model.inference_graphs = graphs
+        model._inf_graphs.clear()
+        model.train(was_training)
+    return out
+
+
+def lib_sha16():
+    import hashlib
+    from gpv1_b200 import _C
+    with open(_C.SO_PATH, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:16]
+
+
 # ---------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -308,6 +398,7 @@ def main():
     ap.add_argument("--profiling", action="store_true", help="under ncu only: allow fewer than 3 warm-up steps, skip the e2e loop")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown of one extra step to this file")
     ap.add_argument("--eval-mode", action="store_true", help="time the dropout-free (model.eval()) arithmetic instead of the training mode")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra measurements of the line (multitask, decode, torch eager GPU bar)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -463,11 +554,11 @@ def main():
 
     # third number: the same end-to-end step fed with the loader's raw format, uint8 NHWC pixels, whose
     # ToTensor + Normalize (coco_generic_dataset.py:31-32) are folded into the stem's read: a quarter of the H2D bytes
-    ms_e2e_u8 = None
+    ms_e2e_u8 = ms_e2e_u8_pf = None
     if not args.no_graph and not args.breakdown and not multitask:
         g8 = torch.Generator().manual_seed(2000 + rank)
         h_u8 = torch.randint(0, 256, (B, H_IMG, W_IMG, 3), generator=g8, dtype=torch.uint8).pin_memory()
-        model.capture_step(h_u8.to(dev), d_qids, d_ans, d_targets)
+        model.capture_step(h_u8.to(dev), d_qids, d_ans, d_targets, add=True)
 
         def step_e2e_u8():
             loss = model(h_u8, h_qids, h_ans, h_targets)
@@ -477,6 +568,76 @@ def main():
         for _ in range(2):
             step_e2e_u8()
         ms_e2e_u8 = timed(step_e2e_u8, args.steps)
+
+        # the headline `e2e`: the loader's raw uint8 batches staged one step ahead by data.DevicePrefetcher -- every timed step
+        # still copies one batch of pinned host pixels + ids + targets to the device and reads the loss back to the host
+        from gpv1_b200.data import DevicePrefetcher
+
+        def host_batches_u8():
+            while True:
+                yield h_u8, h_qids, h_targets
+
+        pf8 = DevicePrefetcher(host_batches_u8(), dev)
+
+        def step_e2e_u8_pf():
+            imgs, q, tg = next(pf8)
+            loss = model(imgs, q, h_ans, tg)
+            loss.backward()
+            return loss.item()
+
+        for _ in range(2):
+            step_e2e_u8_pf()
+        ms_e2e_u8_pf = timed(step_e2e_u8_pf, args.steps)
+
+    # DDP check on hardware: after a step every rank must hold the same (averaged) gradient arena
+    grads_equal = None
+    if world > 1:
+        step_resident()
+        torch.cuda.synchronize()
+        ga = model.engine.grad_arena
+        sig = torch.stack((ga.double().sum(), ga.double().square().sum(), ga[::4097].double().abs().sum())).to(dev)
+        allsig = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(allsig, sig)
+        grads_equal = all(torch.equal(a, allsig[0]) for a in allsig) and bool(torch.isfinite(sig).all()) and sig[1].item() > 0
+
+    # BASELINE configs[2]: the multitask stream (answer length varies per step) on the same replicas, resident and end to end
+    multitask_line = None
+    if not args.no_extras and not multitask and not args.no_graph and not args.breakdown:
+        mt = make_multitask_batches(args.multitask_batches, B, seed=3000 + rank)
+        mt_dev = [(i.to(dev), q.to(dev), a.to(dev), [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in t.items()} for t in tg])
+                  for i, q, a, tg in mt]
+        mt_host = [(i.pin_memory(), q.pin_memory(), a.pin_memory(), [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in t.items()} for t in tg])
+                   for i, q, a, tg in mt]
+        seen = set()
+        for b in mt_dev:
+            if b[2].shape[1] not in seen:
+                seen.add(b[2].shape[1])
+                model.capture_step(*b, add=True)
+        mturn = [0]
+
+        def step_mt():
+            mturn[0] += 1
+            loss = model(*mt_dev[mturn[0] % len(mt_dev)])
+            loss.backward()
+            return loss
+
+        def step_mt_e2e():
+            mturn[0] += 1
+            loss = model(*mt_host[mturn[0] % len(mt_host)])
+            loss.backward()
+            return loss.item()
+
+        for _ in range(max(3, len(mt_dev))):
+            step_mt()
+        ms_mt = timed(step_mt, args.steps)
+        for _ in range(2):
+            step_mt_e2e()
+        ms_mt_e2e = timed(step_mt_e2e, args.steps)
+        multitask_line = {"workload": workload_name(B, "multitask"), "value": world * B * args.steps / (ms_mt / 1e3), "unit": "samples/s",
+                          "ms_per_step": ms_mt / args.steps, "answer_lengths": sorted(seen),
+                          "e2e": {"value": world * B * args.steps / (ms_mt_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_mt_e2e / args.steps,
+                                  "what": "pinned fp32 host batches copied inside the call, loss read back"}}
+        del mt_dev, mt_host
 
     breakdown = None
     if rank == 0 and args.breakdown:
@@ -530,16 +691,18 @@ def main():
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = gf_all * B / ms_step              # TFLOP/s per GPU: GFLOP/sample * samples / ms
     traffic = gemm_traffic = None
-    try:                                     # DRAM bytes from the committed ncu pass (profiles/step_traffic.json): whole step, and per GEMM launch
+    traffic_src = "null: no ncu DRAM-byte pass of THIS build of libgpvb200.so is committed (profiles/step_traffic.json carries the sha of the library it measured)"
+    try:                                     # DRAM bytes from the committed ncu pass, used only when it measured this very library
         tj = json.load(open(os.path.join(ROOT, "profiles", "step_traffic.json")))
-        traffic, gemm_traffic = tj["dram_bytes_per_step"], tj["gemm_kernel"]["dram_bytes_per_launch"]
+        if tj.get("lib_sha16") == lib_sha16():
+            traffic, gemm_traffic = tj["dram_bytes_per_step"], tj["gemm_kernel"]["dram_bytes_per_launch"]
+            traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum of this build (profiles/step_traffic.json, lib_sha16 matches)"
     except (OSError, KeyError, ValueError):
         pass
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)"
     step_roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "what": f"whole step as one unit: {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd ({gf_fwd:.1f} fwd) x {B} samples / step "
-                             "time (graph replay); traffic = DRAM bytes of one step summed over its launches by ncu "
-                             f"(profiles/step_traffic.json); peak = {peak_src}"}
+                             "time (graph replay); traffic = {traffic_src}; peak = {peak_src}"}
     roofline = step_roofline
     attention = None
     if gemm_trace is not None:
@@ -560,12 +723,25 @@ def main():
                     "share_of_step_kernel_time": ms_g / ms_all,
                     "what": f"dominant kernel: algorithmic FLOPs per launch (from each call's descriptor, 2 per MAC) / average launch "
                             f"duration over the {n_g} GEMM launches of one eager step of this run, CUDA events on the launching stream "
-                            f"({n_all} traced launches in the step); traffic = ncu DRAM bytes per GEMM launch "
-                            f"(profiles/step_traffic.json); peak = {peak_src}"}
+                            f"({n_all} traced launches in the step); traffic = {traffic_src}; peak = {peak_src}"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N = 1 only (torchrun pins OMP threads to 1)
         v, cores, sample, _ = cpu_reference_steps(steps=2, warmup=1, workload=args.workload)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+    eager_bar = decode = None
+    if not args.no_extras and world == 1 and not args.breakdown:
+        try:                                           # the extra measurements must never cost the bench line
+            decode = measure_decode(model, dev)
+        except Exception as e:
+            decode = {"error": repr(e)}
+        try:
+            del opt
+            model._captured, model._captures = None, []
+            torch.cuda.empty_cache()
+            eager_bar = torch_eager_gpu(B, dev)
+            eager_bar["speedup_of_value_over_bf16_autocast"] = sps / eager_bar["bf16_autocast"]["value"]
+        except Exception as e:
+            eager_bar = {"error": repr(e)}
     def batch_bytes(b):
         i, q, a, tg = b
         return i.numel() * 4 + q.numel() * 8 + a.numel() * 8 + sum(v.numel() * v.element_size() for t in tg for v in t.values() if torch.is_tensor(v))
@@ -580,7 +756,16 @@ def main():
                                    "on: p=0.1 at every nn.Dropout site (counter-based masks fused into the GEMM epilogues, LayerNorm "
                                    "and attention kernels, regenerated in backward)"), "loss": loss_val},
             "clocks": clocks,
-            "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "e2e": ({"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                     "what": "public API call on pinned fp32 NCHW host images, copied synchronously inside the call; loss read back"}
+                    if ms_e2e_u8_pf is None else
+                    {"value": world * B * args.steps / (ms_e2e_u8_pf / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d - h_images.numel() * 3,
+                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_u8_pf / args.steps,
+                     "what": "public API (GPV.forward + loss.backward + loss.item()) fed by data.DevicePrefetcher with the loader's raw format: every "
+                             "step copies one batch of pinned uint8 NHWC host pixels, token ids and targets to the device on the copy stream (under "
+                             "the previous step) and reads the loss back; ToTensor + Normalize are fused into the stem's read"}),
+            "e2e_fp32_sync": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                              "what": "the same call on pinned fp32 NCHW host images copied synchronously inside the call (the reference's loop, train_distr.py:401)"},
             "e2e_prefetch": None if ms_e2e_pf is None else {
                 "value": world * B * args.steps / (ms_e2e_pf / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e_pf / args.steps,
                 "h2d_bytes_per_step": h2d, "what": "e2e with the next batch's H2D copy double-buffered on a copy stream (data.DevicePrefetcher)"},
@@ -591,9 +776,10 @@ def main():
             "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
                           "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},
             "roofline": roofline, "roofline_step": step_roofline, "attention_kernel": attention,
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "multitask": multitask_line, "decode": decode, "torch_eager_gpu": eager_bar}
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_per_step
+        line["grads_equal_across_ranks"] = grads_equal
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -355,6 +355,34 @@ def attn_block_fwd(q, k, v, *, B, Sq, Sk, scale, key_mask=None, wo=None, bo=None
     return y, o, lse, pre, stats
 
 
+# ------------------------------------------------------------------------------------------------ decode bookkeeping
+def argmax(logits, V, *, vocab_mask=None, out=None):
+    """ids[row] = first arg-max of logits[row, :V] + vocab_mask; the masked logits are also written to out [rows, V] (any row stride)."""
+    rows = logits.shape[0]
+    ids = torch.empty((rows,), device=logits.device, dtype=torch.int64)
+    _C.check(_C.lib().gpvb200_argmax(_C.ptr(_req(logits, torch.float32)), ctypes.c_int64(logits.stride(0)), rows, V,
+                                     _C.ptr(_req(vocab_mask, torch.float32)), _C.ptr(_req(out, torch.float32)),
+                                     ctypes.c_int64(out.stride(0) if out is not None else 0), _C.ptr(ids), _C.stream_ptr()), "argmax")
+    return ids
+
+
+def beam_update(logits, V, t, score_in, ids_in, score_out, ids_out, parent, tok):
+    """One beam-search step (see gpvb200_beam_update): ids_* [B, K, L] int64, score_* [B, K] fp32, parent / tok [B*K] int64."""
+    B, K, L = ids_in.shape
+    _C.check(_C.lib().gpvb200_beam_update(_C.ptr(_req(logits, torch.float32)), ctypes.c_int64(logits.stride(0)), B, K, V, t, L,
+                                          _C.ptr(_req(score_in, torch.float32)), _C.ptr(_req(ids_in, torch.int64)),
+                                          _C.ptr(_req(score_out, torch.float32)), _C.ptr(_req(ids_out, torch.int64)),
+                                          _C.ptr(_req(parent, torch.int64)), _C.ptr(_req(tok, torch.int64)), _C.stream_ptr()), "beam_update")
+
+
+def reorder_rows(src, dst, parent, n_elems):
+    """dst[r, :n_elems] = src[parent[r], :n_elems] over the flattened rows of two [rows, ...] bf16 buffers."""
+    rows = src.shape[0]
+    row_elems = src.numel() // rows
+    _C.check(_C.lib().gpvb200_reorder_rows(_C.ptr(_req(src, BF16)), _C.ptr(_req(dst, BF16)), _C.ptr(_req(parent, torch.int64)), rows,
+                                           ctypes.c_int64(row_elems), ctypes.c_int64(n_elems), _C.stream_ptr()), "reorder_rows")
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def add_rowbcast(x, p, *, M=None, out=None):
     """out[m] = x[m] + p[m % P]; x may be None (pure broadcast of p over M rows)."""

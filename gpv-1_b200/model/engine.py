@@ -920,8 +920,14 @@ class Engine:
     @torch.no_grad()
     def decode_reorder(self, st, parent):
         """Beam search: hypothesis r continues hypothesis parent[r] (int64 [Bp]) -> permute the self-attention caches."""
-        st["kc"] = [c.index_select(0, parent) for c in st["kc"]]
-        st["vc"] = [c.index_select(0, parent) for c in st["vc"]]
+        n = st["t"] * self.D                                   # only the positions decoded so far move
+        if "kc_alt" not in st:
+            st["kc_alt"] = [torch.empty_like(c) for c in st["kc"]]
+            st["vc_alt"] = [torch.empty_like(c) for c in st["vc"]]
+        for a, b in (("kc", "kc_alt"), ("vc", "vc_alt")):
+            for src, dst in zip(st[a], st[b]):
+                k.reorder_rows(src, dst, parent, n)
+            st[a], st[b] = st[b], st[a]
 
     # ================================================================================================ training step
     @torch.no_grad()

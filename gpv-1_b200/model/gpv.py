@@ -473,15 +473,11 @@ class GPV(nn.Module):
         B, L = s["B"], self.cfg.max_text_len
         st = eng.decode_begin(s["memory"], B, s["Tm"], L)
         tok = torch.full((B,), self.word_to_idx["__cls__"], dtype=torch.int64, device=eng.dev)
-        vm = vocab_mask.to(eng.dev).float() if vocab_mask is not None else None
+        vm = vocab_mask.to(eng.dev).float().contiguous() if vocab_mask is not None else None
         out = torch.empty((B, L, eng.V), device=eng.dev, dtype=torch.float32)
         for t in range(L):
-            lg = eng.decode_step(st, tok)[:, :eng.V]
-            if vm is not None:
-                lg = lg + vm
-            out[:, t] = lg
-            if t < L - 1:
-                tok = lg.argmax(-1)
+            # masked logits of position t written in place and the first arg-max of them: one launch (gpvb200_argmax)
+            tok = k.argmax(eng.decode_step(st, tok), eng.V, vocab_mask=vm, out=out[:, t])
         return out.unsqueeze(0)
 
     def _graphed(self, kind, images, qids, vocab_mask, beam_size):
@@ -563,27 +559,18 @@ class GPV(nn.Module):
         eng = self.engine
         B, Tm, L = s["B"], s["Tm"], self.cfg.max_text_len
         st = eng.decode_begin(s["memory"], B, Tm, L, rep=K)
-        ids = torch.full((B, K, 1), self.word_to_idx["__cls__"], dtype=torch.int64, device=eng.dev)
-        score = torch.zeros((B, K), device=eng.dev)
-        base = torch.arange(B, device=eng.dev)[:, None] * K
-        tok = ids[:, :, 0].reshape(-1)
+        dev = eng.dev
+        ids = [torch.full((B, K, L), self.word_to_idx["__cls__"], dtype=torch.int64, device=dev) for _ in range(2)]
+        score = [torch.zeros((B, K), device=dev), torch.zeros((B, K), device=dev)]
+        parent = torch.empty((B * K,), dtype=torch.int64, device=dev)
+        tok = [ids[0][:, :, 0].reshape(-1).contiguous(), torch.empty((B * K,), dtype=torch.int64, device=dev)]
         for t in range(L - 1):
-            lg = eng.decode_step(st, tok)
-            last = lg.view(B, K, -1)[:, :, :eng.V]
-            top = torch.log_softmax(last, -1).topk(K, -1)
-            cand = score[:, :, None] + top.values
-            if t == 0:
-                cand[:, 1:] = -1e9
-            flat = cand.reshape(B, K * K)
-            order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, :K]
-            k1 = torch.div(order, K, rounding_mode="floor")
-            new_last = torch.gather(top.indices.reshape(B, K * K), 1, order)
-            ids = torch.cat((torch.gather(ids, 1, k1[:, :, None].expand(-1, -1, ids.shape[2])), new_last[:, :, None]), 2)
-            score = torch.gather(flat, 1, order)
+            lg = eng.decode_step(st, tok[t & 1])
+            # log-softmax, per-hypothesis top-K, candidate merge, sequence / score / parent update: one launch (gpvb200_beam_update)
+            k.beam_update(lg, eng.V, t, score[t & 1], ids[t & 1], score[(t + 1) & 1], ids[(t + 1) & 1], parent, tok[(t + 1) & 1])
             if t < L - 2:
-                eng.decode_reorder(st, (base + k1).reshape(-1))
-                tok = new_last.reshape(-1)
-        return ids[:, :, 1:], score
+                eng.decode_reorder(st, parent)
+        return ids[(L - 1) & 1][:, :, 1:], score[(L - 1) & 1]
 
     # ------------------------------------------------------------------------------------------------ answers (host)
     def encode_answers(self, targets):

@@ -279,6 +279,26 @@ int gpvb200_layernorm_bwd_drop(const void* dy, int64_t lddy, const void* x, int6
 int gpvb200_dropout_mask(uint8_t* out, int64_t rows, int32_t N, const void* drop_seed, uint32_t drop_site, float drop_p,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Decode-loop bookkeeping (exp/gpv/models/gpv.py:178-196 greedy, 256-362 beam search)
+ * ------------------------------------------------------------------------------------------------ */
+/* Greedy step, gpv.py:186-190: out[row, :V] = logits[row, :V] + vocab_mask (NULL: no mask; out NULL: not written) and
+ * ids[row] = arg-max of it, the FIRST maximal index on ties (torch.max semantics).  logits fp32 [rows, >= V]. */
+int gpvb200_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, const float* vocab_mask, float* out, int64_t ldo,
+                   int64_t* ids, void* stream);
+/* One beam-search step, gpv.py:280-328: logits fp32 [B*K, >= V] are the next-token logits of hypothesis (b, k1).  Per
+ * hypothesis log_softmax and its K best tokens, candidates score_in[b, k1] + logp in (k1 major, k2 minor) order, the K
+ * best candidates in stable descending order (first occurrence wins ties); at t = 0 only hypothesis 0 of each image is
+ * live.  Writes score_out [B, K], ids_out [B, K, L] (ids_out[b, k, :t+1] = ids_in[b, k1, :t+1], ids_out[b, k, t+1] =
+ * the new token), parent [B*K] = b K + k1 (the row whose KV cache hypothesis (b, k) continues) and tok [B*K] = the new
+ * token.  K <= 8; ids / scores are double-buffered by the caller (no in-place update). */
+int gpvb200_beam_update(const float* logits, int64_t ld, int32_t B, int32_t K, int32_t V, int32_t t, int32_t L, const float* score_in,
+                        const int64_t* ids_in, float* score_out, int64_t* ids_out, int64_t* parent, int64_t* tok, void* stream);
+/* KV-cache permutation after a beam step (gpv.py:318-326 re-decodes the re-ordered prefixes; the cached K/V follow the
+ * hypotheses instead): dst[r, :n_elems] = src[parent[r], :n_elems] for `rows` rows of row_elems bf16. */
+int gpvb200_reorder_rows(const void* src, void* dst, const int64_t* parent, int32_t rows, int64_t row_elems, int64_t n_elems,
+                         void* stream);
+
 /* ---- optimizer: clip_grad_norm_ + AdamW over the flat gradient arena (exp/gpv/train_distr.py:414-428, 228-253).
  * items: device array of {float* p; int64 goff; int32 n, group, clip, pad} (gpvb200_optim_item_size() bytes each);
  * blk_item / blk_chunk: one entry per CTA = (tensor index, chunk of gpvb200_optim_chunk() elements).

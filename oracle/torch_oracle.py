@@ -311,8 +311,8 @@ def hungarian(logits, boxes, tgt_boxes_list, w=(1.0, 5.0, 2.0)):
     import oracle
     sizes = [int(t.shape[0]) for t in tgt_boxes_list]
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
-    tb = torch.cat(list(tgt_boxes_list), 0).detach().cpu().numpy() if sum(sizes) else np.zeros((0, 4), np.float32)
-    cost = oracle.matcher_cost(logits.detach().cpu().numpy(), boxes.detach().cpu().numpy(), tb, np.zeros(int(off[-1]), np.int64), off,
+    tb = torch.cat(list(tgt_boxes_list), 0).detach().float().cpu().numpy() if sum(sizes) else np.zeros((0, 4), np.float32)
+    cost = oracle.matcher_cost(logits.detach().float().cpu().numpy(), boxes.detach().float().cpu().numpy(), tb, np.zeros(int(off[-1]), np.int64), off,
                                w[0], w[1], w[2])
     oq, ot = oracle.lsap_batched(cost, off)
     res = []

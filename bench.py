@@ -224,7 +224,7 @@ def gemm_algorithmic_flop(d):
 
 # position of (B, H, Sq, Sk, dh) in the argument list of each attention entry point (include/gpvb200.h, gpv1_b200/kernels.py)
 _ATTENTION_ARGS = {"gpvb200_attention_fwd": 10, "gpvb200_attention_fwd_drop": 10, "gpvb200_attention_fwd_bs": 14,
-                   "gpvb200_attention_bwd": 18, "gpvb200_attention_bwd_drop": 18}
+                   "gpvb200_attention_bwd": 18, "gpvb200_attention_bwd_drop": 18, "gpvb200_attn_block_fwd": 7}
 
 
 def attention_summary(rows, peak_tflops):
@@ -241,9 +241,14 @@ def attention_summary(rows, peak_tflops):
         if not (0 < dh <= 256 and 0 < H <= 64 and B > 0 and Sq > 0 and Sk > 0):
             raise ValueError(f"unexpected attention arguments at {name}: {(B, H, Sq, Sk, dh)}")
         kind = "bwd" if "_bwd" in name else "fwd"
-        c = agg.setdefault(f"{kind}_dh{dh}", [0, 0.0, 0.0])
+        key = f"{kind}_dh{dh}"
+        flop = (10.0 if kind == "bwd" else 4.0) * B * H * Sq * Sk * dh
+        if name == "gpvb200_attn_block_fwd":                  # tcgen05 attention core + out-proj + residual + LayerNorm in one launch
+            key = f"fwd_dh{dh}_attn_block_tcgen05_with_out_proj_ln"
+            flop += 2.0 * B * Sq * (H * dh) * (H * dh)
+        c = agg.setdefault(key, [0, 0.0, 0.0])
         c[0] += 1
-        c[1] += (10.0 if kind == "bwd" else 4.0) * B * H * Sq * Sk * dh
+        c[1] += flop
         c[2] += ms
     out = {}
     for key, (n, flop, ms) in sorted(agg.items()):
@@ -372,6 +377,61 @@ def measure_decode(model, dev, reps=5, K=5):
         model.inference_graphs = graphs
         model._inf_graphs.clear()
         model.train(was_training)
+    return out
+
+
+def measure_encoder_layer(model, B, dev, peak_tflops, reps=20):
+    """BASELINE's "fused encoder-decoder attention kernel" target, measured live: ONE DETR encoder layer (transformer.py:148-161:
+    QKV projections, 8-head attention over 300 tokens, out-proj + residual + LayerNorm, FFN 256-2048-256 + residual + LayerNorm) at
+    the bench batch through the engine's own layer functions -- forward (pos add, QK GEMM, V GEMM, attn_block_fwd, mlp_block_fwd: 5
+    launches) and backward -- CUDA events around `reps` back-to-back runs, train mode (dropout on).  Algorithmic FLOPs per sample and
+    layer: 4 projections 2 S d^2 each + attention 4 H S^2 d_h + FFN 4 S d d_ff; backward 2x."""
+    from gpv1_b200 import _C
+    eng = model.engine
+    S, d, dff, H = (H_IMG // 32) * (W_IMG // 32), 256, 2048, 8
+    p = "detr.transformer.encoder.layers.0"
+    x = torch.randn(B * S, d, device=dev).to(torch.bfloat16)
+    pos = torch.randn(S, d, device=dev).to(torch.bfloat16)
+    dy = (0.1 * torch.randn(B * S, d, device=dev)).to(torch.bfloat16)
+    flop_fwd = B * (4 * 2 * S * d * d + 4 * H * S * S * (d // H) + 2 * 2 * S * d * dff)
+    train = eng.train_mode
+    eng.train_mode = model.training
+    eng.refresh()
+    out = {}
+    try:
+        def fwd():
+            y1, sa = eng._self_attn_fwd(p, x, pos, S, B, S, H)
+            y2, sf = eng._ffn_fwd(p + ".linear1", p + ".linear2", p + ".norm2", y1, 1e-5)
+            return sa, sf
+
+        def fwd_bwd():
+            sa, sf = fwd()
+            d1 = eng._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm2", dy, sf)
+            eng._self_attn_bwd(p, d1, sa, None, B, S, H)
+            eng._join()
+
+        lib = _C.lib()
+        for name, fn, flop in (("fwd", fwd, flop_fwd), ("fwd_bwd", fwd_bwd, 3 * flop_fwd)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            n0 = lib.launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = 1e3 * e0.elapsed_time(e1) / reps
+            tf = flop / us * 1e-6
+            out[name] = {"us_per_layer": us, "launches": (lib.launches - n0) // reps, "flop": flop, "achieved": tf, "unit": "TFLOP/s",
+                         "frac": tf / peak_tflops}
+    finally:
+        eng.train_mode = train
+        eng.grad_arena.zero_()
+    out["what"] = (f"one DETR encoder layer, B={B} x S={S} tokens, d=256, 8 heads, d_ff=2048, dropout {'on' if model.training else 'off'}: "
+                   "eager launches of the engine's layer functions (tcgen05 attn_block_fwd + mlp_block_fwd forward; GEMM / mma.sync "
+                   "attention / LayerNorm kernels backward), frac of the measured bf16 tensor peak")
     return out
 
 
@@ -708,7 +768,7 @@ def main():
     if gemm_trace is not None:
         try:                                     # "attn kernel %peak" of BASELINE.json's metric: attn_fwd / attn_bwd kernels by head width
             attention = attention_summary(gemm_trace[5], peak)
-            attention["what"] = ("gpv::attn_fwd_kernel / attn_bwd_kernel (mma.sync, scores on chip): algorithmic FLOPs per launch / "
+            attention["what"] = ("gpv::attn_fwd_kernel / attn_bwd_kernel (mma.sync, scores on chip) and gpv::attn_block_fwd_kernel (tcgen05, DETR encoder): algorithmic FLOPs per launch / "
                                  "average launch duration in the same traced eager step as `roofline`; frac of the measured bf16 "
                                  "tensor peak; dh32 = DETR encoder / decoder, dh48 = co-attention, dh64 = BERT, dh96 = text decoder")
         except Exception as e:                   # never lose the bench line over the breakdown
@@ -728,8 +788,12 @@ def main():
     if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N = 1 only (torchrun pins OMP threads to 1)
         v, cores, sample, _ = cpu_reference_steps(steps=2, warmup=1, workload=args.workload)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
-    eager_bar = decode = None
+    eager_bar = decode = encdec = None
     if not args.no_extras and world == 1 and not args.breakdown:
+        try:
+            encdec = measure_encoder_layer(model, B, dev, peak)
+        except Exception as e:
+            encdec = {"error": repr(e)}
         try:                                           # the extra measurements must never cost the bench line
             decode = measure_decode(model, dev)
         except Exception as e:
@@ -776,7 +840,8 @@ def main():
             "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
                           "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},
             "roofline": roofline, "roofline_step": step_roofline, "attention_kernel": attention,
-            "cpu_baseline": cpu, "multitask": multitask_line, "decode": decode, "torch_eager_gpu": eager_bar}
+            "cpu_baseline": cpu, "encdec_block": encdec, "multitask": multitask_line, "decode": decode,
+            "torch_eager_gpu": eager_bar}
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_per_step
         line["grads_equal_across_ranks"] = grads_equal

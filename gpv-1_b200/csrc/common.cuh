@@ -262,6 +262,47 @@ GPV_DEVINL void drop_pair(float& a, float& b, uint32_t key, uint32_t pair, uint3
 }
 
 // ---------------------------------------------------------------- misc math
+GPV_DEVINL float ex2_approx(float x) {      // one MUFU.EX2 (exp2f() without fast-math adds a denormal-range rescale around it)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100: one issue slot for two lanes of work)
+GPV_DEVINL uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+GPV_DEVINL void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+GPV_DEVINL uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+GPV_DEVINL uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^t for two values t <= 0 on the FMA pipe instead of the SFU (which retires only 4 lanes per clock per scheduler and bounds a
+// softmax over short head dimensions): j = round(t) by the 1.5 * 2^23 trick, f = t - j in [-0.5, 0.5], a cubic minimax fit of 2^f
+// (relative error 7.5e-5, far below the bf16 rounding of the probabilities), and j added into the exponent field.
+GPV_DEVINL void exp2_poly2(float t0, float t1, float& p0, float& p1) {
+  t0 = fmaxf(t0, -125.0f);
+  t1 = fmaxf(t1, -125.0f);
+  const uint64_t T = pk2(t0, t1);
+  const uint64_t R = fadd2(T, pk2(12582912.0f, 12582912.0f));
+  const uint64_t J = fadd2(R, pk2(-12582912.0f, -12582912.0f));
+  const uint64_t F = ffma2(J, pk2(-1.0f, -1.0f), T);
+  uint64_t P = ffma2(F, pk2(0.055171459913253784f, 0.055171459913253784f), pk2(0.2426108568906784f, 0.2426108568906784f));
+  P = ffma2(P, F, pk2(0.6932609677314758f, 0.6932609677314758f));
+  P = ffma2(P, F, pk2(0.9999281167984009f, 0.9999281167984009f));
+  float r0, r1, q0, q1;
+  upk2(R, r0, r1);
+  upk2(P, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
 GPV_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

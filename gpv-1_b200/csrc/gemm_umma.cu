@@ -833,7 +833,17 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
     configured = true;
   }
   // one persistent CTA per SM; the pair variant launches clusters of two CTAs (the two SMs of a TPC), one pair per work item
-  const int slots = PAIR ? num_sms() / 2 : num_sms();
+  int slots = PAIR ? num_sms() / 2 : num_sms();
+  {
+    // GPVB200_WGRAD_CTAS=<n>: persistent grid of the atomically accumulating launches (weight gradients, which run on a lane beside
+    // the data-gradient chain) capped at n CTAs, so that the chain's own kernels find free SMs (scheduling experiment; default: all)
+    static int wg_cap = -1;
+    if (wg_cap < 0) {
+      const char* e = getenv("GPVB200_WGRAD_CTAS");
+      wg_cap = e ? atoi(e) : 0;
+    }
+    if (wg_cap > 0 && kp.d_atomic && !PAIR && slots > wg_cap) slots = wg_cap;
+  }
   const int grid = (kp.total_work < slots ? kp.total_work : slots) * (PAIR ? 2 : 1);
   static int pdl = -1;   // GPVB200_PDL=0 disables programmatic dependent launch
   if (pdl < 0) {
@@ -1013,6 +1023,12 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   const int bn_cap = d->mode == 2 ? 128 : 256;
   const int k_iters_pre = d->mode == 0 ? (d->K + 63) / 64 : (d->mode == 1 ? d->ntaps * ((d->K + 63) / 64) : 0);
   int BN = 64, splits = splits_in > 0 ? splits_in : 1;
+  static int min_kper = -1;   // GPVB200_MIN_KPER=<n>: automatic split-K keeps at least n 64-deep k-iterations per split (default 8: measured 17.44 -> 17.25 ms per step against 1, profiles/r2p)
+  if (min_kper < 0) {
+    const char* e = getenv("GPVB200_MIN_KPER");
+    min_kper = e ? atoi(e) : 8;
+    if (min_kper < 1) min_kper = 1;
+  }
   static int force_bn = -1;   // developer override (tools/sweep_bn.py): GPVB200_FORCE_BN=64|128|256
   if (force_bn < 0) {
     const char* e = getenv("GPVB200_FORCE_BN");
@@ -1027,7 +1043,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
       int sp = splits_in > 0 ? splits_in : 1;
       if (auto_split && k_iters_pre > 0) {
         sp = (int)((num_sms() + tiles - 1) / tiles);
-        if (sp > k_iters_pre) sp = k_iters_pre;
+        if (sp > k_iters_pre / min_kper) sp = k_iters_pre / min_kper;   // every split keeps at least min_kper k-iterations
         if (sp < 1) sp = 1;
       }
       const double t_iter = 0.24 + 0.0018 * bn;          // 0.35 / 0.47 / 0.70 us

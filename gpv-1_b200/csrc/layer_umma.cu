@@ -455,6 +455,7 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // backward kernel regenerates it.
 // =====================================================================================================================
 constexpr uint32_t kKvTileBytes = 38912u;     // [304 keys x 64] bf16
+constexpr int kPolyNum = 2, kPolyDen = 5;      // of every kPolyDen pairs of probabilities, kPolyNum take exp2 on the FMA pipe (exp2_poly2)
 constexpr uint32_t kKvSlotBytes = 2 * kKvTileBytes;
 
 struct AttnBlkParams {
@@ -501,6 +502,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* acc_full = bars + 13;
   uint64_t* kv_done = bars + 14;     // every MMA that reads the K / V ring has completed (Wo may land there)
   uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+  uint64_t* s_empty = bars + 16;     // the softmax warps hold S_h in registers: S_{h+1} may overwrite it
   float* sVec = reinterpret_cast<float*>(bars + 32);   // bo | gamma | beta
   float* sBo = sVec;
   float* sGamma = sVec + 256;
@@ -537,6 +539,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(wo_full, 4);
     mbar_init(acc_full, 1);
     mbar_init(kv_done, 1);
+    mbar_init(s_empty, 8);
     fence_barrier_init();
   }
   if (warp == kLtMmaWarp) {
@@ -548,9 +551,13 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t t_s = tmem_base, t_p = tmem_base + 320u, t_o = tmem_base + 480u;
+  // warp group 0 (three producers + the MMA issuer) needs few registers; the two softmax warp groups keep a whole half row of
+  // scores (160 fp32) in registers: 128 x 64 + 256 x 208 = 61440 <= 65536
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
   if (warp < kLtProducers) {
     // ================================================================== TMA producers: operations dealt round-robin to the warps
     if (elect_one()) {
@@ -608,18 +615,25 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int h = 0; h < 8; ++h) {
       const int slot = (h >> 1) & 1;
       if (lane == 0) LT_STAMP(1, h, 0);
-      mbar_wait(p_full, (uint32_t)h & 1u);                       // P_h is in tensor memory; S is free again
+      if (h < 7) {                                               // S_{h+1}: K of its pair has landed, the softmax warps hold S_h in registers
+        if (((h + 1) & 1) == 0) mbar_wait(&k_full[((h + 1) >> 1) & 1], ((uint32_t)(h + 1) >> 2) & 1u);
+        mbar_wait(s_empty, (uint32_t)h & 1u);
+        tc_fence_after();
+        if (elect_one()) issue_s(h + 1);
+        __syncwarp();
+      }
+      mbar_wait(p_full, (uint32_t)h & 1u);                       // P_h is in tensor memory
       if (lane == 0) LT_STAMP(1, h, 1);
-      if (h < 7 && ((h + 1) & 1) == 0) mbar_wait(&k_full[((h + 1) >> 1) & 1], ((uint32_t)(h + 1) >> 2) & 1u);
       if ((h & 1) == 0) mbar_wait(&v_full[slot], ((uint32_t)h >> 2) & 1u);
       mbar_wait(o_empty, ((uint32_t)h & 1u) ^ 1u);               // O_{h-1} has been read out
       if (lane == 0) LT_STAMP(1, h, 2);
       tc_fence_after();
       if (elect_one()) {
-        if (h < 7) issue_s(h + 1);
         const uint32_t vb = smem_u32(sKV + (size_t)slot * kKvSlotBytes + kKvTileBytes) + (uint32_t)(h & 1) * 64u;
-        for (int ks = 0; ks < nks; ++ks)
-          umma_f16_ts(t_o, t_p + (uint32_t)(ks * 8), make_sdesc_sw128(vb + (uint32_t)ks * 2048u, 1024u, 1024u), idesc_pv, ks > 0 ? 1u : 0u);
+        const uint64_t vd = make_sdesc_sw128(vb, 1024u, 1024u);
+#pragma unroll
+        for (int ks = 0; ks < 19; ++ks)                          // Skp <= 304: at most 19 sixteen-key steps
+          if (ks < nks) umma_f16_ts(t_o, t_p + (uint32_t)(ks * 8), vd + (uint64_t)(ks * 128), idesc_pv, ks > 0 ? 1u : 0u);
         umma_commit(o_full);
         LT_STAMP(1, h, 3);
         if (h & 1) umma_commit(&kv_empty[slot]);
@@ -642,8 +656,10 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       __syncwarp();
     }
+  }
   } else {
     // ================================================================== softmax / epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
     const int e = warp - kLtEpiWarp0;
     const int q = warp & 3, half = e >> 2;
     const int r = q * 32 + lane;
@@ -694,77 +710,123 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       const float l = sSum[((hh & 1) * 2 + 0) * 128 + r] + sSum[((hh & 1) * 2 + 1) * 128 + r];
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) * inv;
+      const float inv = l > 0.f ? (DROP && p.drop_p.seed ? p.drop_p.scale : 1.0f) / l : 0.f;
+      uint4 w0, w1;
+      w0.x = pack_bf16x2(__uint_as_float(acc[0]) * inv, __uint_as_float(acc[1]) * inv);
+      w0.y = pack_bf16x2(__uint_as_float(acc[2]) * inv, __uint_as_float(acc[3]) * inv);
+      w0.z = pack_bf16x2(__uint_as_float(acc[4]) * inv, __uint_as_float(acc[5]) * inv);
+      w0.w = pack_bf16x2(__uint_as_float(acc[6]) * inv, __uint_as_float(acc[7]) * inv);
+      w1.x = pack_bf16x2(__uint_as_float(acc[8]) * inv, __uint_as_float(acc[9]) * inv);
+      w1.y = pack_bf16x2(__uint_as_float(acc[10]) * inv, __uint_as_float(acc[11]) * inv);
+      w1.z = pack_bf16x2(__uint_as_float(acc[12]) * inv, __uint_as_float(acc[13]) * inv);
+      w1.w = pack_bf16x2(__uint_as_float(acc[14]) * inv, __uint_as_float(acc[15]) * inv);
       const uint32_t ob = smem_u32(sQ) + (uint32_t)(hh >> 1) * kKblkBytes;
-      sts128(ob + sw128_off(r, (hh & 1) * 4 + half * 2), pack8(v));
-      sts128(ob + sw128_off(r, (hh & 1) * 4 + half * 2 + 1), pack8(v + 8));
+      sts128(ob + sw128_off(r, (hh & 1) * 4 + half * 2), w0);
+      sts128(ob + sw128_off(r, (hh & 1) * 4 + half * 2 + 1), w1);
       if (half == 0 && r < rows_valid && p.lse != nullptr)
         p.lse[((long long)img * p.H + hh) * p.Sq + tt * 128 + r] = m_h * p.sl2 + log2f(l);
     };
 
+    bool full_chunk[5];                                  // every key of the chunk is live: no select in the inner loops (warp-uniform)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) full_chunk[c] = vmask[c] == 0xffffffffu;
     for (int h = 0; h < 8; ++h) {
       const bool tr = e == 0 && lane == 0;
       if (tr) LT_STAMP(2, h, 0);
       mbar_wait(s_full, (uint32_t)h & 1u);
       if (tr) LT_STAMP(2, h, 1);
       tc_fence_after();
+      // ---- this warp's half row of S_h into registers (one round trip), then S may be overwritten by head h + 1
+      uint32_t sc[5][32];
+#pragma unroll
+      for (int c = 0; c < 5; ++c)
+        if (c < nch) tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(base_key + c * 32), sc[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      // ---- dead keys (past Sk, or masked) become -inf here, so that both passes below are single straight-line paths: the whole
+      //      per-head body must stay small enough for the instruction cache (the first version, with a masked and an unmasked
+      //      copy of each pass, was 120 KB of code and spent 30 % of its issue slots waiting for instruction fetch)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (c < nch && !full_chunk[c]) {
+          const uint32_t vm = vmask[c];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sc[c][i] = ((vm >> i) & 1u) ? sc[c][i] : 0xff800000u;
+        }
+      }
       // ---- pass 1: row maximum over this warp's keys
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
         if (c < nch) {
-          uint32_t sc[32];
-          tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(base_key + c * 32), sc);
-          tmem_ld_wait();
-          const uint32_t vm = vmask[c];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if ((vm >> i) & 1u) mx = fmaxf(mx, __uint_as_float(sc[i]));
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sc[c][i]));
         }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       if (tr) LT_STAMP(2, h, 2);
       sMax[((h & 1) * 2 + half) * 128 + r] = mx;
       named_bar_sync(1, kLtEpiThreads);
       if (tr) LT_STAMP(2, h, 3);
       const float m = fmaxf(mx, sMax[((h & 1) * 2 + (half ^ 1)) * 128 + r]);
       const float ms = (m == -INFINITY) ? 0.f : m;
-      if (h > 0) o_epilogue(h - 1, m_prev);          // also: P V of head h-1 is complete, so P may be overwritten
-      m_prev = ms;
       if (tr) LT_STAMP(2, h, 4);
       // ---- pass 2: p = exp2((s - m) * scale * log2 e), row sum over every key, dropout on what goes into P V
-      float sum = 0.f;
+      uint64_t sum2[2] = {0ull, 0ull};
       const uint32_t prow = ((uint32_t)(img * p.H + h) * (uint32_t)p.Sq + (uint32_t)(tt * 128 + r)) * hs;
       const float nms = -ms * p.sl2;
+      const uint64_t sl2x2 = pk2(p.sl2, p.sl2), nmsx2 = pk2(nms, nms);
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
         if (c < nch) {
-          uint32_t sc[32];
-          tmem_ld_32x32b_x32(t_s + t_lane + (uint32_t)(base_key + c * 32), sc);
-          tmem_ld_wait();
-          const uint32_t vm = vmask[c];
-          float pv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float pe = exp2f(fmaf(__uint_as_float(sc[i]), p.sl2, nms));
-            pv[i] = ((vm >> i) & 1u) ? pe : 0.f;
-            sum += pv[i];
+          for (int j = 0; j < 16; ++j) {
+            float t0, t1, p0, p1;
+            upk2(ffma2(pk2(__uint_as_float(sc[c][2 * j]), __uint_as_float(sc[c][2 * j + 1])), sl2x2, nmsx2), t0, t1);
+            if ((j % kPolyDen) < kPolyNum) {
+              exp2_poly2(t0, t1, p0, p1);               // a dead key gives 2^-125 here instead of 0: below fp32 resolution of the row sum
+            } else {
+              p0 = ex2_approx(t0);
+              p1 = ex2_approx(t1);
+            }
+            sc[c][2 * j] = __float_as_uint(p0);
+            sc[c][2 * j + 1] = __float_as_uint(p1);
+            sum2[j & 1] = fadd2(sum2[j & 1], pk2(p0, p1));
           }
+        }
+      }
+      // P V of head h-1 has had passes 1 and 2 of this head to finish: O_{h-1} out, after which P may be overwritten
+      if (h > 0) o_epilogue(h - 1, m_prev);
+      m_prev = ms;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (c < nch) {
           if (DROP && p.drop_p.seed) {
             const uint32_t cb = prow + (uint32_t)((base_key + c * 32) >> 1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) drop_pair(pv[2 * i], pv[2 * i + 1], dkey_p, cb + i, p.drop_p.thresh16, p.drop_p.scale);
+            for (int i = 0; i < 16; ++i) {
+              float a = __uint_as_float(sc[c][2 * i]), b = __uint_as_float(sc[c][2 * i + 1]);
+              drop_pair(a, b, dkey_p, cb + i, p.drop_p.thresh16, 1.0f);       // 1 / (1 - p) rides on the normalisation of O
+              sc[c][2 * i] = __float_as_uint(a);
+              sc[c][2 * i + 1] = __float_as_uint(b);
+            }
           }
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(sc[c][2 * i]), __uint_as_float(sc[c][2 * i + 1]));
           tmem_st_32x32b_x16(t_p + t_lane + (uint32_t)((base_key + c * 32) >> 1), pk);
         }
       }
       if (tr) LT_STAMP(2, h, 5);
-      sSum[((h & 1) * 2 + half) * 128 + r] = sum;
+      {
+        float a0, a1, b0, b1;
+        upk2(sum2[0], a0, a1);
+        upk2(sum2[1], b0, b1);
+        // a row without any live key (m = -inf) sums to exactly 0, as in the mma.sync kernel: its output row is 0
+        sSum[((h & 1) * 2 + half) * 128 + r] = (m == -INFINITY) ? 0.f : (a0 + a1) + (b0 + b1);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -24,7 +24,8 @@ struct OptItem {
   int n;            // elements
   int group;        // learning-rate group 0..3
   int clip;         // 1: member of the clipped subset
-  int pad;
+  int step0;        // optimizer step at which this tensor's state started: its Adam step is (global step - step0), as torch keeps
+                    // state['step'] per parameter (parameters unfrozen for the second training phase start their bias correction at 1)
 };
 constexpr int kOptChunk = 4096;
 
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const OptItem* __restr
 
 struct AdamArgs {
   float lr[4];
-  float beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm;
+  float beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm;   // bc1 / bc2_sqrt: for tensors with step0 = 0 (the common case)
+  long long step;
 };
 
 GPV_DEVINL void adam_one(float& p, float& m, float& v, float g, float lr, const AdamArgs& a) {
@@ -82,6 +84,12 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(const OptItem* __restri
   float coef = 1.0f;
   if (it.clip && a.max_norm > 0.f) coef = fminf(1.0f, a.max_norm / (sqrtf(*total_sq) + 1e-6f));
   const float lr = a.lr[it.group];
+  AdamArgs al = a;
+  if (it.step0 != 0) {                                    // this tensor joined later: its own bias correction
+    const double st = (double)(a.step - it.step0);
+    al.bc1 = (float)(1.0 - pow((double)a.beta1, st));
+    al.bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, st));
+  }
   float* g = grads + it.goff;
   float* m = ms + it.goff;
   float* v = vs + it.goff;
@@ -100,10 +108,10 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(const OptItem* __restri
         gg.x *= coef; gg.y *= coef; gg.z *= coef; gg.w *= coef;
         g4[i] = gg;
       }
-      adam_one(pp.x, mm.x, vv.x, gg.x, lr, a);
-      adam_one(pp.y, mm.y, vv.y, gg.y, lr, a);
-      adam_one(pp.z, mm.z, vv.z, gg.z, lr, a);
-      adam_one(pp.w, mm.w, vv.w, gg.w, lr, a);
+      adam_one(pp.x, mm.x, vv.x, gg.x, lr, al);
+      adam_one(pp.y, mm.y, vv.y, gg.y, lr, al);
+      adam_one(pp.z, mm.z, vv.z, gg.z, lr, al);
+      adam_one(pp.w, mm.w, vv.w, gg.w, lr, al);
       m4[i] = mm;
       v4[i] = vv;
       p4[i] = pp;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(const OptItem* __restri
     float gg = g[i] * coef;
     if (coef != 1.0f) g[i] = gg;
     float pp = p[i], mm = m[i], vv = v[i];
-    adam_one(pp, mm, vv, gg, lr, a);
+    adam_one(pp, mm, vv, gg, lr, al);
     p[i] = pp;
     m[i] = mm;
     v[i] = vv;
@@ -157,6 +165,7 @@ extern "C" int gpvb200_clip_adamw(const void* items, const int32_t* blk_item, co
   a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.max_norm = max_norm;
   a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  a.step = step;
   clip_adamw_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>((const OptItem*)items, blk_item, blk_chunk, grads, m, v, total_sq, a);
   return check_launch("clip_adamw_kernel");
 }

@@ -107,11 +107,16 @@ class Engine:
         self.p_drop = {"detr": float(cfg.detr.dropout), "txt": float(cfg.text_decoder.dropout), "bert": 0.1,
                        "co_att_l": float(co.v_attention_probs_dropout_prob), "co_att_v": float(co.attention_probs_dropout_prob),
                        "co_hid_l": float(co.v_hidden_dropout_prob), "co_hid_v": float(co.hidden_dropout_prob)}
-        self.drop_seed = torch.zeros(1, dtype=torch.int64, device=device)     # training-step counter read by the kernels
+        # training-step counter read by the dropout kernels; the rank sits in the high bits so that data-parallel replicas draw
+        # different masks (torch's per-process Philox streams differ too); train.save_checkpoint / load_checkpoint carry it
+        import torch.distributed as _dist
+        rank = _dist.get_rank() if _dist.is_available() and _dist.is_initialized() else 0
+        self.drop_seed = torch.full((1,), rank << 40, dtype=torch.int64, device=device)
         self.frozen = set()                                   # names with requires_grad = False: no weight / bias gradient kernels
         self.last_stage = N_STAGES - 1                        # last gradient stage backward() reaches (lower when the tail is frozen)
         self.concurrent = True                                # run independent branches on side streams (lanes)
         self.fused_layers = os.environ.get("GPVB200_FUSED", "1") != "0"   # row-tile-resident sub-layer kernels (layer_umma.cu)
+        self.use_attn_block = self.fused_layers and os.environ.get("GPVB200_ATTN_BLOCK", "1") != "0"   # tcgen05 attention + out-proj + LN
         self._lanes, self._dirty, self._keep = {}, set(), []
 
     # ================================================================================================ weights
@@ -515,6 +520,15 @@ class Engine:
             qk_in = x
             k.linear(x, wi, bi_, out=qkv)
         dh = D // H
+        if self.use_attn_block and D == 256 and H == 8 and not causal and S <= 304 and B * ((S + 127) // 128) >= 64:
+            # DETR encoder self-attention: tcgen05 attention core + out-proj + dropout + residual + LayerNorm in ONE launch
+            # (gpvb200_attn_block_fwd); with fewer than ~64 row tiles (the decoder's 100 queries per image) its 8-heads-per-CTA
+            # walk leaves most SMs idle and the (batch, head)-parallel mma.sync kernel below is faster
+            y, o, lse, pre, st = k.attn_block_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, Sq=S, Sk=S, scale=dh ** -0.5,
+                                                  key_mask=kmask, wo=W[f"{p}.{attn}.out_proj.weight"], bo=Pm[f"{p}.{attn}.out_proj.bias"],
+                                                  x=x, gamma=Pm[f"{p}.{norm}.weight"], beta=Pm[f"{p}.{norm}.bias"], eps=eps,
+                                                  drop_p=self._drop(f"{p}.{attn}.probs"), drop_o=self._drop(f"{p}.{norm}.in"))
+            return y, (x, qk_in, qkv, o, lse, pre, st)
         o, lse = k.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=H, Sq=S, Sk=S, dh=dh, scale=dh ** -0.5,
                                  causal=causal, key_mask=kmask, drop=self._drop(f"{p}.{attn}.probs"))
         pre = k.linear(o, W[f"{p}.{attn}.out_proj.weight"], Pm[f"{p}.{attn}.out_proj.bias"], residual=x,

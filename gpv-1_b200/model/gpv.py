@@ -266,6 +266,14 @@ class GPV(nn.Module):
         V = len(self.vocab)
         if cfg.roi_head is not True or cfg.answer_head == "linear" or cfg.detr.aux_loss or cfg.detr.pre_norm:
             raise NotImplementedError("only the default GPV-1 variant (roi_head, generated answer head, post-norm, no aux loss) is built")
+        if getattr(cfg.text_decoder, "pos_enc", False):
+            raise NotImplementedError("text_decoder.pos_enc=True (gpv.py:452 adds pos_enc to the answer embeddings) is not built: the "
+                                      "shipped configuration keeps it False")
+        for name in ("CocoVqa", "CocoClassification", "CocoCaptioning"):
+            lc = getattr(cfg.losses, name, None)
+            if lc is not None and getattr(lc, "pad_idx", None) is not None:
+                raise NotImplementedError(f"losses.{name}.pad_idx (the cross-entropy ignore_index of losses.py:12-18) is not built: the "
+                                          "shipped configuration keeps it null, every answer position carries weight")
         self.specs = gpv_specs(cfg, V)
         g = torch.Generator().manual_seed(0 if seed is None else seed)
         for s in self.specs:

@@ -41,7 +41,14 @@ class CapturedStep:
         n0 = _C.lib().launches
         self.pool = torch.cuda.graph_pool_handle()
         self.g_fwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fwd, pool=self.pool):
+        # GPVB200_MAIN_PRIO=1: the issuing (critical-path) stream of the captured step gets a higher priority than the lanes, so
+        # that its CTAs are placed first whenever both have CTAs waiting for an SM (scheduling experiment; kernel nodes keep the
+        # priority of the stream they were captured on)
+        import os
+        prio = -1 if os.environ.get("GPVB200_MAIN_PRIO", "0") == "1" else 0
+        fwd_stream = torch.cuda.Stream(device=dev, priority=prio)
+        fwd_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(self.g_fwd, pool=self.pool, stream=fwd_stream):
             self.loss, _ = eng.forward_train(self.images, self.qids, self.ans, tgt)
         self._saved = eng.saved
         # Backward: one graph per gradient stage when a data-parallel GradSync is attached, so that each bucket's NCCL
@@ -49,7 +56,7 @@ class CapturedStep:
         self.sync = model.grad_sync if (model.grad_sync is not None and model.grad_sync.world > 1) else None
         hooks = (eng.on_stage_done, eng.on_backward_end)
         self.g_bwd = []
-        cap_stream = torch.cuda.Stream(device=dev)
+        cap_stream = torch.cuda.Stream(device=dev, priority=prio)
         cap_stream.wait_stream(torch.cuda.current_stream())
         torch.cuda.synchronize()
         try:

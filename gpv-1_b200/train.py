@@ -11,8 +11,10 @@ freeze_detr_params for `frozen_epochs`, 136-140, 160-161, 322-323), checkpoints 
 optimizer / epoch / step (382-394) and resume from `training.ckpt` (262-285).
 
 What is replaced: DistributedDataParallel(find_unused_parameters=True) by parallel.GradSync (stage-bucketed NCCL
-all-reduce of the gradient arena, overlapped with backward), clip + AdamW by optim.ClipAdamW (two launches), and the
-step by CUDA-graph replay once the batch shape repeats.  Data sets, evaluation and visualisation are out of scope
+all-reduce of the gradient arena, overlapped with backward) and clip + AdamW by optim.ClipAdamW (two launches).  This loop issues
+the step's kernels eagerly (the multitask stream changes shape from batch to batch); `GPV.capture_step` replays a fixed-shape
+step as CUDA graphs (bench.py does, one capture per answer length).  A checkpoint is written at the end of every epoch when
+`ckpt_dir` or `exp_dir` is set.  Data sets, evaluation and visualisation are out of scope
 (SURVEY 8): `data` is any iterable of `(images, queries, targets)` batches as utils/detr_misc.py:collate_fn yields them;
 without one, a synthetic loader of the reference's batch shape is used so that the entry point runs stand-alone.
 """
@@ -52,11 +54,18 @@ def freeze_detr_params(model, requires_grad=False):
             p.requires_grad = requires_grad
 
 
-def save_checkpoint(path, model, optimizer, epoch, step, metric=0.0):
+def save_checkpoint(path, model, optimizer, epoch, step, metric=0.0, lr_scale=1.0):
     """train_distr.py:382-394 layout: 'model' keys carry DDP's `module.` prefix so that the reference's inference.py:57-62
-    and its own resume code read the file unchanged."""
+    and its own resume code read the file unchanged: `optimizer` is torch.optim.AdamW's state_dict layout (optim.ClipAdamW.state_dict),
+    `lr` and `warmup_scheduler` are the entries train_distr.py:309-311 looks up."""
     sd = {f"module.{k}": v.detach().cpu() for k, v in model.state_dict().items()}
-    torch.save({"model": sd, "optimizer": optimizer.state_dict(), "epoch": epoch, "step": step, "model_selection_metric": metric}, path)
+    osd = optimizer.state_dict()
+    eng = getattr(model, "_engine", None)
+    torch.save({"model": sd, "optimizer": osd, "epoch": epoch, "step": step, "model_selection_metric": metric,
+                "drop_seed": int(eng.drop_seed.item()) & ((1 << 40) - 1) if eng is not None else 0,   # dropout step counter (rank bits stripped)
+                "lr": [g["lr"] * lr_scale for g in osd.get("param_groups", [])],
+                # WarmupLinearSchedule.state_dict() of the reference (LambdaLR): what its resume path reads back (train_distr.py:309-311)
+                "warmup_scheduler": {"last_epoch": step, "_step_count": step + 1, "base_lrs": list(getattr(optimizer, "lrs", []))}}, path)
 
 
 def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
@@ -68,8 +77,11 @@ def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
         if k in cur and cur[k].size() == v.size():
             cur[k] = v
     model.load_state_dict(cur)
-    if optimizer is not None and "optimizer" in ckpt and "state" in ckpt["optimizer"] and "t" in ckpt["optimizer"]:
-        optimizer.load_state_dict(ckpt["optimizer"])
+    if "drop_seed" in ckpt and getattr(model, "_engine", None) is not None:        # resumed runs continue the mask sequence
+        eng = model._engine
+        eng.drop_seed.copy_((eng.drop_seed >> 40 << 40) + int(ckpt["drop_seed"]))
+    if optimizer is not None and "optimizer" in ckpt:
+        optimizer.load_state_dict(ckpt["optimizer"])          # torch.optim layout (either implementation) or the earlier name-keyed form; raises on a mismatch
     return int(ckpt.get("epoch", -1)), int(ckpt.get("step", 0))
 
 
@@ -146,7 +158,7 @@ def train(cfg, data=None, vocab=None, vocab_embed=None, log=print):
                 optimizer.zero_grad()
                 total_loss.backward()
                 if tr.lr_linear_decay and tr.lr_warmup:
-                    mult = lr_multiplier(step, total_steps, float(tr.lr_warmup_fraction))
+                    mult = lr_multiplier(step + 1, total_steps, float(tr.lr_warmup_fraction))   # LambdaLR(last_epoch=step) has already stepped once
                 else:
                     mult = multistep_multiplier(epoch, list(tr.lr_milestones), float(tr.lr_drop))
                 optimizer.step(lr_scale=mult)
@@ -154,9 +166,10 @@ def train(cfg, data=None, vocab=None, vocab_embed=None, log=print):
                     loss_val = total_loss.item()
                     log(f"Epoch: {epoch} | Iter: {it} | Step: {step} |  LR: {optimizer.lrs[1] * mult:.3e} | total_loss: {round(loss_val, 4)}")
             step += 1
-        if rank == 0 and getattr(cfg, "ckpt_dir", None):
-            os.makedirs(cfg.ckpt_dir, exist_ok=True)
-            save_checkpoint(os.path.join(cfg.ckpt_dir, "model.pth"), model, optimizer, epoch, step)
+        ckpt_dir = getattr(cfg, "ckpt_dir", None) or (os.path.join(str(cfg.exp_dir), "ckpts") if getattr(cfg, "exp_dir", None) else None)
+        if rank == 0 and ckpt_dir:
+            os.makedirs(ckpt_dir, exist_ok=True)
+            save_checkpoint(os.path.join(ckpt_dir, "model.pth"), model, optimizer, epoch, step, lr_scale=mult if total_loss is not None else 1.0)
     if world > 1:
         dist.barrier()
     return loss_val

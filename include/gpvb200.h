@@ -300,11 +300,12 @@ int gpvb200_reorder_rows(const void* src, void* dst, const int64_t* parent, int3
                          void* stream);
 
 /* ---- optimizer: clip_grad_norm_ + AdamW over the flat gradient arena (exp/gpv/train_distr.py:414-428, 228-253).
- * items: device array of {float* p; int64 goff; int32 n, group, clip, pad} (gpvb200_optim_item_size() bytes each);
+ * items: device array of {float* p; int64 goff; int32 n, group, clip, step0} (gpvb200_optim_item_size() bytes each);
  * blk_item / blk_chunk: one entry per CTA = (tensor index, chunk of gpvb200_optim_chunk() elements).
  * grad_sqnorm: out_sq[0] = sum of squares over the listed chunks.  clip_adamw: gradients of items with clip = 1 are
  * scaled by min(1, max_norm / (sqrt(total_sq[0]) + 1e-6)) in place, then p, m, v follow torch.optim.AdamW at step `step`
- * (>= 1) with the learning rate of the item's group. */
+ * (>= 1) with the learning rate of the item's group; a tensor's own Adam step (bias correction) is step - step0, as torch keeps
+ * state['step'] per parameter. */
 size_t gpvb200_optim_item_size(void);
 int gpvb200_optim_chunk(void);
 int gpvb200_grad_sqnorm(const void* items, const int32_t* blk_item, const int32_t* blk_chunk, int32_t n_blocks, const float* grads,

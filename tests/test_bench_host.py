@@ -94,7 +94,7 @@ def test_attention_summary_from_trace_rows():
     # the positions in bench._ATTENTION_ARGS must be where `B, H, Sq, Sk, dh` sit in each call of kernels.py
     src = inspect.getsource(kernels)
     for name, pos in bench._ATTENTION_ARGS.items():
-        m = re.search(name + r"\((.*?)\),\s*\"attention", src, re.S)
+        m = re.search(name + r"\((.*?)\),\s*\"att", src, re.S)
         if m is None:
             assert name == "gpvb200_attention_fwd"          # only reached through the _bs form
             continue
@@ -115,9 +115,12 @@ def test_attention_summary_from_trace_rows():
     bwd = ("gpvb200_attention_bwd_drop", (p0,) * 10 + (i64(768),) * 8 + (32, 8, 300, 300, 32, 0, ctypes.c_float(0.1), p0, ctypes.c_uint32(1),
                                                                   ctypes.c_float(0.1), p0), 0.087)
     other = ("gpvb200_gemm", (p0, p0), 1.0)
-    out = bench.attention_summary([fwd, fwd, bwd, other], 1386.5)
+    blk = ("gpvb200_attn_block_fwd", (p0, i64(768)) * 3 + (p0, 32, 8, 300, 300, 32, ctypes.c_float(0.1), p0), 0.044)
+    out = bench.attention_summary([fwd, fwd, bwd, other, blk], 1386.5)
     f = 4.0 * 32 * 8 * 300 * 300 * 32
-    assert set(out) == {"fwd_dh32", "bwd_dh32"}
+    kb = "fwd_dh32_attn_block_tcgen05_with_out_proj_ln"
+    assert set(out) == {"fwd_dh32", "bwd_dh32", kb}
+    assert abs(out[kb]["flop_per_launch"] - (f + 2.0 * 32 * 300 * 256 * 256)) < 1
     assert out["fwd_dh32"]["launches_per_step"] == 2 and abs(out["fwd_dh32"]["flop_per_launch"] - f) < 1
     assert abs(out["fwd_dh32"]["achieved"] - f / 35e-6 / 1e12) < 1e-6 * out["fwd_dh32"]["achieved"]
     assert abs(out["bwd_dh32"]["achieved"] - 2.5 * f / 87e-6 / 1e12) < 1e-6 * out["bwd_dh32"]["achieved"]

@@ -87,16 +87,22 @@ def _attn_block_ref(TO, P2, p, attn, norm, xf, q_add, kmem_f, vmem_f, H, causal=
     return TO.ln(P2, f"{p}.{norm}", xf + TO.mha(P2, f"{p}.{attn}", q_in, kmem_f, vmem_f, H), 1e-5)
 
 
-def test_encoder_self_attn_block(ctx, cuda):
-    """transformer.py:153-157 (q = k = x + pos, v = x, +residual, LayerNorm) forward and backward."""
+@pytest.mark.parametrize("B,S", [(2, 63), (22, 300)])
+def test_encoder_self_attn_block(ctx, cuda, B, S):
+    """transformer.py:153-157 (q = k = x + pos, v = x, +residual, LayerNorm) forward and backward.  At (22, 300) (66 row tiles) the
+    forward is the tcgen05 attn_block kernel (attention + out-proj + residual + LayerNorm in one launch), at (2, 63) the
+    mma.sync attention kernel + GEMM + LayerNorm; the backward is the same kernels in both cases."""
     from oracle import torch_oracle as TO
     eng, Pd = ctx
     torch.manual_seed(0)
-    B, S, D = 2, 63, 256
+    D = 256
+    from gpv1_b200 import _C
+    n0 = _C.lib().launches
     p = "detr.transformer.encoder.layers.2"
     x, pos, dy = bfr(B * S, D, dev=cuda), bfr(S, D, dev=cuda), bfr(B * S, D, dev=cuda, scale=0.1)
     eng.grad_arena.zero_()
     y, sa = eng._self_attn_fwd(p, x, pos, S, B, S, 8)
+    assert _C.lib().launches - n0 == (4 if B * ((S + 127) // 128) >= 64 else 6), "unexpected forward launch count (fused path not taken?)"
     dx = eng._self_attn_bwd(p, dy, sa, None, B, S, 8)
     Pl = leafs(Pd, p)
     P2 = dict(Pd)

@@ -131,14 +131,16 @@ def ctx(cuda):
     return model, eng, Pd
 
 
-def test_encoder_layer_with_dropout_matches_autograd(ctx, cuda):
+@pytest.mark.parametrize("B,S", [(2, 64), (22, 300)])
+def test_encoder_layer_with_dropout_matches_autograd(ctx, cuda, B, S):
     """One DETR encoder layer (transformer.py:148-161) in train mode: attention-probability dropout, dropout1, the FFN's
-    hidden dropout and dropout2, forward and backward, against autograd fed with the masks of the engine's sites."""
+    hidden dropout and dropout2, forward and backward, against autograd fed with the masks of the engine's sites.  (22, 300) is
+    large enough (66 row tiles) for the tcgen05 attn_block / mlp_block kernels to be the ones that run."""
     import torch.nn.functional as F
     from gpv1_b200 import kernels as k
     model, eng, Pd = ctx
     torch.manual_seed(0)
-    B, S, D, H = 2, 64, 256, 8
+    D, H = 256, 8
     p = "detr.transformer.encoder.layers.1"
     x = (torch.randn(B * S, D, device=cuda)).to(BF)
     pos = torch.randn(S, D, device=cuda).to(BF)

@@ -331,6 +331,75 @@ def test_clip_adamw_matches_torch(cuda):
             assert torch.allclose(p, ref_params[n].data, rtol=2e-5, atol=2e-6), (step, n, (p - ref_params[n].data).abs().max().item())
 
 
+def test_clip_adamw_state_dict_is_torch_layout_and_steps_are_per_parameter(cuda):
+    """(a) state_dict() is torch.optim.AdamW's own layout -- a torch AdamW built the reference's way
+    (train_distr.py:234-253) loads it and continues identically, and ClipAdamW loads torch's; (b) a tensor whose state is missing
+    from the loaded checkpoint (DETR parameters unfrozen for the second training phase) starts its bias correction at step 1,
+    as torch does, instead of inheriting the global step."""
+    from gpv1_b200.optim import ClipAdamW, group_of
+    torch.manual_seed(6)
+    shapes = {"detr.backbone.0.body.layer2.0.conv1.weight": (16, 8, 1, 1), "detr.class_embed.bias": (24,), "bert_joiner.weight": (8, 8),
+              "relevance_tokens": (2, 8), "frozen.never.steps": (3,)}
+    live = [n for n in shapes if n != "frozen.never.steps"]
+
+    def build(names):
+        arena = torch.zeros(sum(math.prod(shapes[n]) for n in names) + 8, device=cuda)
+        named, off = [], 0
+        for n in names:
+            num = math.prod(shapes[n])
+            named.append((n, torch.randn(shapes[n], device=cuda), arena[off:off + num].view(shapes[n])))
+            off += num
+        return ClipAdamW(named, arena, lr=1e-3, lr_backbone=1e-4, weight_decay=1e-2, clip_max_norm=0.1, all_names=list(shapes)), named
+
+    def torch_opt(params):
+        groups = [[], [], [], []]
+        for n in shapes:
+            groups[group_of(n)].append(params[n])
+        return torch.optim.AdamW([{"params": groups[0], "lr": 1e-4}, {"params": groups[1]}, {"params": groups[2]}, {"params": groups[3]}],
+                                 lr=1e-3, weight_decay=1e-2), groups
+
+    def step_both(opt, named, ref, groups, params):
+        for n, p, g in named:
+            g.copy_(torch.randn_like(g))
+            params[n].grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(groups[0] + groups[1], 0.1)
+        ref.step()
+        opt.step()
+
+    # ---- phase 1: the detr.* tensors are frozen (no optimizer state), 4 steps
+    phase1 = [n for n in live if not n.startswith("detr.")]
+    opt1, named1 = build(phase1)
+    params = {n: torch.nn.Parameter(torch.randn(shapes[n], device=cuda)) for n in shapes}
+    for n, p, g in named1:
+        params[n].data.copy_(p)
+    ref, groups = torch_opt(params)
+    for _ in range(4):
+        step_both(opt1, named1, ref, groups, params)
+    sd = opt1.state_dict()
+    ref_sd = ref.state_dict()
+    assert set(sd["state"]) == set(ref_sd["state"])                    # same indices present (only the tensors that stepped)
+    assert [g["params"] for g in sd["param_groups"]] == [g["params"] for g in ref_sd["param_groups"]]
+    for i, st in ref_sd["state"].items():
+        assert float(sd["state"][i]["step"]) == float(st["step"]) == 4.0
+        assert torch.allclose(sd["state"][i]["exp_avg"], st["exp_avg"], rtol=1e-5, atol=1e-8)
+    ref2, groups2 = torch_opt(params)
+    ref2.load_state_dict({"state": sd["state"], "param_groups": sd["param_groups"]})      # torch reads ClipAdamW's file
+    # ---- phase 2: everything trains; ClipAdamW resumes from TORCH's state dict
+    opt2, named2 = build(live)
+    for n, p, g in named2:
+        p.copy_(params[n].data)
+    opt2.load_state_dict(ref_sd)
+    assert opt2.t == 4 and [opt2.t - s0 for s0 in opt2.step0] == [0 if n.startswith("detr.") else 4 for n in live]
+    for _ in range(3):
+        step_both(opt2, named2, ref2, groups2, params)
+        torch.cuda.synchronize()
+        for n, p, g in named2:
+            assert torch.allclose(p, params[n].data, rtol=2e-5, atol=2e-6), (n, (p - params[n].data).abs().max().item())
+    sd2 = opt2.state_dict()
+    assert float(sd2["state"][opt2.index_of["detr.class_embed.bias"]]["step"]) == 3.0
+    assert float(sd2["state"][opt2.index_of["relevance_tokens"]]["step"]) == 7.0
+
+
 def test_stem_s2d_uint8_equals_normalised_fp32(cuda):
     """uint8 NHWC ingest: (u8/255 - mean)/std folded into the stem's read gives the same s2d map as the
     fp32 NCHW path fed with the reference's ToTensor + Normalize output (coco_generic_dataset.py:31-32)."""

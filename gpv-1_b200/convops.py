@@ -10,10 +10,11 @@ import torch
 from . import kernels as k
 
 
-def conv_dgrad(dy, w, *, ksize, stride, in_hw, aux=None, aux_mode=k.AUX_NONE, residual=None, out=None):
+def conv_dgrad(dy, w, *, ksize, stride, in_hw, aux=None, aux_mode=k.AUX_NONE, residual=None, out=None, only_parity=None):
     """dy [n,Ho,Wo,Cout] bf16, w [taps,Cout,Cin] bf16 (forward layout) -> dx [n,Hi,Wi,Cin] bf16.
 
-    Epilogue: dx = (acc + residual) * mask(aux), with residual/aux indexed like dx.
+    Epilogue: dx = (acc + residual) * mask(aux), with residual/aux indexed like dx.  only_parity = (ph, pw) (stride 2): only that
+    parity class of dx is written (the caller owns the other positions; residual may alias out for an in-place accumulation).
     """
     n, Ho, Wo, Cout = dy.shape
     Hi, Wi = in_hw
@@ -26,6 +27,8 @@ def conv_dgrad(dy, w, *, ksize, stride, in_hw, aux=None, aux_mode=k.AUX_NONE, re
     dx = out if out is not None else torch.empty((n, Hi, Wi, Cin), device=dy.device, dtype=torch.bfloat16)
     for ph in range(2):
         for pw in range(2):
+            if only_parity is not None and (ph, pw) != tuple(only_parity):
+                continue
             sel = [(i, (ph - dh) // 2, (pw - dw) // 2) for i, (dh, dw) in enumerate(taps)
                    if (ph - dh) % 2 == 0 and (pw - dw) % 2 == 0]
             nh, nw = (Hi - ph + 1) // 2, (Wi - pw + 1) // 2

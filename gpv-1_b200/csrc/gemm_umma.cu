@@ -1064,7 +1064,12 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
 
   // ---- pair variant: K-major A (plain GEMM / implicit-GEMM convolution), bf16 or fp32 stores, deep contraction, 256 columns
   const int kb_total_pre = d->mode == 0 ? (d->K + 63) / 64 : k_iters_pre;
-  const bool pair_shape_ok = !kp.a_mn && splits == 1 && !d->d_atomic;
+  static int pair_fwd_only = -1;   // GPVB200_PAIR_FWD=1: pairs only for forward-direction contractions (K-major B), which run without
+  if (pair_fwd_only < 0) {         // the single-CTA weight-gradient lane beside them (a pair needs both SMs of a TPC free at once)
+    const char* e = getenv("GPVB200_PAIR_FWD");
+    pair_fwd_only = e ? atoi(e) : 0;
+  }
+  const bool pair_shape_ok = !kp.a_mn && splits == 1 && !d->d_atomic && !(pair_fwd_only && d->b_mn);
   // GPVB200_PAIR_BN=128 also pairs the 128-column tiles (per CTA: A 16 KB + B 8 KB per k-block -- the L2 traffic of the single-CTA
   // 256-column tile, so only the halved item count remains; default 256)
   static int pair_min_bn = -1;

@@ -140,7 +140,7 @@ extern "C" int gpvb200_grad_sqnorm(const void* items, const int32_t* blk_item, c
                                    const float* grads, float* out_sq, void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
-  GPV_REQUIRE(items && blk_item && blk_chunk && grads && out_sq && n_blocks >= 0, "grad_sqnorm: bad arguments");
+  GPV_REQUIRE(items && grads && out_sq && n_blocks >= 0 && (n_blocks == 0 || (blk_item && blk_chunk)), "grad_sqnorm: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(out_sq, 0, sizeof(float), st);
   if (e != cudaSuccess) {

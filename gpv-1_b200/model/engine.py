@@ -117,6 +117,13 @@ class Engine:
         self.concurrent = True                                # run independent branches on side streams (lanes)
         self.fused_layers = os.environ.get("GPVB200_FUSED", "1") != "0"   # row-tile-resident sub-layer kernels (layer_umma.cu)
         self.use_attn_block = self.fused_layers and os.environ.get("GPVB200_ATTN_BLOCK", "1") != "0"   # tcgen05 attention + out-proj + LN
+        # lane scheduling (measured in profiles/r2q_lanes.txt: 16.97 -> 16.51 ms per step): the weight-gradient lanes may lag behind the
+        # data-gradient chain until the end of a gradient stage instead of being joined after every layer / bottleneck
+        # (GPVB200_LAZY_JOIN=0 restores the per-layer join), and the lane-0 work (weight and bias gradients) is dealt round-robin to
+        # GPVB200_WGRAD_LANES streams (default 3) so that independent weight gradients overlap each other
+        self.lazy_join = os.environ.get("GPVB200_LAZY_JOIN", "1") == "1"
+        self.n_wlanes = max(1, int(os.environ.get("GPVB200_WGRAD_LANES", "3")))
+        self._rr = 0
         self._lanes, self._dirty, self._keep = {}, set(), []
 
     # ================================================================================================ weights
@@ -376,6 +383,9 @@ class Engine:
     def _aside(self, *keep, lane=0):
         if not self.concurrent or self.dev.type != "cuda":
             return contextlib.nullcontext()
+        if lane == 0 and self.n_wlanes > 1:
+            lane = 100 + self._rr % self.n_wlanes
+            self._rr += 1
         st = self._lanes.get(lane)
         if st is None:
             st = self._lanes[lane] = torch.cuda.Stream(device=self.dev)
@@ -383,6 +393,13 @@ class Engine:
         self._keep.extend(t for t in keep if t is not None)
         self._dirty.add(lane)
         return torch.cuda.stream(st)
+
+    def _join_layer(self, *keep):
+        """End of a layer / bottleneck of the backward pass: join the lanes, or (lazy) only keep what they still read alive."""
+        if self.lazy_join and self.concurrent and self.dev.type == "cuda":
+            self._keep.extend(t for t in keep if t is not None)
+        else:
+            self._join()
 
     def _join(self, lane=None):
         lanes = list(self._dirty) if lane is None else ([lane] if lane in self._dirty else [])
@@ -475,20 +492,23 @@ class Engine:
         if self._trains(p + ".conv2.weight"):
             with self._aside(dh2):
                 k.conv_wgrad(dh2, h1, self.Gp[p + ".conv2.weight"], ksize=3, stride=s, rowscale=sc[p + ".bn2"])
-        # identity / downsample branch
-        if ds:
-            didn = conv_dgrad(dpre, W[p + ".downsample.0.weight"], ksize=1, stride=s, in_hw=(H, Wd)) if need_dx else None
-        else:
-            didn = dpre
-        # conv1 (1x1): dx = (dh1 W1 + didn) * relu'(x)  -> already the masked gradient of the previous block
+        # conv1 (1x1) + identity / downsample branch: dx = (dh1 W1 + didn) * relu'(x)  -> already the masked gradient of the previous block
         if self._trains(p + ".conv1.weight"):
             with self._aside(dh1):
                 k.linear_wgrad(dh1.view(-1, planes), xf, G[p + ".conv1.weight"].view(planes, inp), rowscale=sc[p + ".bn1"])
         dx = None
-        if need_dx:
+        if need_dx and ds and s == 2:
+            # stride-2 1x1 down-sample: its data gradient touches only the even positions of dx.  dx = (dh1 W1) * relu'(x) first, then
+            # ONE implicit-GEMM launch adds dpre Wds^T at those positions in place (residual = out; the mask is idempotent), instead
+            # of materialising the mostly-zero branch gradient (three strided zero-fills + one GEMM + a full-size residual read)
+            dx = k.linear_dgrad(dh1.view(-1, planes), W[p + ".conv1.weight"][0], aux=xf, aux_mode=MASK_RELU).view(x.shape)
+            conv_dgrad(dpre, W[p + ".downsample.0.weight"], ksize=1, stride=2, in_hw=(H, Wd), aux=x, aux_mode=MASK_RELU, residual=dx,
+                       out=dx, only_parity=(0, 0))
+        elif need_dx:
+            didn = conv_dgrad(dpre, W[p + ".downsample.0.weight"], ksize=1, stride=s, in_hw=(H, Wd)) if ds else dpre
             dx = k.linear_dgrad(dh1.view(-1, planes), W[p + ".conv1.weight"][0], residual=didn.view(-1, inp), aux=xf,
                                 aux_mode=MASK_RELU).view(x.shape)
-        self._join()            # the saved activations of this block are released by the caller
+        self._join_layer(*saved)            # the saved activations of this block are released by the caller
         return dx
 
     def _backbone_bwd(self, dpre, acts):
@@ -950,6 +970,12 @@ class Engine:
         Returns (total_loss fp32 [1] on device, outputs dict)."""
         if self.train_mode:
             self.drop_seed.add_(1)                            # new masks every step; backward re-reads the same value
+        # the gradient arenas are cleared here, on a lane beside the forward pass (456 MB of stores that used to open the backward's
+        # critical path); the previous step's gradients have been consumed by then (all-reduce and optimizer follow backward)
+        with self._aside(lane=3):
+            self.grad_arena.zero_()
+            self.grad_pack.zero_()
+        self._arena_clean = True
         s = self.encode(images, qids, save=True, mask=mask)
         B, Q, D = s["B"], self.Q, self.D
         M = B * Q
@@ -977,6 +1003,7 @@ class Engine:
         # (n_loc > 0 always holds for a captured step: the set criterion then yields zeros when no image has boxes)
         s.update(S_ans=S, sv_txt=sv_txt, dlogits_v=dlogits_v, dlg=dlg, dbox=dbox, loss_terms=loss_terms, idx_q=idx_q, idx_t=idx_t)
         self.saved = s
+        self._join(3)
         return loss, s
 
     @torch.no_grad()
@@ -986,8 +1013,10 @@ class Engine:
         assert s is not None, "backward() without a forward_train()"
         self.saved = None
         W, Pm, G = self.W, self.P, self.G
-        self.grad_arena.zero_()
-        self.grad_pack.zero_()
+        if not getattr(self, "_arena_clean", False):          # (forward_train clears the arenas beside the forward pass)
+            self.grad_arena.zero_()
+            self.grad_pack.zero_()
+        self._arena_clean = False
         B, Q, D, d = s["B"], self.Q, self.D, self.d
         M, S, Tl, Tm, Sx = B * Q, s["S"], s["Tl"], s["Tm"], s["S_ans"]
         depth = self._backward_depth()
@@ -1008,7 +1037,7 @@ class Engine:
             dx = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm3", dx, sf)
             dx, dmemory = self._cross_attn_bwd(p, dx, sc, s["memory"], s["memory"], dmemory, None, B, Sx, Tm, self.h_txt)
             dx = self._self_attn_bwd(p, dx, sa, None, B, Sx, self.h_txt, causal=True, has_pos=False)
-            self._join()
+            self._join_layer()
         self._lin_bwd("answer_input_embedings.transform", emb, dx, need_dx=False)
         self._done(0)
         # ---- memory split, relevance conditioning
@@ -1024,7 +1053,7 @@ class Engine:
         # ---- co-attention
         for i in range(self.n_co - 1, -1, -1):
             dlang, dvis = self._coatt_bwd(f"co_att_transformer.{i}", dlang, dvis, s["co"][i], B, Tl, Q)
-            self._join()
+            self._join_layer()
         self._lin_bwd("bert_joiner", s["qe_b"], dlang, need_dx=False)
         self._done(1)
         # ---- detr_joiner, ROI head, box / class heads
@@ -1058,7 +1087,7 @@ class Engine:
             dt = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm3", dt, sf)
             dt, dmem = self._cross_attn_bwd(p, dt, sc, s["mem_pos"], s["mem"], dmem, gq, B, Q, S, self.h_detr, kmask=s["kmask"])
             dt = self._self_attn_bwd(p, dt, sa, gq, B, Q, self.h_detr)
-            self._join()
+            self._join_layer()
         self._done(2)
         if depth == 2:
             return self._backward_end()
@@ -1068,7 +1097,7 @@ class Engine:
             sa, sf = s["enc"][i]
             dx = self._ffn_bwd(p + ".linear1", p + ".linear2", p + ".norm2", dx, sf)
             dx = self._self_attn_bwd(p, dx, sa, None, B, S, self.h_detr, kmask=s["kmask"])
-            self._join()
+            self._join_layer()
         # ---- input_proj: dC5 = (dx Wip + dC5_roi) * relu'(c5)  -> masked gradient of the last bottleneck
         c5f = s["c5"].view(B * S, C5)
         dpre = self._lin_bwd("detr.input_proj", c5f, dx, residual=dc5, aux=c5f, aux_mode=MASK_RELU)

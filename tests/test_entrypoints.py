@@ -94,8 +94,16 @@ def test_train_loop_two_phases_and_resume(tmp_path):
         loss1 = T.train(cfg, vocab=vocab, log=logs.append)
         ck = torch.load(os.path.join(str(tmp_path), "model.pth"))
         assert any(k.startswith("module.detr.") for k in ck["model"]) and ck["epoch"] == 0 and ck["step"] == 3
-        frozen_state = [n for n in ck["optimizer"]["state"] if n.startswith("detr.transformer.")]
+        # the optimizer entry is torch.optim.AdamW's layout: index-keyed state in the reference's four-group parameter order
+        from gpv1_b200.optim import group_of
+        names = [n for n, _ in small_gpv(cfg.model, vocab=vocab).named_parameters()]
+        order = [n for g in range(4) for n in names if group_of(n) == g]
+        state = ck["optimizer"]["state"]
+        assert [len(g["params"]) for g in ck["optimizer"]["param_groups"]] == [sum(1 for n in names if group_of(n) == g) for g in range(4)]
+        frozen_state = [n for i, n in enumerate(order) if n.startswith("detr.transformer.") and i in state]
         assert not frozen_state, frozen_state[:3]
+        assert any(i in state for i, n in enumerate(order) if n.startswith("text_decoder."))
+        assert all(float(v["step"]) == 3.0 for v in state.values()) and "warmup_scheduler" in ck and "lr" in ck
         cfg2 = load_config(overrides=ov + [f"training.ckpt={os.path.join(str(tmp_path), 'model.pth')}", "training.num_epochs=2"])
         loss2 = T.train(cfg2, vocab=vocab, log=logs.append)
     finally:

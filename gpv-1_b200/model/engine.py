@@ -520,6 +520,7 @@ class Engine:
             saved, acts[idx] = acts[idx], None
             dpre = self._bottleneck_bwd(blk, dpre, saved, need_dx=idx > 0)
             if bi == 0:                                        # first block of layer `li` was the last one to finish
+                self._join()                                   # the packed 3x3 weight gradients are written on the lanes
                 for name, c, _ in self._g3:
                     if f".layer{li}." in name:
                         k.unpack_conv_grad(self.Gp[name], self.G[name])

@@ -835,12 +835,14 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
   // one persistent CTA per SM; the pair variant launches clusters of two CTAs (the two SMs of a TPC), one pair per work item
   int slots = PAIR ? num_sms() / 2 : num_sms();
   {
-    // GPVB200_WGRAD_CTAS=<n>: persistent grid of the atomically accumulating launches (weight gradients, which run on a lane beside
-    // the data-gradient chain) capped at n CTAs, so that the chain's own kernels find free SMs (scheduling experiment; default: all)
+    // The atomically accumulating launches (weight gradients) run on lanes beside the data-gradient chain; as persistent kernels they
+    // would occupy every SM and the chain's next kernel would wait for their CTAs to retire.  Their grid is therefore capped at half
+    // the SMs (measured: 16.51 -> 16.05 ms per step at 72 of 148, profiles/r2t_wgrad_cta_cap.txt).  GPVB200_WGRAD_CTAS=<n> overrides,
+    // 0 = no cap.
     static int wg_cap = -1;
     if (wg_cap < 0) {
       const char* e = getenv("GPVB200_WGRAD_CTAS");
-      wg_cap = e ? atoi(e) : 0;
+      wg_cap = e ? atoi(e) : num_sms() / 2;
     }
     if (wg_cap > 0 && kp.d_atomic && !PAIR && slots > wg_cap) slots = wg_cap;
   }

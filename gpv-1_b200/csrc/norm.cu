@@ -181,6 +181,105 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
   }
 }
 
+// The same for D <= 256 (DETR encoder / decoder: one 16-byte chunk per lane), FOUR rows per warp iteration: all of a warp's loads
+// (x, dy, statistics of four rows) are in flight before the first reduction, which is what bounds this kernel -- it sits on the
+// critical path of the backward pass (two per transformer layer) and moves only 20 MB per launch.
+template <bool AFFINE, bool DXM>
+__global__ void __launch_bounds__(256) layernorm_bwd_d256_kernel(const bf16* __restrict__ dy, long long lddy,
+                                                                 const bf16* __restrict__ x, long long ldx,
+                                                                 const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                                 bf16* __restrict__ dx, long long lddx, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta, int M, int D, bf16* __restrict__ dxm,
+                                                                 long long lddxm, const DropArgs dr) {
+  pdl_sync();
+  constexpr int R = 4;
+  const uint32_t dkey = DXM ? drop_key(*dr.seed, dr.site) : 0u;
+  __shared__ float red[2 * 256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool live = lane < (D >> 3);
+  float gam[8], ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gam[j] = (AFFINE && live) ? __ldg(gamma + lane * 8 + j) : 1.0f;
+    ag[j] = ab[j] = 0.f;
+  }
+  if (AFFINE) {
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+  }
+  const float invD = 1.0f / (float)D;
+  for (long long row0 = ((long long)blockIdx.x * 8 + warp) * R; row0 < M; row0 += (long long)gridDim.x * 8 * R) {
+    uint4 ux[R], ud[R];
+    float2 st[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      const bool ok = row < M && live;
+      ux[r] = ok ? *reinterpret_cast<const uint4*>(x + row * ldx + lane * 8) : make_uint4(0, 0, 0, 0);
+      ud[r] = ok ? *reinterpret_cast<const uint4*>(dy + row * lddy + lane * 8) : make_uint4(0, 0, 0, 0);
+      st[r] = row < M ? *reinterpret_cast<const float2*>(stats + row * 2) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      if (row >= M) break;                                       // warp-uniform
+      const float mean = st[r].x, rstd = st[r].y;
+      const uint32_t wx[4] = {ux[r].x, ux[r].y, ux[r].z, ux[r].w}, wd[4] = {ud[r].x, ud[r].y, ud[r].z, ud[r].w};
+      float g[8], xh[8];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fx = unpack_bf16x2(wx[j]), fd = unpack_bf16x2(wd[j]);
+        const float h0 = live ? (fx.x - mean) * rstd : 0.f, h1 = live ? (fx.y - mean) * rstd : 0.f;
+        if (AFFINE) {
+          ag[2 * j] += fd.x * h0;
+          ag[2 * j + 1] += fd.y * h1;
+          ab[2 * j] += fd.x;
+          ab[2 * j + 1] += fd.y;
+        }
+        g[2 * j] = fd.x * gam[2 * j];
+        g[2 * j + 1] = fd.y * gam[2 * j + 1];
+        xh[2 * j] = h0;
+        xh[2 * j + 1] = h1;
+        s1 += g[2 * j] + g[2 * j + 1];
+        s2 += g[2 * j] * h0 + g[2 * j + 1] * h1;
+      }
+      const float c1 = warp_sum(s1) * invD, c2 = warp_sum(s2) * invD;
+      if (live) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] - c1 - xh[j] * c2);
+        uint4 u;
+        u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+        u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dx + row * lddx + lane * 8) = u;
+        if (DXM) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            drop_pair(o[2 * j], o[2 * j + 1], dkey, (uint32_t)row * (uint32_t)(D >> 1) + lane * 4 + j, dr.thresh16, dr.scale);
+          u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+          u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dxm + row * lddxm + lane * 8) = u;
+        }
+      }
+    }
+  }
+  if (AFFINE) {
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[lane * 8 + j], ag[j]);
+        atomicAdd(&red[D + lane * 8 + j], ab[j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      atomicAdd(dgamma + i, red[i]);
+      atomicAdd(dbeta + i, red[D + i]);
+    }
+  }
+}
+
 }  // namespace gpv
 
 using namespace gpv;
@@ -243,7 +342,18 @@ extern "C" int gpvb200_layernorm_bwd_drop(const void* dy, int64_t lddy, const vo
 #define GPV_LN_BWD(MAXC, AFF, DXM)                                                                                          \
   launch_k(layernorm_bwd_kernel<MAXC, AFF, DXM>, dim3(grid), dim3(256), smem, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, \
            gamma, (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr)
-  if (gamma != nullptr) {
+  if (D <= 256) {
+    const int g4 = (M + 31) / 32 < 148 * 4 ? (M + 31) / 32 : 148 * 4;
+#define GPV_LN_BWD4(AFF, DXM)                                                                                                   \
+  launch_k(layernorm_bwd_d256_kernel<AFF, DXM>, dim3(g4), dim3(256), 0, st, (const bf16*)dy, lddy, (const bf16*)x, ldx, stats, gamma, \
+           (bf16*)dx, lddx, dgamma, dbeta, M, D, dxm, lddxm, dr)
+    if (gamma != nullptr) {
+      if (dxm) GPV_LN_BWD4(true, true); else GPV_LN_BWD4(true, false);
+    } else {
+      if (dxm) GPV_LN_BWD4(false, true); else GPV_LN_BWD4(false, false);
+    }
+#undef GPV_LN_BWD4
+  } else if (gamma != nullptr) {
     if (dxm) GPV_LN_BWD(3, true, true); else GPV_LN_BWD(3, true, false);
   } else if (D <= 768) {
     if (dxm) GPV_LN_BWD(3, false, true); else GPV_LN_BWD(3, false, false);

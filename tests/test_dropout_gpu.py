@@ -64,10 +64,10 @@ def test_gemm_dropout_after_activation(cuda):
     assert h.float()[mask == 0].abs().max().item() == 0
 
 
-def test_layernorm_dropout_outputs(cuda):
+@pytest.mark.parametrize("M,D", [(640, 768), (3203, 256), (9600, 256), (37, 128)])
+def test_layernorm_dropout_outputs(cuda, M, D):
     from gpv1_b200 import kernels as k
     torch.manual_seed(3)
-    M, D = 640, 768
     x, g, b = torch.randn(M, D, device=cuda).to(BF), torch.randn(D, device=cuda), torch.randn(D, device=cuda)
     d = _drop(cuda, 31)
     mask = k.dropout_mask(M, D, d).float()

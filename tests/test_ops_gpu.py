@@ -70,7 +70,7 @@ def test_attention(cuda, B, H, Sq, Sk, dh, causal, masked):
 
 
 @pytest.mark.parametrize("M,D,eps,affine", [(9600, 256, 1e-5, True), (640, 768, 1e-12, True), (3200, 2048, 1e-5, False),
-                                            (77, 768, 1e-5, True), (5, 256, 1e-5, False)])
+                                            (77, 768, 1e-5, True), (5, 256, 1e-5, False), (3203, 256, 1e-5, True), (50, 64, 1e-5, True)])
 def test_layernorm(cuda, M, D, eps, affine):
     from gpv1_b200 import kernels as k
     torch.manual_seed(1)

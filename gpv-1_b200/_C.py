@@ -27,7 +27,7 @@ class GemmDesc(ctypes.Structure):
         ("bias", c_void_p), ("rowscale", c_void_p), ("residual", c_void_p), ("aux", c_void_p),
         ("lda", c_int64), ("ldb", c_int64), ("ldd", c_int64), ("ldr", c_int64), ("ldaux", c_int64),
         ("a_batch_stride", c_int64), ("b_batch_stride", c_int64), ("d_batch_stride", c_int64),
-        ("drop_seed", c_void_p), ("drop_mode", c_int32), ("drop_site", ctypes.c_uint32), ("drop_p", c_float), ("pad_", c_int32),
+        ("drop_seed", c_void_p), ("drop_mode", c_int32), ("drop_site", ctypes.c_uint32), ("drop_p", c_float), ("max_ctas", c_int32),
     ]
 
 

@@ -40,7 +40,7 @@ struct KParams {
   int ntaps;
   int tap_dh[9], tap_dw[9], tap_w[9];
   int OH, OW, os, ooh, oow;
-  int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal, pf_mode;
+  int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal, pf_mode, max_ctas;
   uint32_t epi_warp_bytes, epi_aux_off, epi_slot_stride;   // per-warp epilogue slabs (coalesced path)
   int nprod;      // producer warps in use (1..kProducers; GPVB200_PRODUCERS, default kProducers)
   int drop_mode;  // 0 none, 1 before the residual add, 2 after the activation (DropArgs below)
@@ -835,16 +835,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
   // one persistent CTA per SM; the pair variant launches clusters of two CTAs (the two SMs of a TPC), one pair per work item
   int slots = PAIR ? num_sms() / 2 : num_sms();
   {
-    // The atomically accumulating launches (weight gradients) run on lanes beside the data-gradient chain; as persistent kernels they
-    // would occupy every SM and the chain's next kernel would wait for their CTAs to retire.  Their grid is therefore capped at half
-    // the SMs (measured: 16.51 -> 16.05 ms per step at 72 of 148, profiles/r2t_wgrad_cta_cap.txt).  GPVB200_WGRAD_CTAS=<n> overrides,
-    // 0 = no cap.
-    static int wg_cap = -1;
-    if (wg_cap < 0) {
-      const char* e = getenv("GPVB200_WGRAD_CTAS");
-      wg_cap = e ? atoi(e) : num_sms() / 2;
-    }
-    if (wg_cap > 0 && kp.d_atomic && !PAIR && slots > wg_cap) slots = wg_cap;
+    // Launches that run on a lane beside a dependent chain of kernels (weight gradients beside the data-gradient chain) ask for a
+    // capped grid (gpvb200_gemm_desc.max_ctas): as persistent kernels they would otherwise occupy every SM and the chain's next
+    // kernel would wait for their CTAs to retire (measured: 16.51 -> 16.05 ms per step at 72 of 148, profiles/r2t_wgrad_cta_cap.txt).
+    const int wg_cap = kp.max_ctas;
+    if (wg_cap > 0 && !PAIR && slots > wg_cap) slots = wg_cap;
   }
   const int grid = (kp.total_work < slots ? kp.total_work : slots) * (PAIR ? 2 : 1);
   static int pdl = -1;   // GPVB200_PDL=0 disables programmatic dependent launch
@@ -944,6 +939,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   kp.aux_mode = d->aux_mode;
   kp.d_fp32 = d->d_fp32;
   kp.d_atomic = d->d_atomic;
+  kp.max_ctas = d->max_ctas > 0 ? d->max_ctas : 0;
   kp.alpha = d->alpha;
   kp.res_fp32 = d->res_fp32;
   kp.D = d->D;

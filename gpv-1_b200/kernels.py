@@ -48,7 +48,12 @@ def _req(t, dtype=None):
     return t
 
 
+LANE_CTA_CAP = 0      # > 0 while the engine issues work on a lane (Engine._aside): cap of the persistent grid of atomically accumulating launches
+
+
 def _launch_gemm(d: _C.GemmDesc):
+    if LANE_CTA_CAP > 0 and d.d_atomic:
+        d.max_ctas = LANE_CTA_CAP
     _C.check(_C.lib().gpvb200_gemm(ctypes.byref(d), _C.stream_ptr()), "gemm")
 
 

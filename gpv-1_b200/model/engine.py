@@ -68,6 +68,22 @@ def sine_position_masked(mask, num_pos_feats=128, temperature=10000.0):
     return torch.cat((py, px), dim=3).reshape(-1, 2 * num_pos_feats)
 
 
+class _Lane:
+    """Context of Engine._aside: work issued inside runs on the lane's stream, and its atomically accumulating GEMM launches (weight
+    gradients) get the lane's CTA cap (kernels.LANE_CTA_CAP -> gpvb200_gemm_desc.max_ctas)."""
+
+    def __init__(self, stream, cap):
+        self.ctx, self.cap = torch.cuda.stream(stream), cap
+
+    def __enter__(self):
+        self.prev, k.LANE_CTA_CAP = k.LANE_CTA_CAP, self.cap
+        return self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        k.LANE_CTA_CAP = self.prev
+        return self.ctx.__exit__(*a)
+
+
 class Engine:
     def __init__(self, tensors, specs, cfg, device):
         """tensors: name -> fp32 CUDA tensor for every state_dict entry (nn.Parameters and buffers of the module that
@@ -121,6 +137,9 @@ class Engine:
         # data-gradient chain until the end of a gradient stage instead of being joined after every layer / bottleneck
         # (GPVB200_LAZY_JOIN=0 restores the per-layer join), and the lane-0 work (weight and bias gradients) is dealt round-robin to
         # GPVB200_WGRAD_LANES streams (default 3) so that independent weight gradients overlap each other
+        # weight-gradient GEMMs issued on a lane use at most this many CTAs (half the SMs: the data-gradient chain keeps the rest;
+        # GPVB200_WGRAD_CTAS overrides, 0 = uncapped; scan in profiles/r2t_wgrad_cta_cap.txt)
+        self.lane_cta_cap = int(os.environ.get("GPVB200_WGRAD_CTAS", str(torch.cuda.get_device_properties(device).multi_processor_count // 2)))
         self.lazy_join = os.environ.get("GPVB200_LAZY_JOIN", "1") == "1"
         self.n_wlanes = max(1, int(os.environ.get("GPVB200_WGRAD_LANES", "3")))
         self._rr = 0
@@ -392,7 +411,7 @@ class Engine:
         st.wait_stream(torch.cuda.current_stream())
         self._keep.extend(t for t in keep if t is not None)
         self._dirty.add(lane)
-        return torch.cuda.stream(st)
+        return _Lane(st, self.lane_cta_cap)
 
     def _join_layer(self, *keep):
         """End of a layer / bottleneck of the backward pass: join the lanes, or (lazy) only keep what they still read alive."""

@@ -94,7 +94,8 @@ typedef struct gpvb200_gemm_desc {
   int32_t drop_mode;      /* 0 none */
   uint32_t drop_site;
   float drop_p;
-  int32_t pad_;
+  int32_t max_ctas;       /* > 0: the persistent grid uses at most this many CTAs (a launch that runs on a lane beside a dependent chain
+                           * of kernels leaves the other SMs to the chain); 0: one CTA per SM */
 } gpvb200_gemm_desc;
 
 size_t gpvb200_gemm_desc_size(void);

@@ -47,8 +47,13 @@ def main(path, as_json=False, traffic_out=None):
     if traffic_out:
         g = [r for r in step if "umma_gemm_kernel" in r["name"]]
         gus, gby = sum(r["us"] for r in g), sum(r["rd"] + r["wr"] for r in g)
+        import hashlib
+        import os
+        so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpv-1_b200", "lib", "libgpvb200.so")
+        sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16] if os.path.exists(so) else None
         with open(traffic_out, "w") as f:
-            json.dump({"source": f"{path}: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+            json.dump({"lib_sha16": sha,        # bench.py reports `roofline.traffic` only when this is the library it is running
+                       "source": f"{path}: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
                                  "python bench.py --steps 1 --warmup 1 --profiling --no-graph; last step of the list",
                        "launches_per_step": len(step), "kernel_us_per_step": tot, "dram_bytes_per_step": dram,
                        "gemm_kernel": {"name": "gpv::umma_gemm_kernel<BN,F>", "launches": len(g), "us": gus, "dram_bytes": gby,

@@ -5,8 +5,10 @@
 //
 //   mlp_block_fwd:   y = LN(x + drop(W2 drop_h(relu(W1 x + b1)) + b2))        transformer.py:157-160, 228-231
 //
-// Roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane), warps 2-9 = epilogue
-// (TMEM lane quarter = warp & 3, column half = (warp - 2) >> 2).
+//   attn_block_fwd:  y = LN(x + drop(concat_h softmax(Q_h K_h^T) V_h  Wo^T + bo))   transformer.py:153-157   (second half of this file)
+//
+// Roles (384 threads): warps 0-2 = TMA producers (one elected lane each), warp 3 = tcgen05.mma issuer (one elected lane), warps
+// 4-11 = epilogue / softmax (TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2).
 //
 // mlp_block_fwd pipeline, per 64-wide chunk j of the hidden dimension (d_ff / 64 chunks):
 //   FFN1(j):  acc1[j&1] (TMEM, 64 cols)  = X[128x256] (smem, resident) . W1[64j..64j+63, :]^T        16 MMAs 128x64x16

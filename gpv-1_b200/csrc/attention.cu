@@ -134,16 +134,16 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnParams p) {
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
       const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0, ms1 = (mn1 == -INFINITY) ? 0.f : mn1;
-      const float c0 = exp2f((m0 - ms0) * sl2), c1 = exp2f((m1 - ms1) * sl2);
+      const float c0 = ex2_approx((m0 - ms0) * sl2), c1 = ex2_approx((m1 - ms1) * sl2);
       m0 = mn0;
       m1 = mn1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = exp2f((s[nt][0] - ms0) * sl2);
-        s[nt][1] = exp2f((s[nt][1] - ms0) * sl2);
-        s[nt][2] = exp2f((s[nt][2] - ms1) * sl2);
-        s[nt][3] = exp2f((s[nt][3] - ms1) * sl2);
+        s[nt][0] = ex2_approx((s[nt][0] - ms0) * sl2);
+        s[nt][1] = ex2_approx((s[nt][1] - ms0) * sl2);
+        s[nt][2] = ex2_approx((s[nt][2] - ms1) * sl2);
+        s[nt][3] = ex2_approx((s[nt][3] - ms1) * sl2);
         rs0 += s[nt][0] + s[nt][1];
         rs1 += s[nt][2] + s[nt][3];
       }
@@ -293,8 +293,8 @@ __global__ void __launch_bounds__(NT, (DH <= 32) ? 2 : 1) attn_bwd_kernel(const 
         for (int e = 0; e < 2; ++e) {
           const int col = kb + nt * 8 + 2 * t + e;
           const bool dead = msk[col] != 0;
-          const float p0 = (dead || (p.causal && col > row0)) ? 0.f : exp2f(s[nt][e] * sl2 - ls0);
-          const float p1 = (dead || (p.causal && col > row1)) ? 0.f : exp2f(s[nt][2 + e] * sl2 - ls1);
+          const float p0 = (dead || (p.causal && col > row0)) ? 0.f : ex2_approx(s[nt][e] * sl2 - ls0);
+          const float p1 = (dead || (p.causal && col > row1)) ? 0.f : ex2_approx(s[nt][2 + e] * sl2 - ls1);
           s[nt][e] = p0;
           s[nt][2 + e] = p1;
         }
@@ -373,8 +373,8 @@ __global__ void __launch_bounds__(NT, (DH <= 32) ? 2 : 1) attn_bwd_kernel(const 
         for (int e = 0; e < 2; ++e) {
           const int qc = qb + nt * 8 + 2 * t + e;  // query index (column of S^T)
           const float ls = lse_s[qc], dd = D_s[qc];
-          const float p0 = (dead0 || (p.causal && key0 > qc)) ? 0.f : exp2f(s[nt][e] * sl2 - ls);
-          const float p1 = (dead1 || (p.causal && key1 > qc)) ? 0.f : exp2f(s[nt][2 + e] * sl2 - ls);
+          const float p0 = (dead0 || (p.causal && key0 > qc)) ? 0.f : ex2_approx(s[nt][e] * sl2 - ls);
+          const float p1 = (dead1 || (p.causal && key1 > qc)) ? 0.f : ex2_approx(s[nt][2 + e] * sl2 - ls);
           float m0 = 1.0f, m1 = 1.0f;
           if (drop) {   // element (query qc, key): one half of the pair's 32 bits
             const uint32_t pr = ((uint32_t)bh * (uint32_t)Sq + (uint32_t)qc) * hs;

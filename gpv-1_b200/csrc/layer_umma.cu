@@ -58,6 +58,11 @@ struct MlpParams {
   long long ldy, ldh, ldpre;
   DropArgs drop_h, drop_o;
   long long* trace;     // developer timeline (tools/trace_layer.py): [3 roles][nchunk + 1][8] clock64 stamps of CTA 0, or null
+  // backward variant (mlp_block_bwd): the saved hidden activation gates the hidden gradient, the residual-branch gradient is added
+  const bf16* hmask;    // [M, dff] h of the forward pass (post ReLU / dropout): dh = alpha * acc1 where h > 0
+  const bf16* res;      // [M, 256] gradient of the residual branch, added to the output
+  long long ldhm, ldres;
+  float alpha;
 };
 
 #define LT_STAMP(role, j, slot) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[((role) * (p.nchunk + 1) + (j)) * 8 + (slot)] = clock64(); } while (0)
@@ -67,7 +72,7 @@ GPV_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0
 // byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 64] bf16 SWIZZLE_128B K-major block whose base is 1024-aligned
 GPV_DEVINL uint32_t sw128_off(int r, int c) { return (uint32_t)r * 128u + ((uint32_t)(c ^ (r & 7)) << 4); }
 
-template <bool DROP>
+template <bool DROP, bool BWD>
 __global__ void __launch_bounds__(kLtThreads, 1)
 mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ MlpParams p) {
@@ -242,10 +247,12 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ---- bias / LayerNorm vectors -> shared memory (one cold L2 round trip here instead of one per epilogue step)
     {
       const int t = threadIdx.x - kLtEpiWarp0 * 32;     // 0..255
-      if (t < 64) reinterpret_cast<float4*>(sB2)[t] = __ldg(reinterpret_cast<const float4*>(p.b2) + t);
-      else if (t < 128) reinterpret_cast<float4*>(sGamma)[t - 64] = __ldg(reinterpret_cast<const float4*>(p.gamma) + t - 64);
-      else if (t < 192) reinterpret_cast<float4*>(sBeta)[t - 128] = __ldg(reinterpret_cast<const float4*>(p.beta) + t - 128);
-      for (int i = t; i < p.dff / 4; i += kLtEpiThreads) reinterpret_cast<float4*>(sB1)[i] = __ldg(reinterpret_cast<const float4*>(p.b1) + i);
+      if constexpr (!BWD) {
+        if (t < 64) reinterpret_cast<float4*>(sB2)[t] = __ldg(reinterpret_cast<const float4*>(p.b2) + t);
+        else if (t < 128) reinterpret_cast<float4*>(sGamma)[t - 64] = __ldg(reinterpret_cast<const float4*>(p.gamma) + t - 64);
+        else if (t < 192) reinterpret_cast<float4*>(sBeta)[t - 128] = __ldg(reinterpret_cast<const float4*>(p.beta) + t - 128);
+        for (int i = t; i < p.dff / 4; i += kLtEpiThreads) reinterpret_cast<float4*>(sB1)[i] = __ldg(reinterpret_cast<const float4*>(p.b1) + i);
+      }
     }
     // ---- X tile: shared memory (TMA, SWIZZLE_128B) -> tensor memory, packed bf16 pairs; this warp copies columns
     // [128 half, 128 half + 128) of its 32 rows = TMEM columns [64 half, 64 half + 64)
@@ -272,6 +279,12 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const uint32_t use = (uint32_t)(j >> 1);           // how many times this group's buffers were used before
       const bool tr = e == 0 && lane == 0;
       if (tr) LT_STAMP(2, j, 0);
+      uint4 hm[8];                                       // backward: this row's 64 saved hidden activations of chunk j (in flight during the wait)
+      if constexpr (BWD) {
+        const bf16* hrow = p.hmask + grow * p.ldhm + j * 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hm[i] = r < rows_valid ? ldg_u4(hrow + 8 * i) : make_uint4(0, 0, 0, 0);
+      }
       mbar_wait(&acc1_full[b], use & 1u);
       if (tr) LT_STAMP(2, j, 1);
       tc_fence_after();
@@ -288,6 +301,20 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
+        if constexpr (BWD) {
+          // dh = alpha * (dy W2)  where the forward's h is positive (relu' and, in train mode, the hidden dropout mask in one test)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 hq = hm[hh * 4 + i];
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const float2 hf = unpack_bf16x2(hw[w]);
+              v[8 * i + 2 * w] = hf.x > 0.f ? __uint_as_float(acc[hh][8 * i + 2 * w]) * p.alpha : 0.f;
+              v[8 * i + 2 * w + 1] = hf.y > 0.f ? __uint_as_float(acc[hh][8 * i + 2 * w + 1]) * p.alpha : 0.f;
+            }
+          }
+        } else {
         const float4* b4 = reinterpret_cast<const float4*>(sB1 + nb + hh * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -296,6 +323,7 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           v[4 * i + 1] = fmaxf(__uint_as_float(acc[hh][4 * i + 1]) + bb.y, 0.f);
           v[4 * i + 2] = fmaxf(__uint_as_float(acc[hh][4 * i + 2]) + bb.z, 0.f);
           v[4 * i + 3] = fmaxf(__uint_as_float(acc[hh][4 * i + 3]) + bb.w, 0.f);
+        }
         }
         if (DROP && p.drop_h.seed) {
           const uint32_t base = (uint32_t)grow * (uint32_t)((p.dff + 1) >> 1) + (uint32_t)((nb + hh * 32) >> 1);
@@ -338,6 +366,39 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     uint32_t own[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) own[i] = 16u * slab_slot(lane, i);
+    if constexpr (BWD) {
+      // dx = acc2 + gradient of the residual branch (read from global memory, row-per-thread), one pass, no LayerNorm
+      const bf16* rrow = p.res + grow * p.ldres + half * 128;
+      const bool rv = r < rows_valid;
+      uint32_t acc[2][32];
+      uint4 xr[2][4];
+      tmem_ld_32x32b_x32(t_acc2 + t_lane + (uint32_t)(half * 128), acc[0]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xr[0][i] = rv ? ldg_u4(rrow + 8 * i) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = half * 128 + c * 32;
+        tmem_ld_wait();
+        if (c < 3) {
+          tmem_ld_32x32b_x32(t_acc2 + t_lane + (uint32_t)(col0 + 32), acc[(c + 1) & 1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xr[(c + 1) & 1][i] = rv ? ldg_u4(rrow + (c + 1) * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[c & 1][i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) unpack8(xr[c & 1][i], v + 8 * i, true);
+        const uint32_t sl = slab + 2048u * (uint32_t)(c & 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts128(sl + own[i], pack8(v + 8 * i));
+        __syncwarp();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if ((ok >> jj) & 1u)
+            *reinterpret_cast<uint4*>(p.y + (crow0 + 8 * jj) * p.ldy + col0 + (lane & 3) * 8) = lds128(sl + co + 512u * jj);
+      }
+    } else {
     float sum = 0.f, sq = 0.f;
     {
       uint32_t acc[2][32], xr[2][16];
@@ -433,6 +494,7 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             *reinterpret_cast<uint4*>(p.y + (crow0 + 8 * jj) * p.ldy + col0 + (lane & 3) * 8) = lds128(sl + co + 512u * jj);
       }
     }
+    }   // !BWD
     if (e == 0 && lane == 0) LT_STAMP(2, n, 2);
   }
 
@@ -1071,8 +1133,54 @@ extern "C" int gpvb200_mlp_block_fwd(const void* x, int64_t ldx, const void* w1,
   const int grid = (p.M / p.S) * p.tps;
   const size_t smem = 1024 + kTileBytes + kRingSlots * kSlotBytes + 256 + (768 + (size_t)d_ff) * 4;
   const bool drop = p.drop_h.seed != nullptr || p.drop_o.seed != nullptr;
-  if (drop) return launch_layer(mlp_block_fwd_kernel<true>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
-  return launch_layer(mlp_block_fwd_kernel<false>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
+  if (drop) return launch_layer(mlp_block_fwd_kernel<true, false>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
+  return launch_layer(mlp_block_fwd_kernel<false, false>, "mlp_block_fwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
+}
+
+// Data gradients of the same sub-layer in one launch (the mirror of mlp_block_fwd with the transposed weights as K-major operands):
+//     dh = alpha * (dy W2) (*) [h > 0]          dx = dh W1 + dres
+// dy [M, 256] = gradient of the sub-layer output before the residual add (LayerNorm backward's masked output), w2t = W2^T [d_ff, 256],
+// w1t = W1^T [256, d_ff], h = the forward's hidden activation, dres = gradient of the residual branch.  dh is written for the two
+// weight-gradient GEMMs (dW2 = dy^T h, dW1 = dh^T x), which stay separate launches beside the chain.
+extern "C" int gpvb200_mlp_block_bwd(const void* dy, int64_t lddy, const void* w2t, int64_t ldw2t, const void* w1t, int64_t ldw1t,
+                                     const void* h, int64_t ldh, float alpha, const void* dres, int64_t lddres, void* dh, int64_t lddh,
+                                     void* dx, int64_t lddx, int64_t M, int32_t d_model, int32_t d_ff, int32_t seq_len, void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(dy && w2t && w1t && h && dres && dh && dx, "mlp_block_bwd: null operand");
+  GPV_REQUIRE(d_model == 256, "mlp_block_bwd: d_model must be 256 (got %d)", d_model);
+  GPV_REQUIRE(d_ff >= 64 && d_ff % 64 == 0 && d_ff <= 4096, "mlp_block_bwd: d_ff must be a multiple of 64, <= 4096 (got %d)", d_ff);
+  GPV_REQUIRE(M > 0 && M < (1ll << 31), "mlp_block_bwd: bad M");
+  GPV_REQUIRE((lddh & 7) == 0 && (lddx & 7) == 0 && (ldh & 7) == 0 && (lddres & 7) == 0, "mlp_block_bwd: row strides must be multiples of 8");
+  GPV_REQUIRE((((uintptr_t)dh | (uintptr_t)dx | (uintptr_t)h | (uintptr_t)dres) & 15) == 0, "mlp_block_bwd: buffers must be 16-byte aligned");
+  MlpParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M;
+  p.S = seq_len > 0 ? seq_len : (int)M;
+  GPV_REQUIRE(p.M % p.S == 0, "mlp_block_bwd: M (%d) is not a multiple of seq_len (%d)", p.M, p.S);
+  p.tps = (p.S + 127) / 128;
+  p.dff = d_ff;
+  p.nchunk = d_ff / 64;
+  p.y = (bf16*)dx; p.h = (bf16*)dh;
+  p.ldy = lddx; p.ldh = lddh;
+  p.hmask = (const bf16*)h; p.ldhm = ldh;
+  p.res = (const bf16*)dres; p.ldres = lddres;
+  p.alpha = alpha;
+  p.trace = g_layer_trace;
+  CUtensorMap mx, m1, m2;
+  {
+    const uint32_t one4[4] = {1, 1, 1, 1};
+    const uint64_t dx4[4] = {64, (uint64_t)M, 4, 1}, sx[3] = {(uint64_t)lddy, 64, 256};
+    const uint32_t bx[4] = {64, 128, 4, 1};
+    if ((rc = make_map(&mx, dy, dx4, sx, bx, one4))) return rc;
+    const uint64_t d1[4] = {64, (uint64_t)d_ff, 4, 1}, s1[3] = {(uint64_t)ldw2t, 64, 256};     // W2^T plays W1's role: [d_ff rows, 256]
+    const uint32_t b1x[4] = {64, 64, 4, 1};
+    if ((rc = make_map(&m1, w2t, d1, s1, b1x, one4))) return rc;
+  }
+  if ((rc = map2d(&m2, w1t, (uint64_t)d_ff, 256, (uint64_t)ldw1t, 64, 256))) return rc;          // W1^T plays W2's role: [256 rows, d_ff]
+  const int grid = (p.M / p.S) * p.tps;
+  const size_t smem = 1024 + kTileBytes + kRingSlots * kSlotBytes + 256 + (768 + (size_t)d_ff) * 4;
+  return launch_layer(mlp_block_fwd_kernel<false, true>, "mlp_block_bwd", grid, smem, (cudaStream_t)stream, mx, m1, m2, p);
 }
 
 extern "C" int gpvb200_attn_block_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

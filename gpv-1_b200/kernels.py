@@ -332,6 +332,22 @@ def mlp_block_fwd(x, w1, b1, w2, b2, gamma, beta, eps, *, save=True, seq_len=0, 
     return y, h, pre, stats
 
 
+def mlp_block_bwd(dy, w2t, w1t, h, dres, *, alpha=1.0, seq_len=0):
+    """(dx, dh) of the fused FFN sub-layer: dh = alpha * (dy @ W2) * [h > 0], dx = dh @ W1 + dres.  w2t = W2^T [d_ff, 256], w1t = W1^T
+    [256, d_ff] (bf16, packed transposed copies)."""
+    M, D = dy.shape
+    dff = w2t.shape[0]
+    dev = dy.device
+    dh = torch.empty((M, dff), device=dev, dtype=BF16)
+    dx = torch.empty((M, D), device=dev, dtype=BF16)
+    i64 = ctypes.c_int64
+    _C.check(_C.lib().gpvb200_mlp_block_bwd(_C.ptr(_req(dy, BF16)), i64(dy.stride(0)), _C.ptr(_req(w2t, BF16)), i64(w2t.stride(0)),
+                                            _C.ptr(_req(w1t, BF16)), i64(w1t.stride(0)), _C.ptr(_req(h, BF16)), i64(h.stride(0)),
+                                            ctypes.c_float(alpha), _C.ptr(_req(dres, BF16)), i64(dres.stride(0)), _C.ptr(dh), i64(dff),
+                                            _C.ptr(dx), i64(D), i64(M), D, dff, seq_len, _C.stream_ptr()), "mlp_block_bwd")
+    return dx, dh
+
+
 def attn_block_fwd(q, k, v, *, B, Sq, Sk, scale, key_mask=None, wo=None, bo=None, x=None, gamma=None, beta=None, eps=1e-5,
                    save=True, drop_p=None, drop_o=None, H=8, dh=32):
     """tcgen05 attention for d_model = 256 (8 x 32).  wo None: returns (o, lse).  Otherwise the output projection, residual and

@@ -132,6 +132,9 @@ class Engine:
         self.last_stage = N_STAGES - 1                        # last gradient stage backward() reaches (lower when the tail is frozen)
         self.concurrent = True                                # run independent branches on side streams (lanes)
         self.fused_layers = os.environ.get("GPVB200_FUSED", "1") != "0"   # row-tile-resident sub-layer kernels (layer_umma.cu)
+        # fused FFN data gradients (gpvb200_mlp_block_bwd): parity-green, but inside the step its 75 row tiles lose 0.08 ms against the
+        # two 148-SM GEMMs they replace (profiles/r2z_mlp_block_bwd.txt), so it is opt-in
+        self.fused_bwd = self.fused_layers and os.environ.get("GPVB200_MLP_BWD", "0") == "1"
         self.use_attn_block = self.fused_layers and os.environ.get("GPVB200_ATTN_BLOCK", "1") != "0"   # tcgen05 attention + out-proj + LN
         # lane scheduling (measured in profiles/r2q_lanes.txt: 16.97 -> 16.51 ms per step): the weight-gradient lanes may lag behind the
         # data-gradient chain until the end of a gradient stage instead of being joined after every layer / bottleneck
@@ -156,6 +159,14 @@ class Engine:
             dst = torch.empty((N, K), device=dev, dtype=BF16)
             items.append((t, dst, None, N, K, 1, 0))
             W[key or name] = dst
+
+        def linT(name):
+            """bf16 W^T [K, N] of an nn.Linear weight [N, K] (the pack kernel's tap index walks the input features)."""
+            t = P[name]
+            N, K = t.shape
+            dst = torch.empty((K, N), device=dev, dtype=BF16)
+            items.append((t, dst, None, N, 1, K, 0))
+            W[name + ".T"] = dst
 
         def cat(key, names):
             K = P[names[0] + ".weight"].shape[1]
@@ -208,6 +219,8 @@ class Engine:
             p = f"detr.transformer.encoder.layers.{i}"
             for n in ("self_attn.in_proj_weight", "self_attn.out_proj.weight", "linear1.weight", "linear2.weight"):
                 lin(f"{p}.{n}")
+            linT(f"{p}.linear1.weight")       # K-major operands of the fused FFN backward (gpvb200_mlp_block_bwd)
+            linT(f"{p}.linear2.weight")
         for i in range(self.n_dec):
             p = f"detr.transformer.decoder.layers.{i}"
             for n in ("self_attn.in_proj_weight", "self_attn.out_proj.weight", "multihead_attn.in_proj_weight",
@@ -705,8 +718,14 @@ class Engine:
         dpre, dpre_m = self._ln_bwd(dy, pre, st, Pm[ln + ".weight"], G[ln + ".weight"], G[ln + ".bias"], self._drop(ln + ".in", p_out))
         dh_drop = self._drop(w1 + ".hidden") if act != GELU else None
         # hidden dropout: the saved h is already masked, so relu'(h) (*) mask = [h > 0]; only the 1/(1-p) scale remains
-        dh = self._lin_bwd(w2, h, dpre_m, aux=hpre, aux_mode=GRAD_GELU if act == GELU else MASK_RELU,
-                           alpha=dh_drop.scale if dh_drop is not None else 1.0)
+        alpha = dh_drop.scale if dh_drop is not None else 1.0
+        if act == RELU and x.shape[1] == 256 and self.fused_bwd and x.shape[0] >= 48 * 128 and (w1 + ".weight.T") in self.W:
+            # both data gradients in one tcgen05 launch (the mirror of mlp_block_fwd); the weight / bias gradients follow on the lanes
+            self._lin_bwd(w2, h, dpre_m, need_dx=False)          # (issued first: it does not depend on the fused kernel)
+            dx, dh = k.mlp_block_bwd(dpre_m, self.W[w2 + ".weight.T"], self.W[w1 + ".weight.T"], h, dpre, alpha=alpha)
+            self._lin_bwd(w1, x, dh, need_dx=False)
+            return dx
+        dh = self._lin_bwd(w2, h, dpre_m, aux=hpre, aux_mode=GRAD_GELU if act == GELU else MASK_RELU, alpha=alpha)
         return self._lin_bwd(w1, x, dh, residual=dpre)
 
     # ================================================================================================ BERT (no grad)

@@ -182,6 +182,15 @@ int gpvb200_mlp_block_fwd(const void* x, int64_t ldx, const void* w1, int64_t ld
                           int32_t seq_len, const void* drop_seed, uint32_t site_h, float p_h, uint32_t site_o, float p_o,
                           void* stream);
 
+/* Data gradients of the same sub-layer in one launch: dh = alpha * (dy W2) (*) [h > 0];  dx = dh W1 + dres  (autograd of
+ * transformer.py:157-160 between the LayerNorm backward and the weight gradients).  dy [M, 256] bf16 (row stride lddy), w2t = W2^T
+ * [d_ff, 256] and w1t = W1^T [256, d_ff] bf16 (the transposed weights, so both contractions read K-major operands), h [M, d_ff] the
+ * forward's hidden activation (post ReLU / dropout: its sign is relu' and the dropout mask at once; alpha = 1 / (1 - p_hidden)), dres
+ * [M, 256] the gradient of the residual branch.  Writes dh [M, d_ff] (for dW2 = dy^T h, dW1 = dh^T x) and dx [M, 256]. */
+int gpvb200_mlp_block_bwd(const void* dy, int64_t lddy, const void* w2t, int64_t ldw2t, const void* w1t, int64_t ldw1t, const void* h,
+                          int64_t ldh, float alpha, const void* dres, int64_t lddres, void* dh, int64_t lddh, void* dx, int64_t lddx,
+                          int64_t M, int32_t d_model, int32_t d_ff, int32_t seq_len, void* stream);
+
 /* Multi-head attention for d_model = 256 (8 heads x 32) on tcgen05, optionally with the output projection, residual and LayerNorm
  * in the same kernel: o = concat_h softmax(scale Q_h K_h^T + key mask) V_h;  y = LayerNorm(x + drop_o(o Wo^T + bo)).
  * nn.MultiheadAttention core + out_proj + dropout + residual + norm of TransformerEncoderLayer.forward_post transformer.py:153-157

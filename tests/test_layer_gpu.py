@@ -88,6 +88,28 @@ def test_mlp_block_fwd_dropout(cuda):
     assert (h != h0).float().mean().item() < 1e-3 and _rel(h, h0) < 1e-3
 
 
+@pytest.mark.parametrize("M,seq,alpha", [(9600, 0, 1.0), (300, 0, 1.0 / 0.9), (640, 320, 1.0), (130, 0, 1.0)])
+def test_mlp_block_bwd(cuda, M, seq, alpha):
+    """dh = alpha (dy W2) (*) [h > 0], dx = dh W1 + dres in one launch, against the torch composition (dh rounded to bf16 in between, as
+    the kernel hands it to the second contraction)."""
+    from gpv1_b200 import kernels as k
+    g = torch.Generator(device="cpu").manual_seed(M)
+    r = lambda *s_: torch.randn(*s_, generator=g).to(cuda)
+    dff = 2048
+    dy, dres = (0.1 * r(M, 256)).to(BF), (0.1 * r(M, 256)).to(BF)
+    w1, w2 = (r(dff, 256) / 16).to(BF), (r(256, dff) / 45).to(BF)
+    h = torch.relu(r(M, dff)).to(BF)
+    h[:, 5] = 0
+    dx, dh = k.mlp_block_bwd(dy, w2.t().contiguous(), w1.t().contiguous(), h, dres, alpha=alpha, seq_len=seq)
+    torch.cuda.synchronize()
+    rdh = alpha * (dy.float() @ w2.float()) * (h.float() > 0)
+    rdx = rdh.to(BF).float() @ w1.float() + dres.float()
+    e_h, e_x = _rel(dh, rdh), _rel(dx, rdx)
+    print("mlp_block_bwd", (M, seq), f"dh {e_h:.2e} dx {e_x:.2e}")
+    assert e_h < 4e-3 and e_x < 4e-3, (e_h, e_x)
+    assert dh.float()[h.float() == 0].abs().max().item() == 0
+
+
 # ---------------------------------------------------------------------------------------------------- attention block
 def _attn_inputs(cuda, B, Sq, Sk, seed, self_attn):
     g = torch.Generator(device="cpu").manual_seed(seed)

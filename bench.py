@@ -762,7 +762,7 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)"
     step_roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "what": f"whole step as one unit: {gf_all:.1f} algorithmic GFLOP/sample fwd+bwd ({gf_fwd:.1f} fwd) x {B} samples / step "
-                             "time (graph replay); traffic = {traffic_src}; peak = {peak_src}"}
+                             f"time (graph replay); traffic = {traffic_src}; peak = {peak_src}"}
     roofline = step_roofline
     attention = None
     if gemm_trace is not None:

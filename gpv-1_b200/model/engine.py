@@ -614,9 +614,10 @@ class Engine:
                     k.linear_wgrad(dqkv[:, 2 * D:], x, gw[2 * D:])
         if not has_pos:
             return k.linear_dgrad(dqkv, wi, residual=dpre)
-        dx = k.linear_dgrad(dqkv[:, 2 * D:], wi[2 * D:], residual=dpre)
         if pos_grad is None:
-            return k.linear_dgrad(dqkv[:, :2 * D], wi[:2 * D], residual=dx)
+            # fixed (sine) position: d(x + pos)/dx = I, so the q / k path and the v path share ONE data-gradient GEMM over K = 3 D
+            return k.linear_dgrad(dqkv, wi, residual=dpre)
+        dx = k.linear_dgrad(dqkv[:, 2 * D:], wi[2 * D:], residual=dpre)
         dqk_in = k.linear_dgrad(dqkv[:, :2 * D], wi[:2 * D])
         k.batch_reduce(dqk_in, pos_grad, B, S)
         return k.add(dx, dqk_in, out=dx)

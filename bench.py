@@ -571,6 +571,7 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    note("e2e (fp32 sync) done")
     clocks = sampler.stop() if rank == 0 else None
     loss_val = step_e2e()
 
@@ -589,6 +590,7 @@ def main():
     for _ in range(2):
         step_full()
     ms_full = timed(step_full, args.steps)
+    note("full step done")
 
     # e2e with the input staged one step ahead (gpv1_b200.data.DevicePrefetcher): every step still moves one
     # batch of pinned host pixels to the device inside the timed region, but on a copy stream, under the previous step
@@ -648,6 +650,7 @@ def main():
         for _ in range(2):
             step_e2e_u8_pf()
         ms_e2e_u8_pf = timed(step_e2e_u8_pf, args.steps)
+        note("e2e uint8 + prefetch done")
 
     # DDP check on hardware: after a step every rank must hold the same (averaged) gradient arena
     grads_equal = None
@@ -659,6 +662,7 @@ def main():
         allsig = [torch.empty_like(sig) for _ in range(world)]
         dist.all_gather(allsig, sig)
         grads_equal = all(torch.equal(a, allsig[0]) for a in allsig) and bool(torch.isfinite(sig).all()) and sig[1].item() > 0
+        note(f"gradient check across ranks: {grads_equal}")
 
     # BASELINE configs[2]: the multitask stream (answer length varies per step) on the same replicas, resident and end to end
     multitask_line = None
@@ -674,6 +678,7 @@ def main():
                 seen.add(b[2].shape[1])
                 model.capture_step(*b, add=True)
         mturn = [0]
+        note(f"multitask: captured answer lengths {sorted(seen)}")
 
         def step_mt():
             mturn[0] += 1
@@ -693,6 +698,7 @@ def main():
         for _ in range(2):
             step_mt_e2e()
         ms_mt_e2e = timed(step_mt_e2e, args.steps)
+        note("multitask done")
         multitask_line = {"workload": workload_name(B, "multitask"), "value": world * B * args.steps / (ms_mt / 1e3), "unit": "samples/s",
                           "ms_per_step": ms_mt / args.steps, "answer_lengths": sorted(seen),
                           "e2e": {"value": world * B * args.steps / (ms_mt_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_mt_e2e / args.steps,

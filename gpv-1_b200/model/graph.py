@@ -31,10 +31,18 @@ class CapturedStep:
         eng.refresh()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):                       # first-call work (smem attributes, tensor maps, position table)
-                eng.forward_train(self.images, self.qids, self.ans, tgt)
-                eng.backward()
+        # the warm-up steps are rank-local: no gradient all-reduce.  (A capture must not contain collectives that other ranks may not
+        # issue: in a multitask stream each rank captures one step per answer length IT sees, so the number of captures differs
+        # between ranks and warm-up all-reduces would pair up wrongly and dead-lock.)
+        warm_hooks = (eng.on_stage_done, eng.on_backward_end)
+        eng.on_stage_done = eng.on_backward_end = None
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):                   # first-call work (smem attributes, tensor maps, position table)
+                    eng.forward_train(self.images, self.qids, self.ans, tgt)
+                    eng.backward()
+        finally:
+            eng.on_stage_done, eng.on_backward_end = warm_hooks
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from .. import _C
@@ -56,6 +64,7 @@ class CapturedStep:
         self.sync = model.grad_sync if (model.grad_sync is not None and model.grad_sync.world > 1) else None
         hooks = (eng.on_stage_done, eng.on_backward_end)
         self.g_bwd = []
+        self.g_stage = []                   # gradient stage at which each backward graph ends (where its bucket is reduced)
         cap_stream = torch.cuda.Stream(device=dev, priority=prio)
         cap_stream.wait_stream(torch.cuda.current_stream())
         torch.cuda.synchronize()
@@ -68,8 +77,9 @@ class CapturedStep:
                 open_capture = [True]
 
                 def split(stage):
-                    if self.sync is None:
+                    if self.sync is None or not self.sync.reduces_at(stage):
                         return
+                    self.g_stage.append(stage)
                     self.g_bwd[-1].capture_end()
                     if stage == eng.last_stage:           # nothing is launched after the last stage backward reaches: no empty trailing graph
                         open_capture[0] = False
@@ -116,8 +126,8 @@ class CapturedStep:
         if self.sync is None:
             self.g_bwd[0].replay()
             return
-        # graph i ends where gradient stage i is complete
-        for i, g in enumerate(self.g_bwd):
+        # graph i ends where gradient stage g_stage[i] is complete: its bucket is reduced while the next graph runs
+        for g, st in zip(self.g_bwd, self.g_stage):
             g.replay()
-            self.sync.stage_done(i)
+            self.sync.stage_done(st)
         self.sync.finish()

@@ -3,6 +3,8 @@ all-reduce per backward stage over contiguous prefixes of the gradient arena) mu
 import os
 import sys
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -18,6 +20,7 @@ class _FakeEngine:
         self.stage_end = stage_end
         self.on_stage_done = None
         self.on_backward_end = None
+        self.last_stage = len(stage_end) - 1              # Engine.backward lowers it when the tail of the model is frozen
 
 
 def _worker(rank, world, port, out):
@@ -58,6 +61,7 @@ def _frozen_worker(rank, world, port, out):
     from gpv1_b200.parallel import GradSync
     ends = [8, 8, 24, 40, 48, 56, 64]
     eng = _FakeEngine(64, ends)
+    eng.last_stage = 2
     sync = GradSync()
     sync.attach(eng)
     torch.manual_seed(10 + rank)
@@ -81,16 +85,21 @@ def _frozen_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_gradsync_frozen_tail_gloo_world2(tmp_path):
+@pytest.mark.parametrize("schedule", ["3,4,5,6", "all"])
+def test_gradsync_frozen_tail_gloo_world2(tmp_path, monkeypatch, schedule):
+    """Both bucket schedules (the default merged one and one bucket per stage, GPVB200_DDP_REDUCE_AT)."""
+    monkeypatch.setenv("GPVB200_DDP_REDUCE_AT", schedule)
     out = str(tmp_path / "res.txt")
-    port = 29700 + os.getpid() % 250
+    port = 29700 + (os.getpid() + len(schedule)) % 250
     mp.spawn(_frozen_worker, args=(2, port, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
 
 
-def test_gradsync_gloo_world2(tmp_path):
+@pytest.mark.parametrize("schedule", ["3,4,5,6", "all"])
+def test_gradsync_gloo_world2(tmp_path, monkeypatch, schedule):
+    monkeypatch.setenv("GPVB200_DDP_REDUCE_AT", schedule)
     out = str(tmp_path / "res.txt")
-    port = 29500 + os.getpid() % 1000
+    port = 29500 + (os.getpid() + len(schedule)) % 1000
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
 

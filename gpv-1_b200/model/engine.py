@@ -1020,25 +1020,28 @@ class Engine:
         B, Q, D = s["B"], self.Q, self.D
         M = B * Q
         S = ans_ids.shape[1]
-        logits_v, sv_txt = self.decode_text(ans_ids.reshape(-1), s["memory"], B, S, s["Tm"], save=True)
-        # ---- criterion
+        # ---- criterion.  The localisation branch (matcher cost -> assignment -> set criterion: a serial chain of ~75 us that needs only
+        # the relevance logits and boxes) runs on a lane beside the text decoder; the answer cross-entropy follows the decoder.
         loss_terms = torch.zeros(4, device=self.dev, dtype=F32)        # [answer CE (weighted), loss_ce, loss_bbox, loss_giou]
-        dlogits_v = torch.empty((B * S, self.Vp), device=self.dev, dtype=BF16)
-        if self.Vp != self.V:
-            dlogits_v.zero_()
-        k.ce_fwd_bwd(logits_v[:, :self.V], tgt.ce_targets, tgt.ce_row_weight, loss_terms[0:1], dlogits_v[:, :self.V])
         dlg = torch.zeros((M, 8), device=self.dev, dtype=F32)
         dbox = torch.zeros((M, 8), device=self.dev, dtype=BF16)
         idx_q = idx_t = None
         if tgt.n_loc > 0:
-            lg3, bx3 = s["logits"].view(B, Q, 8), s["boxes"].view(B, Q, 8)
-            if tgt.Tmax > 0:
-                cost = k.matcher_cost(lg3, bx3, tgt.boxes, tgt.labels, tgt.offsets, tgt.Tmax, *self.cost_w, C=2)
-                idx_q, idx_t = k.lsap(cost, tgt.offsets)
-            k.set_criterion(s["logits"], s["boxes"], tgt.boxes, tgt.offsets, idx_q, idx_t, tgt.loc_valid, eos_coef=self.eos_coef,
-                            weight_sum=tgt.weight_sum, num_boxes=tgt.num_boxes, wt_ce=self.loss_wts["loss_ce"],
-                            wt_bbox=self.loss_wts["loss_bbox"], wt_giou=self.loss_wts["loss_giou"], out3=loss_terms[1:4], dlogits=dlg,
-                            dbox_pre=dbox)
+            with self._aside(loss_terms, dlg, dbox, s["logits"], s["boxes"], lane=4):
+                lg3, bx3 = s["logits"].view(B, Q, 8), s["boxes"].view(B, Q, 8)
+                if tgt.Tmax > 0:
+                    cost = k.matcher_cost(lg3, bx3, tgt.boxes, tgt.labels, tgt.offsets, tgt.Tmax, *self.cost_w, C=2)
+                    idx_q, idx_t = k.lsap(cost, tgt.offsets)
+                k.set_criterion(s["logits"], s["boxes"], tgt.boxes, tgt.offsets, idx_q, idx_t, tgt.loc_valid, eos_coef=self.eos_coef,
+                                weight_sum=tgt.weight_sum, num_boxes=tgt.num_boxes, wt_ce=self.loss_wts["loss_ce"],
+                                wt_bbox=self.loss_wts["loss_bbox"], wt_giou=self.loss_wts["loss_giou"], out3=loss_terms[1:4], dlogits=dlg,
+                                dbox_pre=dbox)
+        logits_v, sv_txt = self.decode_text(ans_ids.reshape(-1), s["memory"], B, S, s["Tm"], save=True)
+        dlogits_v = torch.empty((B * S, self.Vp), device=self.dev, dtype=BF16)
+        if self.Vp != self.V:
+            dlogits_v.zero_()
+        k.ce_fwd_bwd(logits_v[:, :self.V], tgt.ce_targets, tgt.ce_row_weight, loss_terms[0:1], dlogits_v[:, :self.V])
+        self._join(4)
         loss = (loss_terms * (self._wts_loc if tgt.n_loc else self._wts_noloc)).sum().reshape(1)
         # (n_loc > 0 always holds for a captured step: the set criterion then yields zeros when no image has boxes)
         s.update(S_ans=S, sv_txt=sv_txt, dlogits_v=dlogits_v, dlg=dlg, dbox=dbox, loss_terms=loss_terms, idx_q=idx_q, idx_t=idx_t)

@@ -344,8 +344,9 @@ def torch_eager_gpu(B, dev, steps=3):
 
 def measure_decode(model, dev, reps=5, K=5):
     """BASELINE configs[0] (one 480x640 image + a 6-token query, greedy, latency) and configs[3] (beam_size = 5, batch = 64,
-    inference only) through the public API (GPV.forward / GPV.forward_beam_search), inputs in pinned host memory, generated
-    token ids read back to the host inside the timed region; whole-call CUDA graph (model.inference_graphs)."""
+    inference only) through the public API (GPV.forward / GPV.forward_beam_search), inputs (uint8 NHWC pixels, token ids) in pinned
+    host memory, generated token ids / answers read back to the host inside the timed region; whole-call CUDA graph
+    (model.inference_graphs)."""
     was_training, graphs = model.training, model.inference_graphs
     model.eval()
     model.inference_graphs = True
@@ -354,8 +355,10 @@ def measure_decode(model, dev, reps=5, K=5):
     try:
         with torch.no_grad():
             for key, B in (("configs[0] greedy, 1 image", 1), ("configs[3] beam_size=5, batch=64", 64)):
-                images, qids, _, _ = make_batch(B, seed=4)
-                images, qids = images.pin_memory(), (qids[:, :6] if B == 1 else qids).contiguous().pin_memory()
+                _, qids, _, _ = make_batch(B, seed=4)
+                g8 = torch.Generator().manual_seed(40 + B)       # the loader's raw format: uint8 NHWC pixels (normalisation fused into the stem)
+                images = torch.randint(0, 256, (B, H_IMG, W_IMG, 3), generator=g8, dtype=torch.uint8).pin_memory()
+                qids = (qids[:, :6] if B == 1 else qids).contiguous().pin_memory()
                 if B == 1:
                     fn = lambda: model(images.to(dev, non_blocking=True), qids.to(dev, non_blocking=True), None)["answer_logits"].argmax(-1).cpu()
                 else:
@@ -372,7 +375,7 @@ def measure_decode(model, dev, reps=5, K=5):
                 ms = e0.elapsed_time(e1) / reps
                 toks = B * (L if B == 1 else K * (L - 1))
                 out[key] = {"ms_per_call": ms, "samples_per_s": B / ms * 1e3, "decoded_tokens_per_s": toks / ms * 1e3, "max_text_len": L,
-                            "h2d_bytes_per_call": images.numel() * 4 + qids.numel() * 8}
+                            "h2d_bytes_per_call": images.numel() + qids.numel() * 8}
     finally:
         model.inference_graphs = graphs
         model._inf_graphs.clear()

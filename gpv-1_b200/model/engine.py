@@ -951,13 +951,14 @@ class Engine:
                 kv = kv.view(B, 1, Tm, 2 * D).expand(B, rep, Tm, 2 * D).reshape(Bp * Tm, 2 * D)
             kv_mem.append(kv)
         wc = k.linear(W["answer_head.vocab_embed"], W["answer_head.classifier_transform.weight"], Pm["answer_head.classifier_transform.bias"])
-        mk = lambda: [torch.empty((Bp, max_len, D), device=self.dev, dtype=BF16) for _ in range(self.n_txt)]
-        return {"Bp": Bp, "Tm": Tm, "L": max_len, "t": 0, "kv_mem": kv_mem, "wc": wc, "kc": mk(), "vc": mk()}
+        # one cache [Bp, max_len, 3 D] per layer: the packed q | k | v projection of position t is written in place by ONE GEMM
+        qkvc = [torch.empty((Bp, max_len, 3 * D), device=self.dev, dtype=BF16) for _ in range(self.n_txt)]
+        return {"Bp": Bp, "Tm": Tm, "L": max_len, "t": 0, "kv_mem": kv_mem, "wc": wc, "qkvc": qkvc}
 
     @torch.no_grad()
     def decode_step(self, st, tok_ids):
         """tok_ids [Bp] int64 = the token at position st['t'] of every hypothesis -> logits fp32 [Bp, Vp] of the next
-        position.  One query row per hypothesis: 13 launches per layer on [Bp, D] activations."""
+        position.  One query row per hypothesis: 11 launches per layer on [Bp, D] activations."""
         W, Pm, D, H = self.W, self.P, self.D, self.h_txt
         Bp, Tm, L, t = st["Bp"], st["Tm"], st["L"], st["t"]
         assert t < L, "decode_step past max_len"
@@ -968,12 +969,11 @@ class Engine:
         for i in range(self.n_txt):
             p = f"text_decoder.layers.{i}"
             wi, bi_ = W[f"{p}.self_attn.in_proj_weight"], Pm[f"{p}.self_attn.in_proj_bias"]
-            kc, vc = st["kc"][i], st["vc"][i]
-            q = k.linear(x, wi[:D], bi_[:D])
-            k.linear(x, wi[D:2 * D], bi_[D:2 * D], out=kc[:, t])          # appended in place: row stride L*D
-            k.linear(x, wi[2 * D:], bi_[2 * D:], out=vc[:, t])
-            o, _ = k.attention_fwd(q, kc.view(Bp * L, D), vc.view(Bp * L, D), B=Bp, H=H, Sq=1, Sk=t + 1, dh=dh, scale=sc,
-                                   need_lse=False, bs_k=L * D, bs_v=L * D)
+            c = st["qkvc"][i]
+            k.linear(x, wi, bi_, out=c[:, t])                             # q | k | v of position t appended in place: row stride L * 3 D
+            c2 = c.view(Bp * L, 3 * D)
+            o, _ = k.attention_fwd(c[:, t, :D], c2[:, D:2 * D], c2[:, 2 * D:], B=Bp, H=H, Sq=1, Sk=t + 1, dh=dh, scale=sc,
+                                   need_lse=False, bs_k=L * 3 * D, bs_v=L * 3 * D)
             pre = k.linear(o, W[f"{p}.self_attn.out_proj.weight"], Pm[f"{p}.self_attn.out_proj.bias"], residual=x)
             x, _ = k.layernorm_fwd(pre, Pm[f"{p}.norm1.weight"], Pm[f"{p}.norm1.bias"], 1e-5, need_stats=False)
             wi, bi_ = W[f"{p}.multihead_attn.in_proj_weight"], Pm[f"{p}.multihead_attn.in_proj_bias"]
@@ -994,14 +994,12 @@ class Engine:
     @torch.no_grad()
     def decode_reorder(self, st, parent):
         """Beam search: hypothesis r continues hypothesis parent[r] (int64 [Bp]) -> permute the self-attention caches."""
-        n = st["t"] * self.D                                   # only the positions decoded so far move
-        if "kc_alt" not in st:
-            st["kc_alt"] = [torch.empty_like(c) for c in st["kc"]]
-            st["vc_alt"] = [torch.empty_like(c) for c in st["vc"]]
-        for a, b in (("kc", "kc_alt"), ("vc", "vc_alt")):
-            for src, dst in zip(st[a], st[b]):
-                k.reorder_rows(src, dst, parent, n)
-            st[a], st[b] = st[b], st[a]
+        n = st["t"] * 3 * self.D                               # only the positions decoded so far move
+        if "qkvc_alt" not in st:
+            st["qkvc_alt"] = [torch.empty_like(c) for c in st["qkvc"]]
+        for src, dst in zip(st["qkvc"], st["qkvc_alt"]):
+            k.reorder_rows(src, dst, parent, n)
+        st["qkvc"], st["qkvc_alt"] = st["qkvc_alt"], st["qkvc"]
 
     # ================================================================================================ training step
     @torch.no_grad()

@@ -1,8 +1,8 @@
 // Decode-loop bookkeeping on the device (exp/gpv/models/gpv.py:178-196 greedy, 256-362 beam search): the arg-max over
 // the vocabulary with the additive vocab mask, one beam-search update (log-softmax, per-beam top-K, candidate merge
 // with the reference's order and tie rule, sequence / score / parent update) and the permutation of the KV caches by
-// the parent index.  HBM/L2-bound row scans: one CTA per row (arg-max) or per image (beam update), float4 loads,
-// warp-shuffle reductions.
+// the parent index, and the single-query attention of the KV-cached decode step.  HBM/L2-bound row scans: one CTA per row (arg-max,
+// beam candidates), per image (beam merge) or per (K/V batch, head) (decode attention); warp-shuffle reductions.
 #include "../../include/gpvb200.h"
 #include "common.cuh"
 #include "host_util.h"
@@ -87,73 +87,80 @@ __global__ void __launch_bounds__(kDecThreads) argmax_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// One beam-search step for image b (one CTA): for each live beam k1 the log-softmax of its next-token logits and its K
-// best tokens (value descending, lower token id first on ties); candidates cand[k1][k2] = score[k1] + logp (at t = 0
-// only beam 0 is live: the others hold the same prefix, gpv.py:283-286); the K best of the K*K candidates in stable
-// descending order (first occurrence in (k1 major, k2 minor) order wins ties, as torch.sort(stable=True) in the
-// reference's restatement); then ids_out[b, k, :t+1] = ids_in[b, k1, :t+1], ids_out[b, k, t+1] = token,
-// score_out[b, k] = candidate, parent[b K + k] = b K + k1, tok[b K + k] = token.
+// One beam-search step in two launches.
+// beam_rows_kernel (one CTA per hypothesis row b K + k1): the log-softmax of the row's next-token logits and its K best tokens
+// (value descending, lower token id first on ties); candidates cand[k1][k2] = score[k1] + logp go to the workspace (at t = 0 only
+// hypothesis 0 of an image is live: the others hold the same prefix, gpv.py:283-286, and get -1e9).
+// beam_merge_kernel (one CTA per image): the K best of the K*K candidates in stable descending order (first occurrence in (k1 major, k2
+// minor) order wins ties, as torch.sort(stable=True) in the reference's restatement); then ids_out[b, k, :t+1] = ids_in[b, k1, :t+1],
+// ids_out[b, k, t+1] = token, score_out[b, k] = candidate, parent[b K + k] = b K + k1, tok[b K + k] = token.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kDecThreads) beam_update_kernel(const float* __restrict__ logits, long long ld, int K, int V, int t,
-                                                                  int L, const float* __restrict__ score_in,
-                                                                  const int64_t* __restrict__ ids_in, float* __restrict__ score_out,
-                                                                  int64_t* __restrict__ ids_out, int64_t* __restrict__ parent,
-                                                                  int64_t* __restrict__ tok) {
+__global__ void __launch_bounds__(kDecThreads) beam_rows_kernel(const float* __restrict__ logits, long long ld, int K, int V, int t,
+                                                                const float* __restrict__ score_in, float* __restrict__ cand_v,
+                                                                int* __restrict__ cand_tok) {
   pdl_sync();
   __shared__ float red_v[16];
   __shared__ int red_i[16];
+  const int row = blockIdx.x, k1 = row % K;
+  if (t == 0 && k1 > 0) {
+    if (threadIdx.x < K) {
+      cand_v[(long long)row * K + threadIdx.x] = -1e9f;
+      cand_tok[(long long)row * K + threadIdx.x] = 0;
+    }
+    return;
+  }
+  const float* lr = logits + (long long)row * ld;
+  Best m;
+  m.v = -INFINITY;
+  m.i = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += kDecThreads) {
+    const float v = lr[i];
+    if (better(v, i, m.v, m.i)) {
+      m.v = v;
+      m.i = i;
+    }
+  }
+  m = block_best(m, red_v, red_i);
+  const float mx = m.v;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += kDecThreads) s += expf(lr[i] - mx);
+  s = block_sum(s, red_v);
+  const float logsum = logf(s);
+  const float sc = score_in[row];
+  Best prev = m;                                   // the best token is the row maximum found above
+  for (int k2 = 0; k2 < K; ++k2) {
+    if (k2 > 0) {
+      Best c;
+      c.v = -INFINITY;
+      c.i = 0x7fffffff;
+      for (int i = threadIdx.x; i < V; i += kDecThreads) {
+        const float v = lr[i];
+        const bool after = v < prev.v || (v == prev.v && i > prev.i);      // strictly after the previous pick in the order
+        if (after && better(v, i, c.v, c.i)) {
+          c.v = v;
+          c.i = i;
+        }
+      }
+      prev = block_best(c, red_v, red_i);
+    }
+    if (threadIdx.x == 0) {
+      cand_v[(long long)row * K + k2] = sc + ((prev.v - mx) - logsum);          // log_softmax = (x - max) - log(sum exp(x - max))
+      cand_tok[(long long)row * K + k2] = prev.i == 0x7fffffff ? 0 : prev.i;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) beam_merge_kernel(int K, int t, int L, const float* __restrict__ cand_v_g, const int* __restrict__ cand_tok_g,
+                                                         const int64_t* __restrict__ ids_in, float* __restrict__ score_out,
+                                                         int64_t* __restrict__ ids_out, int64_t* __restrict__ parent, int64_t* __restrict__ tok) {
+  pdl_sync();
   __shared__ float cand_v[kMaxBeams * kMaxBeams];
   __shared__ int cand_tok[kMaxBeams * kMaxBeams];
   __shared__ int sel_k1[kMaxBeams];
   const int b = blockIdx.x;
-  const int live = t == 0 ? 1 : K;
-  for (int k1 = 0; k1 < K; ++k1) {
-    if (k1 >= live) {
-      if (threadIdx.x < K) {
-        cand_v[k1 * K + threadIdx.x] = -1e9f;
-        cand_tok[k1 * K + threadIdx.x] = 0;
-      }
-      continue;
-    }
-    const float* lr = logits + ((long long)b * K + k1) * ld;
-    Best m;
-    m.v = -INFINITY;
-    m.i = 0x7fffffff;
-    for (int i = threadIdx.x; i < V; i += kDecThreads) {
-      const float v = lr[i];
-      if (better(v, i, m.v, m.i)) {
-        m.v = v;
-        m.i = i;
-      }
-    }
-    m = block_best(m, red_v, red_i);
-    const float mx = m.v;
-    float s = 0.f;
-    for (int i = threadIdx.x; i < V; i += kDecThreads) s += expf(lr[i] - mx);
-    s = block_sum(s, red_v);
-    const float logsum = logf(s);
-    const float sc = score_in[b * K + k1];
-    Best prev = m;                                   // the best token is the row maximum found above
-    for (int k2 = 0; k2 < K; ++k2) {
-      if (k2 > 0) {
-        Best c;
-        c.v = -INFINITY;
-        c.i = 0x7fffffff;
-        for (int i = threadIdx.x; i < V; i += kDecThreads) {
-          const float v = lr[i];
-          const bool after = v < prev.v || (v == prev.v && i > prev.i);      // strictly after the previous pick in the order
-          if (after && better(v, i, c.v, c.i)) {
-            c.v = v;
-            c.i = i;
-          }
-        }
-        prev = block_best(c, red_v, red_i);
-      }
-      if (threadIdx.x == 0) {
-        cand_v[k1 * K + k2] = sc + ((prev.v - mx) - logsum);          // log_softmax = (x - max) - log(sum exp(x - max))
-        cand_tok[k1 * K + k2] = prev.i == 0x7fffffff ? 0 : prev.i;
-      }
-    }
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+    cand_v[i] = cand_v_g[(long long)b * K * K + i];
+    cand_tok[i] = cand_tok_g[(long long)b * K * K + i];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -183,9 +190,80 @@ __global__ void __launch_bounds__(kDecThreads) beam_update_kernel(const float* _
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * (t + 1); i += kDecThreads) {
+  for (int i = threadIdx.x; i < K * (t + 1); i += blockDim.x) {
     const int k = i / (t + 1), j = i % (t + 1);
     ids_out[((long long)b * K + k) * L + j] = ids_in[((long long)b * K + sel_k1[k]) * L + j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention of ONE query row per hypothesis against cached keys / values (the KV-cached decode step, gpv.py:178-196 / 318-326).  One CTA
+// per (K/V batch, head): K and V of the head are staged in shared memory ONCE and serve every hypothesis that shares them (`rep`
+// hypotheses per K/V batch: the beams of an image attend to the same encoder memory; rep = 1 for the self-attention caches).  K is
+// staged transposed as bf16 pairs (a lane owns keys lane, lane + 32, ...: conflict-free), V row-major (a lane owns output dimensions).
+// HBM/L2-bound: K and V of a step are read once per (batch, head) instead of once per hypothesis by a 16-row MMA tile.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kk, long long ldk,
+                                                          long long bsk, const bf16* __restrict__ vv, long long ldv, long long bsv,
+                                                          bf16* __restrict__ o, long long ldo, int H, int Sk, int dh, int rep, float sl2) {
+  pdl_sync();
+  extern __shared__ __align__(16) uint8_t smem_dec[];
+  const int kvb = blockIdx.x / H, h = blockIdx.x % H;
+  const int Skp = Sk | 1;                                  // odd word stride of the transposed K rows
+  const int dh2 = dh >> 1;
+  uint32_t* Kt = reinterpret_cast<uint32_t*>(smem_dec);   // [dh / 2][Skp] bf16 pairs (d, d + 1) of key s
+  bf16* Vs = reinterpret_cast<bf16*>(Kt + (size_t)dh2 * Skp);   // [Sk][dh]
+  float* prob = reinterpret_cast<float*>(Vs + (size_t)Sk * dh);   // [4 warps][Sk]
+  float* qs = prob + 4 * Sk;                                  // [4 warps][dh]
+  const int CH = dh >> 3;
+  const bf16* kb = kk + (long long)kvb * bsk + h * dh;
+  const bf16* vb = vv + (long long)kvb * bsv + h * dh;
+  for (int i = threadIdx.x; i < Sk * CH; i += blockDim.x) {
+    const int s = i / CH, c = i % CH;
+    const uint4 kq = *reinterpret_cast<const uint4*>(kb + (long long)s * ldk + c * 8);
+    Kt[(c * 4 + 0) * Skp + s] = kq.x;
+    Kt[(c * 4 + 1) * Skp + s] = kq.y;
+    Kt[(c * 4 + 2) * Skp + s] = kq.z;
+    Kt[(c * 4 + 3) * Skp + s] = kq.w;
+    *reinterpret_cast<uint4*>(Vs + (size_t)s * dh + c * 8) = *reinterpret_cast<const uint4*>(vb + (long long)s * ldv + c * 8);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pw = prob + warp * Sk;
+  float* qw = qs + warp * dh;
+  for (int r = warp; r < rep; r += 4) {
+    const long long row = (long long)kvb * rep + r;
+    const bf16* qr = q + row * ldq + h * dh;
+    for (int d = lane; d < dh; d += 32) qw[d] = __bfloat162float(qr[d]);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int s = lane; s < Sk; s += 32) {
+      float acc = 0.f;
+      for (int d2 = 0; d2 < dh2; ++d2) {
+        const float2 kf = unpack_bf16x2(Kt[d2 * Skp + s]);
+        acc = fmaf(qw[2 * d2], kf.x, acc);
+        acc = fmaf(qw[2 * d2 + 1], kf.y, acc);
+      }
+      acc *= sl2;                                           // log2 domain
+      pw[s] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < Sk; s += 32) {
+      const float e = ex2_approx(pw[s] - mx);
+      pw[s] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    for (int d = lane; d < dh; d += 32) {
+      float acc = 0.f;
+      for (int s = 0; s < Sk; ++s) acc = fmaf(pw[s], __bfloat162float(Vs[(size_t)s * dh + d]), acc);
+      o[row * ldo + h * dh + d] = __float2bfloat16(acc * inv);
+    }
+    __syncwarp();
   }
 }
 
@@ -218,17 +296,51 @@ extern "C" int gpvb200_argmax(const float* logits, int64_t ld, int32_t rows, int
 
 extern "C" int gpvb200_beam_update(const float* logits, int64_t ld, int32_t B, int32_t K, int32_t V, int32_t t, int32_t L,
                                    const float* score_in, const int64_t* ids_in, float* score_out, int64_t* ids_out, int64_t* parent,
-                                   int64_t* tok, void* stream) {
+                                   int64_t* tok, void* workspace, void* stream) {
   int rc = ensure_arch();
   if (rc != GPV_OK) return rc;
-  GPV_REQUIRE(logits && score_in && ids_in && score_out && ids_out && parent && tok, "beam_update: null pointer");
+  GPV_REQUIRE(logits && score_in && ids_in && score_out && ids_out && parent && tok && workspace, "beam_update: null pointer");
   GPV_REQUIRE(B >= 0 && K >= 1 && K <= kMaxBeams && V >= K && t >= 0 && t + 1 < L, "beam_update: needs 1 <= K <= %d <= V and t + 1 < L (K %d, V %d, t %d, L %d)",
               kMaxBeams, K, V, t, L);
   GPV_REQUIRE(ids_in != ids_out && score_in != score_out, "beam_update: in-place update is not supported (double-buffer ids and scores)");
+  GPV_REQUIRE(((uintptr_t)workspace & 7) == 0, "beam_update: workspace must be 8-byte aligned");
   if (B == 0) return GPV_OK;
-  launch_k(beam_update_kernel, dim3(B), dim3(kDecThreads), 0, (cudaStream_t)stream, logits, (long long)ld, K, V, t, L, score_in, ids_in, score_out,
+  float* cand_v = (float*)workspace;                       // [B, K, K] candidate scores, then [B, K, K] candidate tokens
+  int* cand_tok = (int*)(cand_v + (size_t)B * K * K);
+  launch_k(beam_rows_kernel, dim3(B * K), dim3(kDecThreads), 0, (cudaStream_t)stream, logits, (long long)ld, K, V, t, score_in, cand_v, cand_tok);
+  rc = check_launch("beam_rows_kernel");
+  if (rc != GPV_OK) return rc;
+  launch_k(beam_merge_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, K, t, L, (const float*)cand_v, (const int*)cand_tok, ids_in, score_out,
            ids_out, parent, tok);
-  return check_launch("beam_update_kernel");
+  return check_launch("beam_merge_kernel");
+}
+
+extern "C" int gpvb200_decode_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t bsk, const void* v, int64_t ldv,
+                                        int64_t bsv, void* o, int64_t ldo, int32_t Bq, int32_t rep, int32_t H, int32_t Sk, int32_t dh,
+                                        float scale, void* stream) {
+  int rc = ensure_arch();
+  if (rc != GPV_OK) return rc;
+  GPV_REQUIRE(q && k && v && o, "decode_attention: null operand");
+  GPV_REQUIRE(Bq >= 0 && rep >= 1 && Bq % rep == 0 && H >= 1 && Sk >= 1, "decode_attention: needs Bq %% rep == 0 (Bq %d, rep %d), H, Sk >= 1", Bq, rep);
+  GPV_REQUIRE(dh >= 8 && dh <= 256 && dh % 8 == 0, "decode_attention: head dim %d must be a multiple of 8, <= 256", dh);
+  GPV_REQUIRE((ldk & 7) == 0 && (ldv & 7) == 0 && (bsk & 7) == 0 && (bsv & 7) == 0 && (((uintptr_t)k | (uintptr_t)v) & 15) == 0,
+              "decode_attention: K / V rows must be 16-byte aligned");
+  if (Bq == 0) return GPV_OK;
+  const size_t smem = (size_t)(dh / 2) * (Sk | 1) * 4 + (size_t)Sk * dh * 2 + (size_t)4 * Sk * 4 + (size_t)4 * dh * 4 + 16;
+  GPV_REQUIRE(smem <= 200 * 1024, "decode_attention: Sk = %d, dh = %d needs %zu bytes of shared memory (> 200 KB)", Sk, dh, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_last_error("decode_attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return GPV_ERR_CUDA;
+    }
+    configured = smem;
+  }
+  launch_k(decode_attn_kernel, dim3((Bq / rep) * H), dim3(128), smem, (cudaStream_t)stream, (const bf16*)q, (long long)ldq, (const bf16*)k,
+           (long long)ldk, (long long)bsk, (const bf16*)v, (long long)ldv, (long long)bsv, (bf16*)o, (long long)ldo, H, Sk, dh, rep,
+           scale * 1.4426950408889634f);
+  return check_launch("decode_attn_kernel");
 }
 
 extern "C" int gpvb200_reorder_rows(const void* src, void* dst, const int64_t* parent, int32_t rows, int64_t row_elems, int64_t n_elems,

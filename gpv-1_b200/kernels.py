@@ -387,13 +387,29 @@ def argmax(logits, V, *, vocab_mask=None, out=None):
     return ids
 
 
-def beam_update(logits, V, t, score_in, ids_in, score_out, ids_out, parent, tok):
-    """One beam-search step (see gpvb200_beam_update): ids_* [B, K, L] int64, score_* [B, K] fp32, parent / tok [B*K] int64."""
+def beam_update(logits, V, t, score_in, ids_in, score_out, ids_out, parent, tok, workspace=None):
+    """One beam-search step (see gpvb200_beam_update): ids_* [B, K, L] int64, score_* [B, K] fp32, parent / tok [B*K] int64;
+    workspace: int64 tensor of >= B*K*K elements (allocated here when None)."""
     B, K, L = ids_in.shape
+    if workspace is None:
+        workspace = torch.empty((B * K * K,), device=logits.device, dtype=torch.int64)
+    assert workspace.numel() * 8 >= 8 * B * K * K
     _C.check(_C.lib().gpvb200_beam_update(_C.ptr(_req(logits, torch.float32)), ctypes.c_int64(logits.stride(0)), B, K, V, t, L,
                                           _C.ptr(_req(score_in, torch.float32)), _C.ptr(_req(ids_in, torch.int64)),
                                           _C.ptr(_req(score_out, torch.float32)), _C.ptr(_req(ids_out, torch.int64)),
-                                          _C.ptr(_req(parent, torch.int64)), _C.ptr(_req(tok, torch.int64)), _C.stream_ptr()), "beam_update")
+                                          _C.ptr(_req(parent, torch.int64)), _C.ptr(_req(tok, torch.int64)), _C.ptr(_req(workspace, torch.int64)),
+                                          _C.stream_ptr()), "beam_update")
+
+
+def decode_attention(q, k, v, *, Bq, rep, H, Sk, dh, scale, bs_k, bs_v, out=None):
+    """One query row per hypothesis against cached K / V (see gpvb200_decode_attention).  q [Bq, >= H*dh]; k / v: 2-D views whose row
+    stride is the key stride, bs_k / bs_v the batch strides (elements); rep hypotheses share one K / V batch."""
+    o = out if out is not None else torch.empty((Bq, H * dh), device=q.device, dtype=BF16)
+    i64 = ctypes.c_int64
+    _C.check(_C.lib().gpvb200_decode_attention(_C.ptr(_req(q, BF16)), i64(q.stride(0)), _C.ptr(_req(k, BF16)), i64(k.stride(0)), i64(bs_k),
+                                               _C.ptr(_req(v, BF16)), i64(v.stride(0)), i64(bs_v), _C.ptr(o), i64(o.stride(0)), Bq, rep, H, Sk, dh,
+                                               ctypes.c_float(scale), _C.stream_ptr()), "decode_attention")
+    return o
 
 
 def reorder_rows(src, dst, parent, n_elems):

@@ -946,14 +946,11 @@ class Engine:
         Bp = B * rep
         kv_mem = []
         for i in range(self.n_txt):
-            kv = self._cross_kv(f"text_decoder.layers.{i}", memory, memory)
-            if rep > 1:
-                kv = kv.view(B, 1, Tm, 2 * D).expand(B, rep, Tm, 2 * D).reshape(Bp * Tm, 2 * D)
-            kv_mem.append(kv)
+            kv_mem.append(self._cross_kv(f"text_decoder.layers.{i}", memory, memory))     # [B*Tm, 2D]: shared by the rep hypotheses of an image
         wc = k.linear(W["answer_head.vocab_embed"], W["answer_head.classifier_transform.weight"], Pm["answer_head.classifier_transform.bias"])
         # one cache [Bp, max_len, 3 D] per layer: the packed q | k | v projection of position t is written in place by ONE GEMM
         qkvc = [torch.empty((Bp, max_len, 3 * D), device=self.dev, dtype=BF16) for _ in range(self.n_txt)]
-        return {"Bp": Bp, "Tm": Tm, "L": max_len, "t": 0, "kv_mem": kv_mem, "wc": wc, "qkvc": qkvc}
+        return {"Bp": Bp, "rep": rep, "Tm": Tm, "L": max_len, "t": 0, "kv_mem": kv_mem, "wc": wc, "qkvc": qkvc}
 
     @torch.no_grad()
     def decode_step(self, st, tok_ids):
@@ -972,14 +969,16 @@ class Engine:
             c = st["qkvc"][i]
             k.linear(x, wi, bi_, out=c[:, t])                             # q | k | v of position t appended in place: row stride L * 3 D
             c2 = c.view(Bp * L, 3 * D)
-            o, _ = k.attention_fwd(c[:, t, :D], c2[:, D:2 * D], c2[:, 2 * D:], B=Bp, H=H, Sq=1, Sk=t + 1, dh=dh, scale=sc,
-                                   need_lse=False, bs_k=L * 3 * D, bs_v=L * 3 * D)
+            # one query row per hypothesis against its own cache: gpvb200_decode_attention (K / V staged once per (hypothesis, head))
+            o = k.decode_attention(c[:, t, :D], c2[:, D:2 * D], c2[:, 2 * D:], Bq=Bp, rep=1, H=H, Sk=t + 1, dh=dh, scale=sc,
+                                   bs_k=L * 3 * D, bs_v=L * 3 * D)
             pre = k.linear(o, W[f"{p}.self_attn.out_proj.weight"], Pm[f"{p}.self_attn.out_proj.bias"], residual=x)
             x, _ = k.layernorm_fwd(pre, Pm[f"{p}.norm1.weight"], Pm[f"{p}.norm1.bias"], 1e-5, need_stats=False)
             wi, bi_ = W[f"{p}.multihead_attn.in_proj_weight"], Pm[f"{p}.multihead_attn.in_proj_bias"]
             q = k.linear(x, wi[:D], bi_[:D])
             kv = st["kv_mem"][i]
-            o, _ = k.attention_fwd(q, kv[:, :D], kv[:, D:], B=Bp, H=H, Sq=1, Sk=Tm, dh=dh, scale=sc, need_lse=False)
+            # the beams of an image share the encoder memory's K / V: staged once per (image, head) for all of them
+            o = k.decode_attention(q, kv[:, :D], kv[:, D:], Bq=Bp, rep=st["rep"], H=H, Sk=Tm, dh=dh, scale=sc, bs_k=Tm * 2 * D, bs_v=Tm * 2 * D)
             pre = k.linear(o, W[f"{p}.multihead_attn.out_proj.weight"], Pm[f"{p}.multihead_attn.out_proj.bias"], residual=x)
             x, _ = k.layernorm_fwd(pre, Pm[f"{p}.norm2.weight"], Pm[f"{p}.norm2.bias"], 1e-5, need_stats=False)
             h = k.linear(x, W[f"{p}.linear1.weight"], Pm[f"{p}.linear1.bias"], act=RELU)

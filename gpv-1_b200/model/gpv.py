@@ -571,11 +571,12 @@ class GPV(nn.Module):
         ids = [torch.full((B, K, L), self.word_to_idx["__cls__"], dtype=torch.int64, device=dev) for _ in range(2)]
         score = [torch.zeros((B, K), device=dev), torch.zeros((B, K), device=dev)]
         parent = torch.empty((B * K,), dtype=torch.int64, device=dev)
+        work = torch.empty((B * K * K,), dtype=torch.int64, device=dev)       # candidates between the two launches of a beam update
         tok = [ids[0][:, :, 0].reshape(-1).contiguous(), torch.empty((B * K,), dtype=torch.int64, device=dev)]
         for t in range(L - 1):
             lg = eng.decode_step(st, tok[t & 1])
-            # log-softmax, per-hypothesis top-K, candidate merge, sequence / score / parent update: one launch (gpvb200_beam_update)
-            k.beam_update(lg, eng.V, t, score[t & 1], ids[t & 1], score[(t + 1) & 1], ids[(t + 1) & 1], parent, tok[(t + 1) & 1])
+            # log-softmax, per-hypothesis top-K, candidate merge, sequence / score / parent update: gpvb200_beam_update (two launches)
+            k.beam_update(lg, eng.V, t, score[t & 1], ids[t & 1], score[(t + 1) & 1], ids[(t + 1) & 1], parent, tok[(t + 1) & 1], work)
             if t < L - 2:
                 eng.decode_reorder(st, parent)
         return ids[(L - 1) & 1][:, :, 1:], score[(L - 1) & 1]

@@ -301,9 +301,18 @@ int gpvb200_argmax(const float* logits, int64_t ld, int32_t rows, int32_t V, con
  * best candidates in stable descending order (first occurrence wins ties); at t = 0 only hypothesis 0 of each image is
  * live.  Writes score_out [B, K], ids_out [B, K, L] (ids_out[b, k, :t+1] = ids_in[b, k1, :t+1], ids_out[b, k, t+1] =
  * the new token), parent [B*K] = b K + k1 (the row whose KV cache hypothesis (b, k) continues) and tok [B*K] = the new
- * token.  K <= 8; ids / scores are double-buffered by the caller (no in-place update). */
+ * token.  K <= 8; ids / scores are double-buffered by the caller (no in-place update); workspace: >= 8 B K K bytes of device memory,
+ * 8-byte aligned (candidate scores and tokens between the per-row and the per-image launch). */
 int gpvb200_beam_update(const float* logits, int64_t ld, int32_t B, int32_t K, int32_t V, int32_t t, int32_t L, const float* score_in,
-                        const int64_t* ids_in, float* score_out, int64_t* ids_out, int64_t* parent, int64_t* tok, void* stream);
+                        const int64_t* ids_in, float* score_out, int64_t* ids_out, int64_t* parent, int64_t* tok, void* workspace,
+                        void* stream);
+/* Attention of ONE query row per hypothesis against cached keys / values: the self- and cross-attention cores of a KV-cached decode step
+ * (nn.TransformerDecoderLayer inside GPV.decode_text, gpv.py:449-466, called with a one-token query).  q [Bq, >= H*dh] bf16 (row stride
+ * ldq); hypothesis r reads the K / V batch r / rep (rep hypotheses share one batch: the beams of an image attend to the same encoder
+ * memory; rep = 1 for per-hypothesis caches): key s of batch b at k + b*bsk + s*ldk, Sk keys; o [Bq, H*dh] bf16.  K and V of a
+ * (batch, head) are staged on chip once and serve its rep hypotheses. */
+int gpvb200_decode_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t bsk, const void* v, int64_t ldv, int64_t bsv,
+                             void* o, int64_t ldo, int32_t Bq, int32_t rep, int32_t H, int32_t Sk, int32_t dh, float scale, void* stream);
 /* KV-cache permutation after a beam step (gpv.py:318-326 re-decodes the re-ordered prefixes; the cached K/V follow the
  * hypotheses instead): dst[r, :n_elems] = src[parent[r], :n_elems] for `rows` rows of row_elems bf16. */
 int gpvb200_reorder_rows(const void* src, void* dst, const int64_t* parent, int32_t rows, int64_t row_elems, int64_t n_elems,

@@ -103,3 +103,32 @@ def test_reorder_rows(cuda):
     k.reorder_rows(src, dst, parent, t * D)
     assert torch.equal(dst[:, :t], src.index_select(0, parent)[:, :t])
     assert (dst[:, t:] == 7.0).all()                                 # positions not decoded yet are not touched
+
+
+@pytest.mark.parametrize("B,rep,H,Sk,dh,L", [(64, 5, 8, 120, 96, 0), (320, 1, 8, 7, 96, 20), (3, 2, 12, 33, 64, 0), (1, 1, 8, 1, 96, 20), (2, 3, 16, 20, 48, 0)])
+def test_decode_attention(cuda, B, rep, H, Sk, dh, L):
+    """One query row per hypothesis against cached K / V, `rep` hypotheses sharing a K / V batch (the beams of an image) or per-hypothesis
+    caches read in place with a batch stride (L > 0: cache [Bq, L, 3 D], keys 0..Sk-1), against torch."""
+    from gpv1_b200 import kernels as k
+    torch.manual_seed(B * 7 + rep)
+    D = H * dh
+    Bq = B if rep == 1 else B * rep
+    nb = Bq // rep
+    q = torch.randn(Bq, D, device=cuda).to(torch.bfloat16)
+    if L:
+        cache = torch.randn(nb, L, 3 * D, device=cuda).to(torch.bfloat16)
+        c2 = cache.view(nb * L, 3 * D)
+        kk, vv, bs = c2[:, D:2 * D], c2[:, 2 * D:], L * 3 * D
+        kf, vf = cache[:, :Sk, D:2 * D].float(), cache[:, :Sk, 2 * D:].float()
+    else:
+        kv = torch.randn(nb * Sk, 2 * D, device=cuda).to(torch.bfloat16)
+        kk, vv, bs = kv[:, :D], kv[:, D:], Sk * 2 * D
+        kf, vf = kv[:, :D].float().view(nb, Sk, D), kv[:, D:].float().view(nb, Sk, D)
+    scale = dh ** -0.5
+    o = k.decode_attention(q, kk, vv, Bq=Bq, rep=rep, H=H, Sk=Sk, dh=dh, scale=scale, bs_k=bs, bs_v=bs)
+    qh = q.float().view(nb, rep, H, dh)
+    kh, vh = kf.view(nb, Sk, H, dh), vf.view(nb, Sk, H, dh)
+    sc = torch.einsum("brhd,bshd->brhs", qh, kh) * scale
+    ref = torch.einsum("brhs,bshd->brhd", sc.softmax(-1), vh).reshape(Bq, D)
+    err = ((o.float() - ref).norm() / ref.norm()).item()
+    assert err < 5e-3, err

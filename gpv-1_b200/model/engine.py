@@ -315,6 +315,7 @@ class Engine:
         self.stage_end[-1] = total
         self.on_stage_done = None                             # parallel.py: callable(stage) fired as backward finishes a stage
         self.on_backward_end = None                           # parallel.py: joins the all-reduce stream (inside a graph capture too)
+        self.stage_joins = None                               # parallel.py: callable(stage) -> does a bucket end (and get reduced) after this stage?
         self.grad_arena = torch.zeros(total, device=self.dev, dtype=F32)
         self.G = {n: self.grad_arena[offs[n]:offs[n] + math.prod(byname[n].shape)].view(byname[n].shape) for n in order}
         self.live_names = order
@@ -339,7 +340,11 @@ class Engine:
 
     # ================================================================================================ small helpers
     def _done(self, stage):
-        self._join()
+        # the lanes are joined where a gradient bucket is handed to the all-reduce (a hook is attached) and where backward ends;
+        # without a hook (one GPU) intermediate stage boundaries do not make the data-gradient chain wait for the lanes
+        hook_joins = self.on_stage_done is not None and (self.stage_joins is None or self.stage_joins(stage))
+        if hook_joins or stage >= self.last_stage or not self.lazy_join:
+            self._join()
         if self.on_stage_done is not None:
             self.on_stage_done(stage)
 
@@ -425,6 +430,18 @@ class Engine:
         self._keep.extend(t for t in keep if t is not None)
         self._dirty.add(lane)
         return _Lane(st, self.lane_cta_cap)
+
+    def _aside_after_lanes(self, lane):
+        """A lane whose work also follows everything issued on the other lanes so far (not only the issuing stream)."""
+        if not (self.concurrent and self.lazy_join and self.dev.type == "cuda"):
+            self._join()
+            return contextlib.nullcontext()
+        ctx = self._aside(lane=lane)
+        st = self._lanes[lane]
+        for ln in list(self._dirty):
+            if ln != lane:
+                st.wait_stream(self._lanes[ln])
+        return ctx
 
     def _join_layer(self, *keep):
         """End of a layer / bottleneck of the backward pass: join the lanes, or (lazy) only keep what they still read alive."""
@@ -552,10 +569,12 @@ class Engine:
             saved, acts[idx] = acts[idx], None
             dpre = self._bottleneck_bwd(blk, dpre, saved, need_dx=idx > 0)
             if bi == 0:                                        # first block of layer `li` was the last one to finish
-                self._join()                                   # the packed 3x3 weight gradients are written on the lanes
-                for name, c, _ in self._g3:
-                    if f".layer{li}." in name:
-                        k.unpack_conv_grad(self.Gp[name], self.G[name])
+                # the packed 3x3 weight gradients are written on the lanes: they are unpacked on a lane that waits for those lanes, so
+                # the data-gradient chain itself never waits (_done() joins where a bucket is reduced or backward ends)
+                with self._aside_after_lanes(5):
+                    for name, c, _ in self._g3:
+                        if f".layer{li}." in name:
+                            k.unpack_conv_grad(self.Gp[name], self.G[name])
                 self._done({4: 4, 3: 5, 2: 6}[li])
 
     # ================================================================================================ attention blocks

@@ -40,6 +40,7 @@ class GradSync:
         self.engine = engine
         engine.on_stage_done = self.stage_done
         engine.on_backward_end = self.finish
+        engine.stage_joins = self.reduces_at                   # the engine joins its lanes only where a bucket ends
         self.cuda = engine.grad_arena.is_cuda
         self.stream = torch.cuda.Stream(device=engine.grad_arena.device) if self.cuda else None
         self.bytes_per_step = engine.grad_arena.numel() * 4

@@ -30,12 +30,35 @@
 
 namespace gpv {
 
+// Division by a run-time constant as multiply-high + shift (dividend < 2^31).  Every role of the persistent kernel decodes every work
+// item; with plain `/` and `%` that was ~600-800 clocks of dependent arithmetic per item and role (clock64 timeline,
+// profiles/r4a_trace_gemm.txt) -- more than the whole main loop of a 128 x 64 x 64 item.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+GPV_DEVINL int fdiv(int n, const FastDiv& f) { return f.d == 1u ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)(d < 1 ? 1 : d);
+  f.mul = 0;
+  f.shr = 0;
+  if (f.d > 1) {
+    int l = 0;
+    while ((1ull << l) < f.d) ++l;                       // smallest l with 2^l >= d
+    const int p = 31 + l;
+    f.mul = (uint32_t)(((1ull << p) + f.d - 1) / f.d);   // ceil(2^p / d) fits 32 bits because 2^(l-1) < d
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+
 struct KParams {
   int mode, M, N, a_mn, b_mn, bk, k_iters, splits, nstages, b_batched;
   int m_tiles, n_tiles, gy, total_work, k_per_split;
   int m_tiles_cta;  // 128-row tiles of the problem; m_tiles counts work-item rows (pairs of tiles in the pair variant)
   int kblk, kb_total;  // 64-deep k-blocks per pipeline stage of a K-major operand (1; 2 in the pair variant) and in the whole contraction
   int kc_per_tap;
+  FastDiv fd_nt, fd_mt, fd_gy, fd_tpi, fd_tws, fd_tw, fd_kc;   // n_tiles, m_tiles, gy, tiles_h * tiles_w, tiles_w, tw, kc_per_tap
   int Ho, Wo, th, tw, tiles_h, tiles_w, stride;
   int ntaps;
   int tap_dh[9], tap_dw[9], tap_w[9];
@@ -66,6 +89,14 @@ constexpr int kProducers = 3;
 constexpr int kMmaWarp = kProducers;
 constexpr int kEpiWarp0 = kProducers + 1;
 constexpr int kThreads = 32 * (kProducers + 1 + kEpiWarps);
+// Narrow tiles (BN = 64) move 24 KB per stage in two small boxes and are bound by the issue side, not by bandwidth: three producer
+// warps deliver one stage per ~850 clocks (28 B/clk per SM; profiles/r4a_trace_gemm.txt) against 128 clocks of MMA.  Their kernels
+// are launched with four more producer warps behind the epilogue warps (warps 12-15; 512 threads still leave 128 registers each).
+constexpr int kExtraProducers = 4;
+template <int BN>
+constexpr int kProdWarps = BN == 64 ? kProducers + kExtraProducers : kProducers;
+template <int BN>
+constexpr int kThreadsBN = kThreads + (BN == 64 ? 32 * kExtraProducers : 0);
 constexpr int BM = 128;
 constexpr int kChunk = 32;  // accumulator columns per epilogue step
 
@@ -73,14 +104,42 @@ struct Work {
   int nt, mt, bz, it0, it1;
 };
 
+// Developer timeline (tools/trace_gemm.py builds a second library with -DGPV_GEMM_TRACE; the shipped library carries none of this):
+// clock64 stamps of CTA 0, [6 roles][kTraceN uses][8 slots] -- roles 0-2 producer warps (index = stage use), 3 MMA issuer, 4 / 5 the
+// first / last epilogue warp (index = work item).
+#ifdef GPV_GEMM_TRACE
+constexpr int kTraceN = 96;
+__device__ long long* g_gemm_trace = nullptr;
+#define GT_STAMP(role, idx, slot)                                                                      \
+  do {                                                                                                 \
+    if (gt_buf != nullptr && (idx) < kTraceN) gt_buf[((role) * kTraceN + (idx)) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define GT_STAMP(role, idx, slot) do { } while (0)
+#endif
+
+// Position in the stage ring, advanced once per stage use (no `%` / `/` by the run-time stage count in the loops).
+struct Ring {
+  int s;         // stage slot, gi % nstages
+  uint32_t ph;   // (gi / nstages) & 1
+  int turn;      // gi % nprod: the producer warp this stage use belongs to
+};
+GPV_DEVINL void ring_next(Ring& r, int S, int nprod) {
+  if (++r.s == S) {
+    r.s = 0;
+    r.ph ^= 1u;
+  }
+  if (++r.turn == nprod) r.turn = 0;
+}
+
 GPV_DEVINL Work decode_work(const KParams& p, int w) {
   Work k;
-  k.nt = w % p.n_tiles;
-  int r = w / p.n_tiles;
-  k.mt = r % p.m_tiles;
-  r /= p.m_tiles;
-  k.bz = r % p.gy;
-  const int sp = r / p.gy;
+  const int q1 = fdiv(w, p.fd_nt);
+  k.nt = w - q1 * p.n_tiles;
+  const int q2 = fdiv(q1, p.fd_mt);
+  k.mt = q1 - q2 * p.m_tiles;
+  const int sp = fdiv(q2, p.fd_gy);
+  k.bz = q2 - sp * p.gy;
   k.it0 = sp * p.k_per_split;
   k.it1 = min(k.it0 + p.k_per_split, p.k_iters);
   return k;
@@ -102,10 +161,10 @@ GPV_DEVINL Work decode_work(const KParams& p, int w) {
 // Global row (pixel) index of tile row r of work item wk, and whether it exists.
 GPV_DEVINL bool tile_row(const KParams& p, const Work& wk, int r, long long* pix) {
   if (p.mode == 1) {
-    const int tpi = p.tiles_h * p.tiles_w;
-    const int img = wk.mt / tpi;
-    const int rr_ = wk.mt % tpi;
-    const int ho = (rr_ / p.tiles_w) * p.th + r / p.tw, wo = (rr_ % p.tiles_w) * p.tw + r % p.tw;
+    const int img = fdiv(wk.mt, p.fd_tpi);
+    const int rr_ = wk.mt - img * (p.tiles_h * p.tiles_w);
+    const int trow = fdiv(rr_, p.fd_tws), prow = fdiv(r, p.fd_tw);
+    const int ho = trow * p.th + prow, wo = (rr_ - trow * p.tiles_w) * p.tw + (r - prow * p.tw);
     *pix = ((long long)img * p.OH + (ho * p.os + p.ooh)) * p.OW + (wo * p.os + p.oow);
     return (r < p.th * p.tw) && ho < p.Ho && wo < p.Wo;
   }
@@ -330,7 +389,7 @@ GPV_DEVINL void epi_chunk_coal(const KParams& p, const uint32_t (&acc)[kChunk], 
 // 128 x BN output tile of one batch/tap and one K split).  Two TMEM accumulator buffers let the epilogue of item j
 // overlap the TMA/MMA main loop of item j+1.
 template <int BN, int F, bool PAIR = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsBN<BN>, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -392,18 +451,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // are released at once -- their own prologue then overlaps this kernel's work.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef GPV_GEMM_TRACE
+  long long* const gt_buf = blockIdx.x == 0 ? g_gemm_trace : nullptr;   // read once: a stamp is one clock read and one store
+#endif
 
-  if (warp < kProducers) {
-    // ================================================================== TMA producers (stage gi belongs to warp gi % kProducers)
+  if (warp < kProducers || warp >= kEpiWarp0 + kEpiWarps) {
+    // ================================================================== TMA producers (stage gi belongs to producer gi % nprod)
+    const int pw = warp < kProducers ? warp : warp - (kEpiWarp0 + kEpiWarps) + kProducers;   // producer index (BN = 64: 0..6)
     // Lane 0 issues the TMA loads; before that, all 32 lanes L2-prefetch the residual / aux rows the epilogue of this
     // work item will read (the producer runs 2+ tiles ahead of the epilogue, so they are L2 hits by then).
     const bool pf_r = p.pf_mode && p.coal && p.residual != nullptr, pf_a = p.pf_mode && p.coal && p.aux_mode != GPVB200_AUX_NONE;
     int gi = 0;  // stage-use counter, runs across work items
+    Ring rg = {0, 0u, 0};
     for (int w = first_work; w < p.total_work; w += work_step) {
       Work wk = decode_work(p, w);
       if constexpr (PAIR) wk.mt = 2 * wk.mt + rank;   // may be one past the last tile: TMA zero-fills, the epilogue skips it
       const int n0 = wk.nt * BN + rank * BNC, m0 = wk.mt * BM, bz = wk.bz;
-      if ((pf_r || pf_a) && warp == 0) {
+      if ((pf_r || pf_a) && pw == 0) {
         const uint32_t bytes = (uint32_t)(min(BN, p.N - n0) * 2) & ~15u;
         const long long row_off = (long long)bz * p.d_batch_stride + n0;
         if (bytes > 0) {
@@ -417,20 +481,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if (elect_one()) {
+      const bool elected = elect_one();
+      if (elected) {
         int img = 0, ho0 = 0, wo0 = 0;
         if (p.mode == 1) {
-          const int tpi = p.tiles_h * p.tiles_w;
-          img = wk.mt / tpi;
-          const int r = wk.mt % tpi;
-          ho0 = (r / p.tiles_w) * p.th;
-          wo0 = (r % p.tiles_w) * p.tw;
+          img = fdiv(wk.mt, p.fd_tpi);
+          const int r = wk.mt - img * (p.tiles_h * p.tiles_w);
+          const int trow = fdiv(r, p.fd_tws);
+          ho0 = trow * p.th;
+          wo0 = (r - trow * p.tiles_w) * p.tw;
         }
-        for (int it = wk.it0; it < wk.it1; ++it, ++gi) {
-          if (gi % p.nprod != warp) continue;
-          const int s = gi % S;
-          const uint32_t ph = (uint32_t)(gi / S) & 1u;
+        for (int it = wk.it0; it < wk.it1; ++it, ++gi, ring_next(rg, S, p.nprod)) {
+          if (rg.turn != pw) continue;
+          const int s = rg.s;
+          const uint32_t ph = rg.ph;
           mbar_wait(&empty_bar[s], ph ^ 1u);
+          GT_STAMP(0, gi, 0);
+          GT_STAMP(0, gi, 2 + (pw & 3));
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           if constexpr (PAIR) {
@@ -487,7 +554,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, k0, bzB, 0);
             }
           } else if (p.mode == 1) {
-            const int tap = it / p.kc_per_tap, kc = it % p.kc_per_tap;
+            const int tap = fdiv(it, p.fd_kc), kc = it - tap * p.kc_per_tap;
             tma_load_4d(sa, &tmA, &full_bar[s], kc * 64, wo0 * p.stride + p.tap_dw[tap], ho0 * p.stride + p.tap_dh[tap], img);
             if (!p.b_mn) {
               tma_load_4d(sb, &tmB, &full_bar[s], kc * 64, n0, p.tap_w[tap], 0);
@@ -497,9 +564,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, kc * 64, p.tap_w[tap], 0);
             }
           } else {
-            const int tpi = p.tiles_h * p.tiles_w;
-            const int im = it / tpi, r = it % tpi;
-            const int h0 = (r / p.tiles_w) * p.th, w0 = (r % p.tiles_w) * p.tw;
+            const int im = fdiv(it, p.fd_tpi), r = it - im * (p.tiles_h * p.tiles_w);
+            const int trow = fdiv(r, p.fd_tws);
+            const int h0 = trow * p.th, w0 = (r - trow * p.tiles_w) * p.tw;
             tma_load_4d(sa, &tmA, &full_bar[s], m0, w0, h0, im);
             tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, w0, h0, im);
             const int wi = w0 * p.stride + p.tap_dw[bz], hi = h0 * p.stride + p.tap_dh[bz];
@@ -507,11 +574,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < BN / 64; ++j)
               tma_load_4d(sb + j * p.bk * 128, &tmB, &full_bar[s], n0 + 64 * j, wi, hi, im);
           }
+          GT_STAMP(0, gi, 1);
         }
       } else {
         gi += wk.it1 - wk.it0;
       }
       __syncwarp();
+      {   // the ring position travels from the lane that walked the stages to the others (any lane may be elected next time)
+        const int src = __ffs(__ballot_sync(0xffffffffu, elected)) - 1;
+        const uint32_t packed = __shfl_sync(0xffffffffu, (uint32_t)rg.s | (rg.ph << 8) | ((uint32_t)rg.turn << 16), src);
+        rg.s = (int)(packed & 0xffu);
+        rg.ph = (packed >> 8) & 1u;
+        rg.turn = (int)(packed >> 16);
+      }
     }
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer
@@ -522,17 +597,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
     const int ksteps = p.bk / 16;
     int gi = 0, j = 0;
+    Ring rg = {0, 0u, 0};
     for (int w = first_work; w < p.total_work && (!PAIR || rank == 0); w += work_step, ++j) {
       const Work wk = decode_work(p, w);
       const int buf = j & 1;
+      if (lane == 0) GT_STAMP(3, j, 0);
       mbar_wait(&acc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
+      if (lane == 0) GT_STAMP(3, j, 1);
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-      for (int it = wk.it0; it < wk.it1; ++it, ++gi) {
-        const int s = gi % S;
-        const uint32_t ph = (uint32_t)(gi / S) & 1u;
+      for (int it = wk.it0; it < wk.it1; ++it, ++gi, ring_next(rg, S, 1)) {
+        const int s = rg.s;
+        const uint32_t ph = rg.ph;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (lane == 0 && it == wk.it0) GT_STAMP(3, j, 2);
+        if (lane == 0 && it == wk.it1 - 1) GT_STAMP(3, j, 3);
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
@@ -562,6 +642,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         __syncwarp();
+        if (lane == 0 && it == wk.it1 - 1) GT_STAMP(3, j, 4);
       }
     }
   } else {
@@ -586,6 +667,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t dkey = E::drop(p) ? drop_key(*p.drop.seed, p.drop.site) : 0u;
     int j = 0;
     for (int w = first_work; w < p.total_work; w += work_step, ++j) {
+#ifdef GPV_GEMM_TRACE
+      const int trole = warp == kEpiWarp0 ? 4 : (warp == kEpiWarp0 + kEpiWarps - 1 ? 5 : -1);
+#define GT_EPI(slot) do { if (trole >= 0 && lane == 0) GT_STAMP(trole, j, slot); } while (0)
+#else
+#define GT_EPI(slot) do { } while (0)
+#endif
+      GT_EPI(0);
       Work wk = decode_work(p, w);
       if constexpr (PAIR) wk.mt = 2 * wk.mt + rank;
       const int n0 = wk.nt * BN, bz = wk.bz;
@@ -633,8 +721,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c = 1; c < kChunksPerHalf; ++c) issue(c);
         }
       }
+      GT_EPI(1);
       mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
+      GT_EPI(2);
 #pragma unroll
       for (int c = 0; c < kChunksPerHalf; ++c) {
         const int nb = n0 + cbase + c * kChunk;
@@ -657,6 +747,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();           // ... and every other lane's
           }
           tmem_ld_wait();
+          if (c == kChunksPerHalf - 1) GT_EPI(3);
           const int nvalid = min(kChunk, p.N - nb);
           const bool full = nvalid == kChunk;
           if (coal && full) {                     // whole warp takes part (shared-memory slabs)
@@ -667,6 +758,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      GT_EPI(4);
       if (coal) {
         cp_async_wait<0>();
         __syncwarp();           // the slabs are free for the next work item
@@ -677,6 +769,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (PAIR) mbar_arrive_cluster(leader_smem_addr(smem_u32(&acc_empty[buf])));
         else mbar_arrive(&acc_empty[buf]);
       }
+      GT_EPI(5);
     }
   }
 
@@ -849,7 +942,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& k
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kThreadsBN<BN>);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -911,6 +1004,14 @@ using namespace gpv;
 
 extern "C" size_t gpvb200_gemm_desc_size(void) { return sizeof(gpvb200_gemm_desc); }
 
+#ifdef GPV_GEMM_TRACE
+/* developer hook of the trace build only (tools/trace_gemm.py): device buffer [6][96][8] int64 that CTA 0 fills; NULL = off */
+extern "C" int gpvb200_gemm_trace(void* buf) {
+  long long* b = (long long*)buf;
+  return cudaMemcpyToSymbol(gpv::g_gemm_trace, &b, sizeof(b)) == cudaSuccess ? GPV_OK : GPV_ERR_CUDA;
+}
+#endif
+
 static long long g_pair_launches = 0;   // statistics only (tests assert that the pair variant really ran)
 extern "C" int64_t gpvb200_gemm_pair_launches(void) { return (int64_t)g_pair_launches; }
 
@@ -970,11 +1071,11 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
     static int nprod = -1;   // GPVB200_PRODUCERS=1 reproduces the single-producer kernel (A/B measurements)
     if (nprod < 0) {
       const char* e = getenv("GPVB200_PRODUCERS");
-      nprod = e ? atoi(e) : kProducers;
+      nprod = e ? atoi(e) : kProducers + kExtraProducers;
       if (nprod < 1) nprod = 1;
-      if (nprod > kProducers) nprod = kProducers;
+      if (nprod > kProducers + kExtraProducers) nprod = kProducers + kExtraProducers;
     }
-    kp.nprod = nprod;
+    kp.nprod = nprod;   // clamped to the producer warps of the chosen tile width below
   }
   kp.drop_mode = 0;
   if (d->drop_mode != 0 && d->drop_p > 0.f) {
@@ -1236,10 +1337,23 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   const uint32_t stage = a_bytes + b_bytes;
   const uint32_t epi_smem = kEpiWarps * kp.epi_warp_bytes + 128;     // 16 / 32 / 64 KB of epilogue slabs
   int nst = (int)((227u * 1024u - 1024u - 256u - epi_smem) / stage);
-  if (nst > 6) nst = 6;
+  if (nst > (BN == 64 ? 8 : 6)) nst = BN == 64 ? 8 : 6;
   GPV_REQUIRE(nst >= 2, "gemm: stage of %u bytes does not fit twice in shared memory", stage);
   kp.nstages = nst;
   const size_t smem = (size_t)nst * stage + 1024 /*alignment slack*/ + (2 * nst + 4) * 8 + 32 + epi_smem;
+
+  if (kp.nprod > (BN == 64 ? kProducers + kExtraProducers : kProducers)) kp.nprod = BN == 64 ? kProducers + kExtraProducers : kProducers;
+  // A producer waits on the PARITY of a slot's empty barrier, which tells the current phase from the previous one only: the warp that
+  // fills stage use g has passed the wait of use g - nprod, i.e. uses up to g - nprod - nst are consumed, and needs use g - 2 nst
+  // consumed for its parity test to be unambiguous -> nprod <= nst.
+  if (kp.nprod > nst) kp.nprod = nst;
+  kp.fd_nt = make_fastdiv(kp.n_tiles);
+  kp.fd_mt = make_fastdiv(kp.m_tiles);
+  kp.fd_gy = make_fastdiv(kp.gy);
+  kp.fd_tpi = make_fastdiv(kp.mode == 0 ? 1 : kp.tiles_h * kp.tiles_w);
+  kp.fd_tws = make_fastdiv(kp.mode == 0 ? 1 : kp.tiles_w);
+  kp.fd_tw = make_fastdiv(kp.mode == 0 ? 1 : kp.tw);
+  kp.fd_kc = make_fastdiv(kp.mode == 1 ? kp.kc_per_tap : 1);
 
   cudaStream_t st = (cudaStream_t)stream;
   int f = -1;

@@ -1,0 +1,10 @@
+#!/bin/bash
+out=gpurun_out; mkdir -p $out
+timeout 300 python tools/trace_gemm.py stem l1.conv2 l1.conv1.k64 l1.conv1.k256 l3.conv1 > $out/r4b_trace_gemm.txt 2>&1; echo "trace exit $?"; grep "==\|steady" $out/r4b_trace_gemm.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $out/r4b_pytest.log 2>&1; echo "pytest exit $?"; tail -3 $out/r4b_pytest.log
+timeout 600 python bench.py --no-extras --no-cpu-baseline --steps 30 > $out/r4b_bench.json 2> $out/r4b_bench.err; echo "bench exit $?"
+python - <<PY
+import json
+d=json.load(open("$out/r4b_bench.json"))
+print(d["ms_per_step"], d["value"], d["e2e"]["value"])
+PY

@@ -65,6 +65,7 @@ struct KParams {
   int OH, OW, os, ooh, oow;
   int act, aux_mode, d_fp32, d_atomic, vec_ok, res_fp32, coal, pf_mode, max_ctas;
   uint32_t epi_warp_bytes, epi_aux_off, epi_slot_stride;   // per-warp epilogue slabs (coalesced path)
+  int b_res;      // 1: the whole K-major B operand of the (single) column tile stays in shared memory, stages carry A only
   int nprod;      // producer warps in use (1..kProducers; GPVB200_PRODUCERS, default kProducers)
   int drop_mode;  // 0 none, 1 before the residual add, 2 after the activation (DropArgs below)
   DropArgs drop;
@@ -400,21 +401,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int first_work = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int work_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int BNC = PAIR ? BN / 2 : BN;   // B columns this CTA stages
+  constexpr bool kAltEpi = BN == 64 && !PAIR;   // narrow tiles: the two epilogue warp groups take alternate work items
 
   // ---- shared memory carve-up ----------------------------------------------------------------------
   const int rowsA = (p.mode == 1) ? p.th * p.tw : BM;
   const uint32_t a_blk = 128u * 128u;                  // one 64-deep k-block of a K-major A tile (reserved; conv tiles may write less)
   const uint32_t b_blk = (uint32_t)BNC * 128u;         // one 64-deep k-block of a K-major B tile
   const uint32_t a_bytes = p.a_mn ? 2u * p.bk * 128u : (uint32_t)p.kblk * a_blk;  // reserved per stage
-  const uint32_t b_bytes = p.b_mn ? (uint32_t)(BNC / 64) * p.bk * 128u : (uint32_t)p.kblk * b_blk;
+  // Resident B (narrow forward convolutions: one column tile, <= 96 KB of weights): loaded once per CTA in front of the stage ring;
+  // a 24 KB stage becomes 16 KB, and these launches are bound by the chip-wide L2 -> SM rate (~43 B/clk per SM with every SM pulling).
+  const uint32_t b_res_bytes = p.b_res ? (uint32_t)p.kb_total * b_blk : 0u;
+  const uint32_t b_bytes = p.b_res ? 0u : (p.b_mn ? (uint32_t)(BNC / 64) * p.bk * 128u : (uint32_t)p.kblk * b_blk);
   const uint32_t a_tx = p.a_mn ? a_bytes : (uint32_t)p.kblk * rowsA * 128u;    // bytes TMA actually writes
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int S = p.nstages;
+  uint8_t* const bres = smem;
+  smem += b_res_bytes;                                  // (a multiple of 8 KB: the stage ring stays 1024-byte aligned)
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)S * stage_bytes);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* acc_full = empty_bar + S;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  uint64_t* bres_bar = acc_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bres_bar + 1);
   // per epilogue warp: residual ring 2 x 2 KB (also the output transposition slab), aux ring 2 x 2 KB, bias slice 512 B
   const uint32_t stg_base = (smem_u32(tmem_slot + 4) + 127u) & ~127u;
   constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
@@ -428,8 +436,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], PAIR ? 2 * kEpiWarps : kEpiWarps);   // pair: the leader's barrier collects both CTAs' epilogue warps
+      // pair: the leader's barrier collects both CTAs' epilogue warps; BN = 64: one group of four warps per accumulator (see the epilogue)
+      mbar_init(&acc_empty[b], PAIR ? 2 * kEpiWarps : (kAltEpi ? kEpiWarps / 2 : kEpiWarps));
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
@@ -463,6 +473,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool pf_r = p.pf_mode && p.coal && p.residual != nullptr, pf_a = p.pf_mode && p.coal && p.aux_mode != GPVB200_AUX_NONE;
     int gi = 0;  // stage-use counter, runs across work items
     Ring rg = {0, 0u, 0};
+    if (p.b_res && pw == 0 && first_work < p.total_work) {
+      if (elect_one()) {
+        mbar_expect_tx(bres_bar, b_res_bytes);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          if (p.mode == 0) {
+            tma_load_4d(bres + (size_t)kb * b_blk, &tmB, bres_bar, kb * 64, 0, 0, 0);
+          } else {
+            const int tap = fdiv(kb, p.fd_kc), kc = kb - tap * p.kc_per_tap;
+            tma_load_4d(bres + (size_t)kb * b_blk, &tmB, bres_bar, kc * 64, 0, p.tap_w[tap], 0);
+          }
+        }
+      }
+      __syncwarp();
+    }
     for (int w = first_work; w < p.total_work; w += work_step) {
       Work wk = decode_work(p, w);
       if constexpr (PAIR) wk.mt = 2 * wk.mt + rank;   // may be one past the last tile: TMA zero-fills, the epilogue skips it
@@ -546,7 +570,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_4d(sa, &tmA, &full_bar[s], m0, k0, bz, 0);
               tma_load_4d(sa + p.bk * 128, &tmA, &full_bar[s], m0 + 64, k0, bz, 0);
             }
-            if (!p.b_mn) {
+            if (p.b_res) {
+            } else if (!p.b_mn) {
               tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, bzB, 0);
             } else {
 #pragma unroll
@@ -556,7 +581,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else if (p.mode == 1) {
             const int tap = fdiv(it, p.fd_kc), kc = it - tap * p.kc_per_tap;
             tma_load_4d(sa, &tmA, &full_bar[s], kc * 64, wo0 * p.stride + p.tap_dw[tap], ho0 * p.stride + p.tap_dh[tap], img);
-            if (!p.b_mn) {
+            if (p.b_res) {
+            } else if (!p.b_mn) {
               tma_load_4d(sb, &tmB, &full_bar[s], kc * 64, n0, p.tap_w[tap], 0);
             } else {
 #pragma unroll
@@ -598,60 +624,104 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ksteps = p.bk / 16;
     int gi = 0, j = 0;
     Ring rg = {0, 0u, 0};
-    for (int w = first_work; w < p.total_work && (!PAIR || rank == 0); w += work_step, ++j) {
+    if constexpr (!PAIR) {
+      // ONE elected thread runs the whole role loop (waits, MMAs, commits), and the operand descriptors advance by adding constants to
+      // a base descriptor.  Measured (tools/proto/mma_issue.cu, profiles/r4g_mma_issue.txt): electing per stage and rebuilding both
+      // descriptors per MMA costs the issuing warp 376 / 392 / 513 clocks per 64-deep stage at N = 64 / 128 / 256 whatever the tensor
+      // time (128 / 256 / 512); this form costs 219 / 260 / 511.  With the waits and fences on top, the per-stage chain of this warp
+      // (650-750 clocks for every tile width: clock64 timeline, profiles/r4f_trace_gemm.txt) was what bounded every main loop.
+      if (elect_one()) {
+        if (p.b_res) {
+          mbar_wait(bres_bar, 0u);
+          tc_fence_after();
+        }
+        const uint32_t stage0 = smem_u32(smem);
+        const uint64_t a_base = make_sdesc_sw128(stage0, a_lbo, 1024u), b_base = make_sdesc_sw128(stage0 + a_bytes, b_lbo, 1024u);
+        const uint64_t bres_base = make_sdesc_sw128(smem_u32(bres), 0u, 1024u);
+        const uint64_t sstep = stage_bytes >> 4, bres_step = b_blk >> 4;       // descriptor address units (16 bytes)
+        const uint64_t a_kd = a_kstep >> 4, b_kd = b_kstep >> 4;
+        for (int w = first_work; w < p.total_work; w += work_step, ++j) {
+          const Work wk = decode_work(p, w);
+          const int buf = j & 1;
+          GT_STAMP(3, j, 0);
+          mbar_wait(&acc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+          tc_fence_after();
+          GT_STAMP(3, j, 1);
+          const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+          uint32_t accum = 0u;                                         // the first MMA of an item overwrites the accumulator
+          for (int it = wk.it0; it < wk.it1; ++it, ++gi, ring_next(rg, S, 1)) {
+            const int s = rg.s;
+            mbar_wait(&full_bar[s], rg.ph);
+            tc_fence_after();
+            GT_STAMP(1, gi, 0);
+            if (it == wk.it0) GT_STAMP(3, j, 2);
+            if (it == wk.it1 - 1) GT_STAMP(3, j, 3);
+            uint64_t ad = a_base + (uint64_t)s * sstep;
+            uint64_t bd = p.b_res ? bres_base + (uint64_t)it * bres_step : b_base + (uint64_t)s * sstep;
+            if (ksteps == 4) {
+              umma_f16(tacc, ad, bd, idesc, accum);
+              umma_f16(tacc, ad + a_kd, bd + b_kd, idesc, 1u);
+              umma_f16(tacc, ad + 2 * a_kd, bd + 2 * b_kd, idesc, 1u);
+              umma_f16(tacc, ad + 3 * a_kd, bd + 3 * b_kd, idesc, 1u);
+            } else {
+              umma_f16(tacc, ad, bd, idesc, accum);
+              for (int k = 1; k < ksteps; ++k) {
+                ad += a_kd;
+                bd += b_kd;
+                umma_f16(tacc, ad, bd, idesc, 1u);
+              }
+            }
+            accum = 1u;
+            umma_commit(&empty_bar[s]);                         // frees the smem stage once these MMAs retire
+            if (it == wk.it1 - 1) umma_commit(&acc_full[buf]);  // accumulator complete
+            GT_STAMP(1, gi, 1);
+            if (it == wk.it1 - 1) GT_STAMP(3, j, 4);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+    for (int w = first_work; w < p.total_work && rank == 0; w += work_step, ++j) {
       const Work wk = decode_work(p, w);
       const int buf = j & 1;
-      if (lane == 0) GT_STAMP(3, j, 0);
       mbar_wait(&acc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) GT_STAMP(3, j, 1);
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
       for (int it = wk.it0; it < wk.it1; ++it, ++gi, ring_next(rg, S, 1)) {
         const int s = rg.s;
         const uint32_t ph = rg.ph;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0 && it == wk.it0) GT_STAMP(3, j, 2);
-        if (lane == 0 && it == wk.it1 - 1) GT_STAMP(3, j, 3);
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          if constexpr (PAIR) {
-            for (int k = 0; k < ksteps; ++k) {
-              // K-major operands: 64-deep k-blocks (4 steps of 32 bytes inside the 128-byte swizzle row), one after the other
-              const uint32_t ao = p.a_mn ? k * a_kstep : (uint32_t)(k >> 2) * a_blk + (uint32_t)(k & 3) * 32u;
-              const uint32_t bo = p.b_mn ? k * b_kstep : (uint32_t)(k >> 2) * b_blk + (uint32_t)(k & 3) * 32u;
-              const uint64_t ad = make_sdesc_sw128(sa + ao, a_lbo, 1024u);
-              const uint64_t bd = make_sdesc_sw128(sb + bo, b_lbo, 1024u);
-              umma_f16_pair(tacc, ad, bd, idesc, (it > wk.it0 || k > 0) ? 1u : 0u);
-            }
-          } else {
-            // the issue rate of this one thread bounds narrow tiles (a 128 x 64 x 16 MMA lasts 32 clocks): keep the loop minimal
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = make_sdesc_sw128(sa + k * a_kstep, a_lbo, 1024u);
-              const uint64_t bd = make_sdesc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-              umma_f16(tacc, ad, bd, idesc, (it > wk.it0 || k > 0) ? 1u : 0u);
-            }
+          for (int k = 0; k < ksteps; ++k) {
+            // K-major operands: 64-deep k-blocks (4 steps of 32 bytes inside the 128-byte swizzle row), one after the other
+            const uint32_t ao = p.a_mn ? k * a_kstep : (uint32_t)(k >> 2) * a_blk + (uint32_t)(k & 3) * 32u;
+            const uint32_t bo = p.b_mn ? k * b_kstep : (uint32_t)(k >> 2) * b_blk + (uint32_t)(k & 3) * 32u;
+            const uint64_t ad = make_sdesc_sw128(sa + ao, a_lbo, 1024u);
+            const uint64_t bd = make_sdesc_sw128(sb + bo, b_lbo, 1024u);
+            umma_f16_pair(tacc, ad, bd, idesc, (it > wk.it0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (PAIR) {
-            umma_commit_pair(&empty_bar[s]);                          // frees the stage in both CTAs
-            if (it == wk.it1 - 1) umma_commit_pair(&acc_full[buf]);   // both epilogues
-          } else {
-            umma_commit(&empty_bar[s]);                     // frees the smem stage once these MMAs retire
-            if (it == wk.it1 - 1) umma_commit(&acc_full[buf]);  // accumulator complete
-          }
+          umma_commit_pair(&empty_bar[s]);                          // frees the stage in both CTAs
+          if (it == wk.it1 - 1) umma_commit_pair(&acc_full[buf]);   // both epilogues
         }
         __syncwarp();
-        if (lane == 0 && it == wk.it1 - 1) GT_STAMP(3, j, 4);
       }
+    }
     }
   } else {
     // ================================================================== epilogue (warps kEpiWarp0 .. kEpiWarp0 + 7)
     typedef EpiFlags<F> E;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - kEpiWarp0) >> 2;       // which half of the BN columns
+    // BN >= 128: the two groups of four warps split the columns of every item.  BN = 64 (kAltEpi): a group takes every other work item
+    // whole -- its accumulator buffer is its own -- so two epilogues are in flight and each warp stores full 128-byte rows; the per-item
+    // epilogue chain of ~1700-2600 clocks (addressing, TMEM read, transposition, stores) bounded the 1- to 4-stage items of the
+    // frozen trunk prefix (clock64 timeline, profiles/r4c_trace_gemm.txt).
+    const int grp = (warp - kEpiWarp0) >> 2;
+    const int half = kAltEpi ? 0 : grp;             // which half of the BN columns
     const int r = q * 32 + lane;
-    constexpr int kChunksPerHalf = BN / 2 / kChunk;
+    constexpr int kChunksPerHalf = kAltEpi ? BN / kChunk : BN / 2 / kChunk;
     const int cbase = half * (BN / 2);
     const bool coal = F >= 0 || p.coal != 0;
     const uint32_t res_ring = stg_base + (uint32_t)(warp - kEpiWarp0) * p.epi_warp_bytes, aux_ring = res_ring + p.epi_aux_off;
@@ -665,8 +735,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 4; ++i) so.own[i] = 16u * slab_slot(lane, i);
     const long long ldd = p.ldd, ldr = p.ldr, lda = p.ldaux;
     const uint32_t dkey = E::drop(p) ? drop_key(*p.drop.seed, p.drop.site) : 0u;
-    int j = 0;
-    for (int w = first_work; w < p.total_work; w += work_step, ++j) {
+    const int jstep = kAltEpi ? 2 : 1;
+    int j = kAltEpi ? grp : 0;
+    for (int w = first_work + j * work_step; w < p.total_work; w += jstep * work_step, j += jstep) {
 #ifdef GPV_GEMM_TRACE
       const int trole = warp == kEpiWarp0 ? 4 : (warp == kEpiWarp0 + kEpiWarps - 1 ? 5 : -1);
 #define GT_EPI(slot) do { if (trole >= 0 && lane == 0) GT_STAMP(trole, j, slot); } while (0)
@@ -1323,7 +1394,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
   // through a slot of its own when there is none.
   {
     const int rings = (kp.coal && d->residual ? 1 : 0) + (kp.coal && d->aux_mode != GPVB200_AUX_NONE ? 1 : 0);
-    const int chunks = BN / 2 / kChunk;
+    const int chunks = (BN == 64 && !pair) ? BN / kChunk : BN / 2 / kChunk;   // slabs per epilogue warp and work item
     kp.epi_full = rings > 0 && kp.k_per_split <= 4 && rings * chunks <= 4 && !pair;   // pair items are deep-K by construction
     const int depth = kp.epi_full ? chunks : 2;
     kp.epi_warp_bytes = rings ? 2048u * depth * rings : 2048u;
@@ -1333,14 +1404,28 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
 
   // ---- pipeline depth ---------------------------------------------------------------------------------
   const uint32_t a_bytes = kp.a_mn ? 2u * kp.bk * 128u : (uint32_t)kp.kblk * 128u * 128u;
-  const uint32_t b_bytes = kp.b_mn ? (BNC / 64) * kp.bk * 128u : (uint32_t)kp.kblk * BNC * 128u;
+  uint32_t b_bytes = kp.b_mn ? (BNC / 64) * kp.bk * 128u : (uint32_t)kp.kblk * BNC * 128u;
+  // resident B: one column tile, K-major un-batched B, one split (every CTA walks whole contractions), at most 96 KB of weights
+  static int bres_on = -1;   // GPVB200_BRES=0 switches it off (A/B measurements)
+  if (bres_on < 0) {
+    const char* e = getenv("GPVB200_BRES");
+    bres_on = e ? atoi(e) : 1;
+  }
+  uint32_t b_res_bytes = 0;
+  kp.b_res = 0;
+  if (bres_on && !pair && kp.mode != 2 && !kp.a_mn && !kp.b_mn && !kp.b_batched && kp.n_tiles == 1 && kp.gy == 1 && kp.splits == 1 &&
+      kp.kblk == 1 && (uint32_t)kp.kb_total * BNC * 128u <= 96u * 1024u) {
+    kp.b_res = 1;
+    b_res_bytes = (uint32_t)kp.kb_total * BNC * 128u;
+    b_bytes = 0;
+  }
   const uint32_t stage = a_bytes + b_bytes;
   const uint32_t epi_smem = kEpiWarps * kp.epi_warp_bytes + 128;     // 16 / 32 / 64 KB of epilogue slabs
-  int nst = (int)((227u * 1024u - 1024u - 256u - epi_smem) / stage);
+  int nst = (int)((227u * 1024u - 1024u - 256u - epi_smem - b_res_bytes) / stage);
   if (nst > (BN == 64 ? 8 : 6)) nst = BN == 64 ? 8 : 6;
   GPV_REQUIRE(nst >= 2, "gemm: stage of %u bytes does not fit twice in shared memory", stage);
   kp.nstages = nst;
-  const size_t smem = (size_t)nst * stage + 1024 /*alignment slack*/ + (2 * nst + 4) * 8 + 32 + epi_smem;
+  const size_t smem = (size_t)nst * stage + b_res_bytes + 1024 /*alignment slack*/ + (2 * nst + 5) * 8 + 32 + epi_smem;
 
   if (kp.nprod > (BN == 64 ? kProducers + kExtraProducers : kProducers)) kp.nprod = BN == 64 ? kProducers + kExtraProducers : kProducers;
   // A producer waits on the PARITY of a slot's empty barrier, which tells the current phase from the previous one only: the warp that

@@ -66,6 +66,37 @@ def main(which):
         b = torch.randn(64, device=dev)
         return lambda: k.conv(xv, w, ksize=7, taps=k.STEM_TAPS, Ho=Ho, Wo=Wo, N=64, K=64, bias=b, act=k.ACT_RELU)
 
+    def conv3n(C, H, W, B=32):
+        x = torch.randn(B, H, W, C, device=dev).to(BF)
+        w = (torch.randn(9, C, C, device=dev) / (9 * C) ** 0.5).to(BF)
+        b = torch.randn(C, device=dev)
+        return lambda: k.conv(x, w, ksize=3, bias=b, act=k.ACT_RELU)
+
+    def dgrad3(C, H, W, B=32):
+        from gpv1_b200.convops import conv_dgrad
+        dy = torch.randn(B, H, W, C, device=dev).to(BF)
+        w = (torch.randn(9, C, C, device=dev) / (9 * C) ** 0.5).to(BF)
+        aux = torch.randn(B, H, W, C, device=dev).to(BF)
+        return lambda: conv_dgrad(dy, w, ksize=3, stride=1, in_hw=(H, W), aux=aux, aux_mode=k.AUX_RELU_MASK)
+
+    def wgrad3(C, H, W, B=32):
+        dy = torch.randn(B, H, W, C, device=dev).to(BF)
+        x = torch.randn(B, H, W, C, device=dev).to(BF)
+        dw = torch.zeros(9, C, C, device=dev)
+        return lambda: k.conv_wgrad(dy, x, dw, ksize=3)
+
+    def wgrad1(M, N, K):
+        dy = torch.randn(M, N, device=dev).to(BF)
+        x = torch.randn(M, K, device=dev).to(BF)
+        dw = torch.zeros(N, K, device=dev)
+        return lambda: k.linear_wgrad(dy, x, dw)
+
+    def lin_plain(M, N, K):
+        x = torch.randn(M, K, device=dev).to(BF)
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF)
+        b = torch.randn(N, device=dev)
+        return lambda: k.linear(x, w, b)
+
     shapes = {
         "l1.conv1.k256": lambda: lin(614400, 64, 256),
         "l1.conv1.k64": lambda: lin(614400, 64, 64),
@@ -73,6 +104,14 @@ def main(which):
         "l1.conv2": conv3,
         "stem": stem,
         "l3.conv1": lambda: lin(38400, 256, 1024),
+        "l2.conv2": lambda: conv3n(128, 60, 80),
+        "l3.conv2": lambda: conv3n(256, 30, 40),
+        "l3.conv2.dgrad": lambda: dgrad3(256, 30, 40),
+        "l3.conv2.wgrad": lambda: wgrad3(256, 30, 40),
+        "l3.conv3.wgrad": lambda: wgrad1(38400, 1024, 256),
+        "l2.conv1.wgrad": lambda: wgrad1(153600, 128, 512),
+        "enc.qk": lambda: lin_plain(9600, 512, 256),
+        "txt.qkv": lambda: lin_plain(640, 2304, 768),
     }
     for name in (which or list(shapes)):
         fn = shapes[name]()
@@ -100,9 +139,10 @@ def main(which):
         print(f"== {name}: {us:.1f} us per launch.  clocks of CTA 0 relative to its first stamp")
         print("   P[stage use] = [slot free, loads issued];  M[item] = [top, acc free, first stage landed, last stage landed, committed];"
               "  E / E'[item] = first / last epilogue warp [top, before acc wait, acc full, tmem read, stores issued, released]")
-        for g in range(40):
+        print("   stage use: producer [slot free, loads issued]   MMA warp [stage landed (seen), MMAs + commit issued]")
+        for g in range(16, 64):
             if int(t[0, g, 0]) > 0:
-                print(f"   P[{g}]", [rel(v) for v in t[0, g, :2]])
+                print(f"   use {g}: P", [rel(v) for v in t[0, g, :2]], " M", [rel(v) for v in t[1, g, :2]])
         for j in range(24):
             if int(t[3, j, 0]) <= 0:
                 break

@@ -15,6 +15,7 @@ from pinned host buffers with a device->host read of the loss every step.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -540,13 +541,15 @@ def main():
 
     host_ms = [0.0]
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()                                                # (the last step's deferred loss read, inside the timed region)
         host_ms[0] = 1e3 * (time.perf_counter() - t0) / steps      # host time to ENQUEUE one step (no sync inside)
         e1.record()
         barrier()
@@ -652,7 +655,28 @@ def main():
 
         for _ in range(2):
             step_e2e_u8_pf()
-        ms_e2e_u8_pf = timed(step_e2e_u8_pf, args.steps)
+        ms_e2e_u8_pf_sync = timed(step_e2e_u8_pf, args.steps)
+        note("e2e uint8 + prefetch (synchronous loss read) done")
+
+        # the same loop as gpv1_b200.train runs it: every step's loss is copied to pinned host memory behind the step and read
+        # one step late (data.LossReader), so the host enqueues step i+1 while step i computes; the last read is inside the region
+        from gpv1_b200.data import LossReader
+        reader = LossReader()
+        e2e_losses = []
+
+        def step_e2e_u8_pf_deferred():
+            imgs, q, tg = next(pf8)
+            loss = model(imgs, q, h_ans, tg)
+            loss.backward()
+            v = reader.push(loss)
+            if v is not None:
+                e2e_losses.append(v)
+
+        for _ in range(2):
+            step_e2e_u8_pf_deferred()
+        e2e_losses.clear()
+        ms_e2e_u8_pf = timed(step_e2e_u8_pf_deferred, args.steps, finish=lambda: e2e_losses.append(reader.flush()))
+        assert len(e2e_losses) == args.steps + 1 and all(math.isfinite(v) for v in e2e_losses), e2e_losses   # (+1: the warm-up's last step)
         note("e2e uint8 + prefetch done")
 
     # DDP check on hardware: after a step every rank must hold the same (averaged) gradient arena
@@ -834,9 +858,15 @@ def main():
                     if ms_e2e_u8_pf is None else
                     {"value": world * B * args.steps / (ms_e2e_u8_pf / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d - h_images.numel() * 3,
                      "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_u8_pf / args.steps,
-                     "what": "public API (GPV.forward + loss.backward + loss.item()) fed by data.DevicePrefetcher with the loader's raw format: every "
-                             "step copies one batch of pinned uint8 NHWC host pixels, token ids and targets to the device on the copy stream (under "
-                             "the previous step) and reads the loss back; ToTensor + Normalize are fused into the stem's read"}),
+                     "what": "the training loop of gpv1_b200.train: GPV.forward + loss.backward fed by data.DevicePrefetcher with the loader's raw "
+                             "format (every step copies one batch of pinned uint8 NHWC host pixels, token ids and targets to the device on the copy "
+                             "stream, under the previous step; ToTensor + Normalize are fused into the stem's read) and data.LossReader (every step's "
+                             "loss is copied to pinned host memory behind the step and read by the host one step late, the last one inside the timed "
+                             "region); e2e_sync_read is the same loop with loss.item() after every backward"}),
+            "e2e_sync_read": None if ms_e2e_u8_pf is None else {
+                "value": world * B * args.steps / (ms_e2e_u8_pf_sync / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e_u8_pf_sync / args.steps,
+                "h2d_bytes_per_step": h2d - h_images.numel() * 3, "d2h_bytes_per_step": 4,
+                "what": "uint8 + DevicePrefetcher with a synchronous loss.item() after every backward (the host enqueues the next step only then)"},
             "e2e_fp32_sync": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                               "what": "the same call on pinned fp32 NCHW host images copied synchronously inside the call (the reference's loop, train_distr.py:401)"},
             "e2e_prefetch": None if ms_e2e_pf is None else {

@@ -651,6 +651,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t accum = 0u;                                         // the first MMA of an item overwrites the accumulator
           for (int it = wk.it0; it < wk.it1; ++it, ++gi, ring_next(rg, S, 1)) {
             const int s = rg.s;
+            // (measured and not kept, profiles/r4k_mma_loop_switches.txt: dropping this per-stage fence, or testing the next stage's
+            // barrier before this stage's MMAs are issued, changes nothing / costs 1-5 % on the narrow shapes)
             mbar_wait(&full_bar[s], rg.ph);
             tc_fence_after();
             GT_STAMP(1, gi, 0);
@@ -1204,6 +1206,20 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
     const char* e = getenv("GPVB200_FORCE_BN");
     force_bn = e ? atoi(e) : 0;
   }
+  // per-k-iteration cost a + b * BN (us); GPVB200_TITER="a,b" overrides (developer sweeps)
+  static double titer_a = -1.0, titer_b = 0.0;
+  if (titer_a < 0.0) {
+    titer_a = 0.24;
+    titer_b = 0.0018;
+    const char* e = getenv("GPVB200_TITER");
+    if (e) {
+      double a_ = 0, b_ = 0;
+      if (sscanf(e, "%lf,%lf", &a_, &b_) == 2 && a_ >= 0.0) {
+        titer_a = a_;
+        titer_b = b_;
+      }
+    }
+  }
   {
     double best = 1e30;
     for (int bn = 64; bn <= bn_cap; bn *= 2) {
@@ -1216,7 +1232,7 @@ extern "C" int gpvb200_gemm(const gpvb200_gemm_desc* d, void* stream) {
         if (sp > k_iters_pre / min_kper) sp = k_iters_pre / min_kper;   // every split keeps at least min_kper k-iterations
         if (sp < 1) sp = 1;
       }
-      const double t_iter = 0.24 + 0.0018 * bn;          // 0.35 / 0.47 / 0.70 us
+      const double t_iter = titer_a + titer_b * bn;
       const double t_epi = (d->d_atomic ? 4.0 : 3.0) * bn / 256.0;
       const int kper = k_iters_pre > 0 ? (k_iters_pre + sp - 1) / sp : 8;
       const long long waves = (tiles * sp + num_sms() - 1) / num_sms();

@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 from .config import load_config
+from .data import LossReader
 from .model import GPV
 from .optim import ClipAdamW
 from .parallel import GradSync, broadcast_parameters
@@ -145,7 +146,8 @@ def train(cfg, data=None, vocab=None, vocab_embed=None, log=print):
     if data is None:
         data = SyntheticBatches(int(getattr(tr, "synthetic_iters", 8)), bs, 480, 640, model.vocab, seed=1000 + rank)
     total_steps = len(data) * epochs
-    loss_val = None
+    loss_val, prev_lr = None, 0.0
+    reader = LossReader()
     for epoch in range(last_epoch + 1, epochs):
         for it, (imgs, queries, targets) in enumerate(data):
             targets = [{k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
@@ -162,14 +164,23 @@ def train(cfg, data=None, vocab=None, vocab_embed=None, log=print):
                 else:
                     mult = multistep_multiplier(epoch, list(tr.lr_milestones), float(tr.lr_drop))
                 optimizer.step(lr_scale=mult)
-                if rank == 0 and step % int(tr.log_step) == 0:
-                    loss_val = total_loss.item()
-                    log(f"Epoch: {epoch} | Iter: {it} | Step: {step} |  LR: {optimizer.lrs[1] * mult:.3e} | total_loss: {round(loss_val, 4)}")
+                # the loss of every step reaches the host one step late (data.LossReader): the log line never drains the GPU queue
+                prev = reader.push(total_loss)
+                if prev is not None:
+                    loss_val = prev
+                    if rank == 0 and (step - 1) % int(tr.log_step) == 0:
+                        log(f"Epoch: {epoch} | Iter: {it} | Step: {step - 1} |  LR: {prev_lr:.3e} | total_loss: {round(loss_val, 4)}")
+                prev_lr = optimizer.lrs[1] * mult
             step += 1
         ckpt_dir = getattr(cfg, "ckpt_dir", None) or (os.path.join(str(cfg.exp_dir), "ckpts") if getattr(cfg, "exp_dir", None) else None)
         if rank == 0 and ckpt_dir:
             os.makedirs(ckpt_dir, exist_ok=True)
             save_checkpoint(os.path.join(ckpt_dir, "model.pth"), model, optimizer, epoch, step, lr_scale=mult if total_loss is not None else 1.0)
+    last = reader.flush()
+    if last is not None:
+        loss_val = last
+        if rank == 0 and (step - 1) % int(tr.log_step) == 0:
+            log(f"Step: {step - 1} |  LR: {prev_lr:.3e} | total_loss: {round(loss_val, 4)}")
     if world > 1:
         dist.barrier()
     return loss_val

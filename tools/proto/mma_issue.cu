@@ -8,18 +8,21 @@
 using namespace gpv;
 
 // variant: 0 = the kernel's loop (elect per stage, descriptors rebuilt per MMA); 1 = one elect around the whole loop, descriptors advanced
-// by adding constants to a base; 2 = as 1 with four stages (16 MMAs) unrolled per iteration
+// by adding constants to a base; 2 = as 1 with four stages (16 MMAs) unrolled per iteration; 3 = as 1 plus tcgen05.fence::after_thread_sync
+// per stage; 4 = as 1 plus an mbarrier try_wait (on a completed phase) per stage; 5 = as 1 plus both (the kernel's per-stage sequence)
 __global__ void __launch_bounds__(128, 1) issue_kernel(long long* out, int N, int stages, int commit_each, int nslots, int variant) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar[8], done;
+  __shared__ uint64_t bar[8], done, ready;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u + i;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
     mbar_init(&done, 1);
+    mbar_init(&ready, 1);
     fence_barrier_init();
+    mbar_arrive(&ready);    // phase 0 of `ready` is complete: a wait on parity 0 passes at once
   }
   if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
   fence_proxy_async();
@@ -36,10 +39,12 @@ __global__ void __launch_bounds__(128, 1) issue_kernel(long long* out, int N, in
         if (elect_one()) {
           const uint64_t a0 = make_sdesc_sw128(smem_u32(smem), 0, 1024), b0 = make_sdesc_sw128(smem_u32(smem) + 16384u, 0, 1024);
           const uint64_t sstep = stage_bytes >> 4;
-          if (variant == 1) {
+          if (variant == 1 || variant >= 3) {
 #pragma unroll 1
             for (int st = 0; st < stages; ++st) {
               const int s = st % nslots;
+              if (variant == 4 || variant == 5) mbar_wait(&ready, 0u);
+              if (variant == 3 || variant == 5) tc_fence_after();
               const uint64_t a = a0 + s * sstep, b = b0 + s * sstep;
               umma_f16(tm, a, b, idesc, st > 0 ? 1u : 0u);
               umma_f16(tm, a + 2, b + 2, idesc, 1u);
@@ -94,9 +99,9 @@ int main() {
   long long* d;
   cudaMalloc(&d, 64);
   cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int variant : {0, 1, 2})
+  for (int variant : {1, 3, 4, 5})
   for (int grid : {148})
-    for (int commit_each : {0, 1})
+    for (int commit_each : {1})
       for (int N : {32, 64, 128, 256}) {
         const int stages = 64, nslots = 4;
         issue_kernel<<<grid, 128, 200 * 1024>>>(d, N, stages, commit_each, nslots, variant);

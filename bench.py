@@ -858,7 +858,7 @@ def main():
                     if ms_e2e_u8_pf is None else
                     {"value": world * B * args.steps / (ms_e2e_u8_pf / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d - h_images.numel() * 3,
                      "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_u8_pf / args.steps,
-                     "what": "the training loop of gpv1_b200.train: GPV.forward + loss.backward fed by data.DevicePrefetcher with the loader's raw "
+                     "what": "the loop of gpv1_b200.train (step replayed from the captured graphs): GPV.forward + loss.backward fed by data.DevicePrefetcher with the loader's raw "
                              "format (every step copies one batch of pinned uint8 NHWC host pixels, token ids and targets to the device on the copy "
                              "stream, under the previous step; ToTensor + Normalize are fused into the stem's read) and data.LossReader (every step's "
                              "loss is copied to pinned host memory behind the step and read by the host one step late, the last one inside the timed "

@@ -30,21 +30,20 @@ class DevicePrefetcher:
             return
         s = self.slot
         self.slot ^= 1
-        if torch.is_tensor(images) and not images.is_cuda:
-            if self.buf[s] is None or self.buf[s].shape != images.shape or self.buf[s].dtype != images.dtype:
-                self.buf[s] = torch.empty(images.shape, dtype=images.dtype, device=self.dev)
-            src = self._pin(images)
-            self.stream.wait_stream(torch.cuda.current_stream(self.dev))   # the buffer's previous consumer has been enqueued
-            with torch.cuda.stream(self.stream):
-                self.buf[s].copy_(src, non_blocking=True)
-                if torch.is_tensor(queries):
-                    queries = self._pin(queries).to(self.dev, non_blocking=True)
-                targets = [{k: (self._pin(v).to(self.dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in t.items()}
-                           for t in targets]
-            images = self.buf[s]
-            keep = src
-        else:
-            keep = None
+        keep = None
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))   # the buffers' previous consumer has been enqueued
+        with torch.cuda.stream(self.stream):
+            if torch.is_tensor(images) and not images.is_cuda:
+                if self.buf[s] is None or self.buf[s].shape != images.shape or self.buf[s].dtype != images.dtype:
+                    self.buf[s] = torch.empty(images.shape, dtype=images.dtype, device=self.dev)
+                keep = self._pin(images)
+                self.buf[s].copy_(keep, non_blocking=True)
+                images = self.buf[s]
+            # (a list of differently sized images is passed through: GPV.forward pads and copies it itself)
+            if torch.is_tensor(queries):
+                queries = self._pin(queries).to(self.dev, non_blocking=True)
+            targets = [{k: (self._pin(v).to(self.dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in t.items()}
+                       for t in targets]
         ev = torch.cuda.Event()
         ev.record(self.stream)
         self.ready = (images, queries, targets, ev, keep)

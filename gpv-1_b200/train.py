@@ -11,7 +11,9 @@ freeze_detr_params for `frozen_epochs`, 136-140, 160-161, 322-323), checkpoints 
 optimizer / epoch / step (382-394) and resume from `training.ckpt` (262-285).
 
 What is replaced: DistributedDataParallel(find_unused_parameters=True) by parallel.GradSync (stage-bucketed NCCL
-all-reduce of the gradient arena, overlapped with backward) and clip + AdamW by optim.ClipAdamW (two launches).  This loop issues
+all-reduce of the gradient arena, overlapped with backward) and clip + AdamW by optim.ClipAdamW (two launches); the synchronous
+`imgs.to(gpu)` (401) by data.DevicePrefetcher (the next batch is copied on a copy stream under the current step) and the per-step
+`loss.item()` of the log line (433) by data.LossReader (every loss reaches the host one step late, the GPU queue never drains).  This loop issues
 the step's kernels eagerly (the multitask stream changes shape from batch to batch); `GPV.capture_step` replays a fixed-shape
 step as CUDA graphs (bench.py does, one capture per answer length).  A checkpoint is written at the end of every epoch when
 `ckpt_dir` or `exp_dir` is set.  Data sets, evaluation and visualisation are out of scope
@@ -27,7 +29,7 @@ import torch
 import torch.distributed as dist
 
 from .config import load_config
-from .data import LossReader
+from .data import DevicePrefetcher, LossReader
 from .model import GPV
 from .optim import ClipAdamW
 from .parallel import GradSync, broadcast_parameters
@@ -149,8 +151,8 @@ def train(cfg, data=None, vocab=None, vocab_embed=None, log=print):
     loss_val, prev_lr = None, 0.0
     reader = LossReader()
     for epoch in range(last_epoch + 1, epochs):
-        for it, (imgs, queries, targets) in enumerate(data):
-            targets = [{k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in t.items()} for t in targets]
+        # batches cross PCIe one step ahead on a copy stream (pinned staging buffers, device ping-pong buffers: data.DevicePrefetcher)
+        for it, (imgs, queries, targets) in enumerate(DevicePrefetcher(iter(data), dev)):
             model.train()
             _, answer_token_ids = model.encode_answers(targets)
             for i, t in enumerate(targets):

@@ -10,7 +10,11 @@ import torch
 
 
 class DevicePrefetcher:
-    def __init__(self, batches, device):
+    def __init__(self, batches, device, move_targets=False):
+        """move_targets=False leaves the per-sample target dicts on the host (pinned): GPV.forward packs them into ONE staging buffer
+        and one copy (HostTargets._stage_host), which is cheaper than 2-3 tiny tensors per sample moved here and re-assembled by
+        a dozen small device kernels in front of every step (0.6 ms per step at B = 32)."""
+        self.move_targets = move_targets
         self.it = iter(batches)
         self.dev = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -42,8 +46,9 @@ class DevicePrefetcher:
             # (a list of differently sized images is passed through: GPV.forward pads and copies it itself)
             if torch.is_tensor(queries):
                 queries = self._pin(queries).to(self.dev, non_blocking=True)
-            targets = [{k: (self._pin(v).to(self.dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in t.items()}
-                       for t in targets]
+            if self.move_targets:
+                targets = [{k: (self._pin(v).to(self.dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in t.items()}
+                           for t in targets]
         ev = torch.cuda.Event()
         ev.record(self.stream)
         self.ready = (images, queries, targets, ev, keep)

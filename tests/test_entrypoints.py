@@ -125,11 +125,12 @@ def test_device_prefetcher_yields_the_same_batches():
     for i in range(5):
         imgs = torch.randn(2, 3, 32, 48, generator=g)
         host.append((imgs, torch.randint(0, 100, (2, 6), generator=g), [{"task": "CocoVqa", "boxes": torch.rand(3, 4, generator=g)} for _ in range(2)]))
-    got = []
-    for imgs, q, tg in DevicePrefetcher(host, "cuda:0"):
-        assert imgs.is_cuda and q.is_cuda and tg[0]["boxes"].is_cuda and tg[0]["task"] == "CocoVqa"
-        got.append((imgs.clone(), q.clone(), tg[1]["boxes"].clone()))       # consumed on the compute stream, like a step would
-    torch.cuda.synchronize()
-    assert len(got) == 5
-    for (hi, hq, ht), (di, dq, db) in zip(host, got):
-        assert torch.equal(hi, di.cpu()) and torch.equal(hq, dq.cpu()) and torch.equal(ht[1]["boxes"], db.cpu())
+    for move in (True, False):      # targets moved here, or left on the host for GPV.forward's packed staging copy (the default)
+        got = []
+        for imgs, q, tg in DevicePrefetcher(host, "cuda:0", move_targets=move):
+            assert imgs.is_cuda and q.is_cuda and tg[0]["boxes"].is_cuda == move and tg[0]["task"] == "CocoVqa"
+            got.append((imgs.clone(), q.clone(), tg[1]["boxes"].clone()))       # consumed on the compute stream, like a step would
+        torch.cuda.synchronize()
+        assert len(got) == 5
+        for (hi, hq, ht), (di, dq, db) in zip(host, got):
+            assert torch.equal(hi, di.cpu()) and torch.equal(hq, dq.cpu()) and torch.equal(ht[1]["boxes"], db.cpu())

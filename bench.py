@@ -440,10 +440,9 @@ def measure_encoder_layer(model, B, dev, peak_tflops, reps=20):
 
 
 def lib_sha16():
-    import hashlib
-    from gpv1_b200 import _C
-    with open(_C.SO_PATH, "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()[:16]
+    """sha of the library's sources + nvcc flags (build.source_sha16): the .so's bytes differ between builds of the same code."""
+    from gpv1_b200 import build
+    return build.source_sha16()
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -784,12 +783,12 @@ def main():
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = gf_all * B / ms_step              # TFLOP/s per GPU: GFLOP/sample * samples / ms
     traffic = gemm_traffic = None
-    traffic_src = "null: no ncu DRAM-byte pass of THIS build of libgpvb200.so is committed (profiles/step_traffic.json carries the sha of the library it measured)"
+    traffic_src = "null: no ncu DRAM-byte pass of THIS build of libgpvb200.so is committed (profiles/step_traffic.json carries the source sha of the library it measured)"
     try:                                     # DRAM bytes from the committed ncu pass, used only when it measured this very library
         tj = json.load(open(os.path.join(ROOT, "profiles", "step_traffic.json")))
         if tj.get("lib_sha16") == lib_sha16():
             traffic, gemm_traffic = tj["dram_bytes_per_step"], tj["gemm_kernel"]["dram_bytes_per_launch"]
-            traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum of this build (profiles/step_traffic.json, lib_sha16 matches)"
+            traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum of this build (profiles/step_traffic.json: same csrc/ + include/ + nvcc flags)"
     except (OSError, KeyError, ValueError):
         pass
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1400 (of fallback)"

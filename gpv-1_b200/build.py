@@ -14,6 +14,19 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
 
 
+def source_sha16():
+    """Identity of the library's CODE: sha256 over csrc/*, include/*.h and the nvcc flags.  (The .so's own bytes differ from build to
+    build by ~90 bytes of embedded ids, so a file hash cannot tie a profile to a build.)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    files = sorted(glob.glob(os.path.join(CSRC, "*"))) + sorted(glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def _newer(a, b):
     return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 

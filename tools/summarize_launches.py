@@ -47,10 +47,11 @@ def main(path, as_json=False, traffic_out=None):
     if traffic_out:
         g = [r for r in step if "umma_gemm_kernel" in r["name"]]
         gus, gby = sum(r["us"] for r in g), sum(r["rd"] + r["wr"] for r in g)
-        import hashlib
         import os
-        so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpv-1_b200", "lib", "libgpvb200.so")
-        sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16] if os.path.exists(so) else None
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from gpv1_b200 import build
+        sha = build.source_sha16()              # csrc/ + include/ + nvcc flags: the code the launch list was taken from
         with open(traffic_out, "w") as f:
             json.dump({"lib_sha16": sha,        # bench.py reports `roofline.traffic` only when this is the library it is running
                        "source": f"{path}: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "

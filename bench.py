@@ -439,6 +439,15 @@ def measure_encoder_layer(model, B, dev, peak_tflops, reps=20):
     return out
 
 
+def _spread(xs):
+    """median / p10 / p90 of the K timed steps, from one CUDA event between consecutive steps on rank 0."""
+    if not xs:
+        return None
+    v = sorted(xs)
+    q = lambda f: v[min(len(v) - 1, max(0, int(round(f * (len(v) - 1)))))]
+    return {"median": q(0.5), "p10": q(0.1), "p90": q(0.9), "min": v[0], "max": v[-1], "n": len(v)}
+
+
 def lib_sha16():
     """sha of the library's sources + nvcc flags (build.source_sha16): the .so's bytes differ between builds of the same code."""
     from gpv1_b200 import build
@@ -540,13 +549,17 @@ def main():
 
     host_ms = [0.0]
 
-    def timed(fn, steps, finish=None):
+    def timed(fn, steps, finish=None, per_step=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [e0]
         e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+            if per_step is not None:                                # one event between steps: the spread of the K timed steps
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         if finish is not None:
             finish()                                                # (the last step's deferred loss read, inside the timed region)
         host_ms[0] = 1e3 * (time.perf_counter() - t0) / steps      # host time to ENQUEUE one step (no sync inside)
@@ -555,6 +568,8 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if per_step is not None:
+            per_step.extend(a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:]))
         return ms.item()
 
     note("captured" if graph_launches is not None else "eager")
@@ -566,7 +581,8 @@ def main():
     if rank == 0:
         sampler.start()
     n0 = lib.launches
-    ms = timed(step_resident, args.steps)
+    step_ms = []
+    ms = timed(step_resident, args.steps, per_step=step_ms)
     note("timed region done")
     launches = graph_launches if graph_launches is not None else (lib.launches - n0) // args.steps
     host_enqueue_ms = host_ms[0]
@@ -875,6 +891,7 @@ def main():
                 "value": world * B * args.steps / (ms_e2e_u8 / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e_u8 / args.steps,
                 "h2d_bytes_per_step": h2d - h_images.numel() * 3, "what": "e2e with uint8 NHWC host images, normalisation fused into the stem"},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
+            "step_ms": _spread(step_ms),
             "full_step": {"value": world * B * args.steps / (ms_full / 1e3), "unit": "samples/s", "ms_per_step": ms_full / args.steps,
                           "what": "fwd + bwd (+ all-reduce) + fused clip_grad_norm_/AdamW (2 launches over the gradient arena) + bf16 weight re-pack"},
             "roofline": roofline, "roofline_step": step_roofline, "attention_kernel": attention,

@@ -297,6 +297,7 @@ class GPV(nn.Module):
         self.grad_sync = None          # parallel.GradSync installs itself here
         self._captured = None          # model/graph.py:CapturedStep once capture_step() ran (the one forward() tries first)
         self._captures = []            # every CapturedStep kept by capture_step(..., add=True): one per batch shape
+        self.auto_capture = 0          # forward() captures up to this many batch shapes by itself (0: only explicit capture_step calls)
         self.inference_graphs = False  # True: greedy / beam inference of a repeated input shape replays one CUDA graph
         self._inf_graphs = {}
 
@@ -439,6 +440,11 @@ class GPV(nn.Module):
                 cap = next((c for c in self._captures if c.matches(images, qids, ans)), None)
                 if cap is not None:
                     self._captured = cap              # _run_backward replays the backward graphs of the step that ran forward
+            if (cap is None and self.auto_capture > len(self._captures) and mask is None and torch.is_grad_enabled()
+                    and all(not c.matches(images, qids, ans) for c in self._captures)):
+                # a batch shape seen for the first time (train.py sets auto_capture): record it, then replay it below and from now on
+                cap = self.capture_step(images, qids, ans, targets, add=True)
+                eng.train_mode = bool(self.training)
             if cap is not None and mask is None and torch.is_grad_enabled() and cap.matches(images, qids, ans):
                 loss = cap.forward(images, qids, ans, targets)
                 return None if loss is None else _Step.apply(self._anchor(), loss, self)

@@ -13,9 +13,11 @@ optimizer / epoch / step (382-394) and resume from `training.ckpt` (262-285).
 What is replaced: DistributedDataParallel(find_unused_parameters=True) by parallel.GradSync (stage-bucketed NCCL
 all-reduce of the gradient arena, overlapped with backward) and clip + AdamW by optim.ClipAdamW (two launches); the synchronous
 `imgs.to(gpu)` (401) by data.DevicePrefetcher (the next batch is copied on a copy stream under the current step) and the per-step
-`loss.item()` of the log line (433) by data.LossReader (every loss reaches the host one step late, the GPU queue never drains).  This loop issues
-the step's kernels eagerly (the multitask stream changes shape from batch to batch); `GPV.capture_step` replays a fixed-shape
-step as CUDA graphs (bench.py does, one capture per answer length).  A checkpoint is written at the end of every epoch when
+`loss.item()` of the log line (433) by data.LossReader (every loss reaches the host one step late, the GPU queue never drains).  The step
+is replayed from CUDA graphs: the multitask stream changes shape from batch to batch (answers are padded to the batch maximum), so
+the first `training.cuda_graphs` distinct batch shapes (image size, query length, answer length; default 4, each owns ~4 GB of saved
+activations at B = 32) are captured the first time they are seen (`GPV.auto_capture` -> `GPV.capture_step(add=True)`) and replayed
+afterwards; other shapes and mixed-size (padded) batches issue the step's ~1000 kernels eagerly.  A checkpoint is written at the end of every epoch when
 `ckpt_dir` or `exp_dir` is set.  Data sets, evaluation and visualisation are out of scope
 (SURVEY 8): `data` is any iterable of `(images, queries, targets)` batches as utils/detr_misc.py:collate_fn yields them;
 without one, a synthetic loader of the reference's batch shape is used so that the entry point runs stand-alone.
@@ -138,6 +140,7 @@ def train(cfg, data=None, vocab=None, vocab_embed=None, log=print):
     broadcast_parameters(model)
     if world > 1:
         GradSync(model)
+    model.auto_capture = int(getattr(tr, "cuda_graphs", 4))      # batch shapes replayed from CUDA graphs (0: eager launches only)
     optimizer = ClipAdamW.for_model(model, tr)
     last_epoch, step = -1, 0
     if tr.ckpt is not None:

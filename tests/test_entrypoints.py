@@ -78,12 +78,13 @@ def test_train_loop_two_phases_and_resume(tmp_path):
     ov = ["training.batch_size=2", "training.frozen_batch_size=2", "training.num_epochs=1", "training.frozen_epochs=1",
           "training.log_step=1", f"ckpt_dir={tmp_path}", "training.synthetic_iters=3"]
     vocab = ["__pad__", "__cls__", "__stop__", "__unk__"] + [f"w{i}" for i in range(60)]
-    logs = []
+    logs, built = [], []
     real_gpv = T.GPV
 
     def small_gpv(cfg_model, vocab=None, vocab_embed=None):
         m = real_gpv(cfg_model, vocab=vocab, vocab_embed=vocab_embed, seed=0)
         m.init_detr_params = [n for n, _ in m.named_parameters() if n.startswith("detr.transformer.")]   # as load_pretr_detr would
+        built.append(m)
         return m
 
     T.GPV = small_gpv
@@ -92,6 +93,8 @@ def test_train_loop_two_phases_and_resume(tmp_path):
     try:
         cfg = load_config(overrides=ov + ["training.freeze=True"])
         loss1 = T.train(cfg, vocab=vocab, log=logs.append)
+        # the loop replays CUDA graphs: every batch shape it met was captured on first sight (training.cuda_graphs = 4 shapes at most)
+        assert built[0].auto_capture == 4 and 1 <= len(built[0]._captures) <= 3 and all(c.launches_per_step > 0 for c in built[0]._captures)
         ck = torch.load(os.path.join(str(tmp_path), "model.pth"))
         assert any(k.startswith("module.detr.") for k in ck["model"]) and ck["epoch"] == 0 and ck["step"] == 3
         # the optimizer entry is torch.optim.AdamW's layout: index-keyed state in the reference's four-group parameter order

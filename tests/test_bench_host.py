@@ -216,3 +216,25 @@ def test_encode_answers_equals_reference_golden():
     assert max(len(r) for r in gold["cases"]["long"]["ids"]) == gold["max_text_len"]          # truncation was exercised
     unk = stub.word_to_idx["__unk__"]
     assert any(unk in r for r in gold["cases"]["mixed"]["ids"])                                 # and the OOV path
+
+
+def test_step_spread_and_source_hash():
+    """bench._spread (median / p10 / p90 of the timed steps) and build.source_sha16 (the identity bench.py uses to decide
+    whether profiles/step_traffic.json measured the library it is running: a hash of csrc/ + include/ + nvcc flags, not of the .so's
+    bytes, which differ between builds of the same code)."""
+    import bench
+    from gpv1_b200 import build
+    sp = bench._spread([float(i) for i in range(1, 21)])
+    assert sp["n"] == 20 and sp["min"] == 1.0 and sp["max"] == 20.0 and sp["p10"] <= sp["median"] <= sp["p90"]
+    assert sp["median"] in (10.0, 11.0) and sp["p10"] == 3.0 and sp["p90"] == 18.0
+    assert bench._spread([]) is None and bench._spread([2.5])["median"] == 2.5
+    a, b = build.source_sha16(), build.source_sha16()
+    assert a == b and len(a) == 16 and int(a, 16) >= 0
+    assert bench.lib_sha16() == a
+    flags = list(build.FLAGS)
+    try:
+        build.FLAGS.append("-DGPV_SOMETHING_ELSE")
+        assert build.source_sha16() != a                                  # the flags are part of the identity
+    finally:
+        build.FLAGS[:] = flags
+    assert build.source_sha16() == a

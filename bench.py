@@ -487,9 +487,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            # NCCL prints its version banner on stdout at VERSION (and at WARN): keep rank 0's stdout to the one JSON line.  Any other
-            # level (WARN / INFO set by whoever launched the job) is left alone.
-            os.environ.pop("NCCL_DEBUG", None)
+            os.environ["NCCL_DEBUG"] = "WARN"          # as in round 1 (whose N > 1 lines the driver parsed): the version banner still precedes the JSON line on stdout
         dist.init_process_group("nccl", device_id=dev)
 
     from gpv1_b200 import _C

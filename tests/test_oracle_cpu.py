@@ -1,6 +1,6 @@
 """CPU: the fp32 oracle (oracle/torch_oracle.py) against the REFERENCE's numbers committed under tests/golden/ (written by
 oracle/make_golden.py from the unmodified /root/reference modules).  This is what pins the checker the GPU parity tests
-rely on; it needs neither a GPU nor /root/reference."""
+rely on; it needs neither a GPU nor /root/reference (the last test, which re-runs the reference itself, skips without it)."""
 import json
 import os
 
@@ -126,3 +126,48 @@ def test_bert_key_padding_mask_changes_the_encoding(state):
         unmasked = TO.bert_forward(P2, ids2)
     assert torch.allclose(masked[0], unmasked[0], atol=1e-5)                  # the unpadded sample is unaffected
     assert (masked[1, :5] - unmasked[1, :5]).abs().max().item() > 1e-2         # real tokens of the padded sample see different keys
+
+
+def test_committed_fixture_regenerates_from_the_reference(tmp_path, monkeypatch):
+    """Where /root/reference is present (the build container; never the GPU box): run oracle/make_golden.py's `train_small` case
+    again on the UNMODIFIED reference modules and require the committed tests/golden/gpv_train_small.pt (to fp32 round-off) -- the state-dict
+    specs, the loss and its terms, the matcher indices, every output and the norm of all gradients.  Inside train_case the oracle is
+    also asserted against the reference it just ran (1e-4 outputs, 2e-3 gradients), so this one test pins both the fixtures and the
+    oracle to the reference itself."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("/root/reference is not present on this machine")
+    from oracle import make_golden as MG, torch_oracle as TO
+    torch.manual_seed(0)
+    model, _cfg = ref_harness.build_reference_gpv(V=MG.V, seed=0, eval_mode=True)
+    specs = MG.specs_from_model(model)
+    committed_specs = json.load(open(os.path.join(GOLD, "gpv_specs.json")))
+    assert committed_specs["V"] == MG.V and [[n, list(s), k] for n, s, k in specs] == committed_specs["specs"]
+    P = TO.make_state(specs, seed=0)
+    model.load_state_dict(P, strict=True)
+    model.eval()
+    monkeypatch.setattr(MG, "GOLD", str(tmp_path))
+    MG.train_case(model, P, "train_small", B=2, H=224, W=288, Tl=6, S=7, seed=11, tasks=["CocoCaptioning"])
+    new = torch.load(os.path.join(str(tmp_path), "gpv_train_small.pt"))
+    old = torch.load(os.path.join(GOLD, "gpv_train_small.pt"))
+
+    def same(a, b, what):
+        # bit-identical on the machine that wrote the fixture; another core count may change the summation order of the fp32
+        # convolutions by a few 1e-6 (measured with 3 threads), hence the round-off allowance, 5x below the oracle-vs-reference tolerance
+        a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+        assert a.shape == b.shape and (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item()), what
+
+    same(new["loss"], old["loss"], "loss")
+    assert set(new["losses"]) == set(old["losses"])
+    for k, v in old["losses"].items():
+        same(new["losses"][k], v, k)
+    assert len(new["indices"]) == len(old["indices"])
+    for (q, t), (oq, ot) in zip(new["indices"], old["indices"]):
+        assert torch.equal(q, oq) and torch.equal(t, ot)                     # integer work: exact
+    for k in ("pred_relevance_logits", "pred_boxes", "answer_logits", "detr_hs_sample"):
+        same(new[k], old[k], k)
+    assert new["grad_norm"].keys() == old["grad_norm"].keys() and len(old["grad_norm"]) == 396
+    for k, v in old["grad_norm"].items():
+        assert abs(new["grad_norm"][k] - v) <= 5e-4 * v + 2e-6, k            # (a few norms are ~1e-6: gradients that are zero up to round-off)
+    for k, v in old["grad_sample"].items():
+        assert (new["grad_sample"][k] - v).abs().max().item() <= 1e-3 * v.abs().max().item() + 2e-6, k

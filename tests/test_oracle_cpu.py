@@ -148,6 +148,12 @@ def test_committed_fixture_regenerates_from_the_reference(tmp_path, monkeypatch)
     model.eval()
     monkeypatch.setattr(MG, "GOLD", str(tmp_path))
     MG.train_case(model, P, "train_small", B=2, H=224, W=288, Tl=6, S=7, seed=11, tasks=["CocoCaptioning"])
+    # the decode loops on FRESH inputs (seeds no committed fixture uses): greedy_case / beam_case assert the oracle's ids, sequences and
+    # probabilities against the reference's GPV.forward(images, queries, None) / forward_beam_search they run (gpv.py:178-196, 256-362)
+    mtl = model.cfg.max_text_len
+    MG.greedy_case(model, P, "greedy_live", B=2, H=160, W=192, Tl=6, seed=113, max_text_len=6)
+    MG.beam_case(model, P, "beam_live", B=3, H=160, W=192, Tl=6, seed=114, K=4, max_text_len=5)
+    model.cfg.max_text_len = mtl
     new = torch.load(os.path.join(str(tmp_path), "gpv_train_small.pt"))
     old = torch.load(os.path.join(GOLD, "gpv_train_small.pt"))
 

@@ -33,3 +33,41 @@ def test_no_cpu_fallback_in_product_package():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_tensor_core_kernels_are_tcgen05_tma_tmem_in_sass():
+    """Static proof of the hardware path (cuobjdump only, no GPU): every instantiation of the contraction kernel and of the
+    row-tile-resident sub-layer kernels issues tcgen05.mma (UTCHMMA), stages its operands with TMA (UTMALDG), reads its accumulators
+    out of tensor memory (LDTM) and contains no warp-level mma.sync (HMMA); the kernels that still run on mma.sync are exactly the
+    attention kernels DESIGN.md section 6 names."""
+    import shutil
+    import subprocess
+    import pytest
+    import __graft_entry__ as g
+    g.build()
+    from gpv1_b200 import _C
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _C.SO_PATH], capture_output=True, text=True, check=True).stdout
+    counts, fn = {}, None
+    for line in sass.splitlines():
+        if "Function : " in line:
+            fn = line.split("Function : ")[1].strip()
+            counts[fn] = dict(UTCHMMA=0, UTMALDG=0, LDTM=0, HMMA=0)
+        elif fn is not None:
+            c = counts[fn]
+            if "UTCHMMA" in line:
+                c["UTCHMMA"] += 1
+            elif "HMMA" in line:
+                c["HMMA"] += 1
+            if "UTMALDG" in line:
+                c["UTMALDG"] += 1
+            if "LDTM" in line:
+                c["LDTM"] += 1
+    tc = {k: v for k, v in counts.items() if re.search(r"umma_gemm_kernel|attn_block_fwd_kernel|mlp_block_fwd_kernel|mlp_block_bwd_kernel", k)}
+    assert len([k for k in tc if "umma_gemm_kernel" in k]) >= 20 and any("attn_block_fwd" in k for k in tc) and any("mlp_block_fwd" in k for k in tc)
+    for k, v in tc.items():
+        assert v["UTCHMMA"] > 0 and v["UTMALDG"] > 0 and v["LDTM"] > 0 and v["HMMA"] == 0, (k, v)
+    hmma = sorted({re.sub(r"^_ZN3gpv\d+", "", k).split("ILi")[0].split("ILb")[0] for k, v in counts.items() if v["HMMA"] > 0})
+    assert set(hmma) == {"attn_fwd_kernel", "attn_bwd_kernel"}, hmma
